@@ -1,0 +1,217 @@
+/*
+ * pia_b200.h -- C ABI of libpia_b200.so: the B200 (sm_100a) draft -> verify -> accept hot loop of
+ * PIA LOOKAHEAD.
+ *
+ * The reference path has no FFI: it is plain Python.  This ABI therefore sits *below* the
+ * Python surface the package keeps (LookaheadCache, lookahead_generation, the per-model forward) and
+ * each entry point names the reference code whose work it takes over (paths relative to
+ * /root/reference/lookahead/lookahead/).  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every function returns PIA_OK (0) or a negative pia_status; pia_last_error() gives the text
+ *     (thread local).  Nothing here allocates caller-visible memory: all `d_*` pointers are
+ *     caller-owned DEVICE buffers, all `h_*` pointers are HOST buffers; `stream` is a cudaStream_t
+ *     passed as void*.  Calls are asynchronous on `stream` unless stated otherwise and are legal
+ *     inside CUDA-graph capture unless stated otherwise.
+ *   - token ids are int32; attention masks are bit rows: row i of a draft of n <= 64*W nodes is W
+ *     uint64 words, bit j set <=> node i attends draft node j (i.e. j is i or an ancestor of i).
+ */
+#ifndef PIA_B200_H_
+#define PIA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIA_ABI_VERSION 1
+
+typedef enum {
+  PIA_OK = 0,
+  PIA_ERR_INVALID = -1,   /* bad argument (python: AssertionError / ValueError)                     */
+  PIA_ERR_INDEX = -2,     /* python IndexError of Tree.get (k-th largest beyond the collected list) */
+  PIA_ERR_CAPACITY = -3,  /* node / edge / frontier pool exhausted                                   */
+  PIA_ERR_CUDA = -4,      /* CUDA runtime error, see pia_last_error()                                */
+  PIA_ERR_UNSUPPORTED = -5
+} pia_status;
+
+const char *pia_last_error(void);
+int pia_abi_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches claim) */
+unsigned long long pia_launch_count(void);
+
+/* ============================================================================================
+ * Trie draft cache   (common/lookahead_cache.py: Tree :24-333, LookaheadCache :336-587)
+ * ============================================================================================ */
+typedef struct pia_trie pia_trie_t;
+
+enum { PIA_MODE_INPUT = 0, PIA_MODE_OUTPUT = 1, PIA_MODE_MIX = 2 };
+enum { PIA_GET_HIER = 0, PIA_GET_ONE = 1 };
+/* pia_trie_get flags */
+enum {
+  PIA_GET_TAIL = 1,      /* d_queries is one growing token sequence per row; the query is its last
+                            min(max_query_length, len) tokens (pretrained_model.py:708) */
+  PIA_GET_FIRST_ONLY = 2 /* consult only the tree of the first query token: Tree.get(token_ids[1:]) (:65) */
+};
+
+typedef struct {
+  int32_t vocab_capacity;      /* token ids must be in [0, vocab_capacity)                          */
+  int64_t node_capacity;       /* 32-byte node records                                              */
+  int64_t edge_capacity;       /* 8-byte (token,node) child entries                                 */
+  int32_t n_input_slots;       /* distinct request `idx` values (>=1; bs=1 loop uses idx 0)         */
+  int32_t max_node;            /* Tree.max_node          (lookahead_cache.py:337, default 65536)    */
+  int32_t max_output_node;     /* Tree.max_output_node   (default 512)                              */
+  int32_t max_put_tokens;      /* longest token list of one put/stream_put call                     */
+  int32_t frontier_capacity;   /* BFS frontier entries per resident query CTA                       */
+  int32_t max_resident_queries;/* query CTAs resident at once (scratch is sized for this many)      */
+} pia_trie_config_t;
+
+typedef struct {
+  int64_t nodes_used, edges_used;
+  int32_t n_trees;
+  int32_t n_update_trees;       /* len(_update_trees)       */
+  int32_t n_update_input_trees; /* len(_update_input_trees) */
+  int32_t error_flags;          /* sticky device-side PIA_ERR_CAPACITY indicators */
+  int64_t nodes_visited;        /* cumulative node records read by get kernels (roofline accounting) */
+  int64_t edges_visited;
+} pia_trie_stats_t;
+
+/* LookaheadCache.__init__ (lookahead_cache.py:337-347). Synchronous; not capturable. */
+int pia_trie_create(const pia_trie_config_t *cfg, pia_trie_t **out);
+int pia_trie_destroy(pia_trie_t *t);
+/* eos_ids / stop_words attributes (written by callers: pretrained_model.py:1088-1089). Synchronous. */
+int pia_trie_set_eos(pia_trie_t *t, const int32_t *h_eos, int n);
+int pia_trie_set_stop_words(pia_trie_t *t, const int32_t *h_words, int n);
+int pia_trie_set_limits(pia_trie_t *t, int max_node, int max_output_node);
+
+/* LookaheadCache.put (lookahead_cache.py:349-373).  d_tokens[n]; if d_n != NULL the live length is
+ * min(*d_n, n) read on the device.  mode PIA_MODE_INPUT needs 0 <= idx < n_input_slots.
+ * final != 0 runs reset_input_freqs(idx) + squeeze_branch_counts() afterwards (:371-373). */
+int pia_trie_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n, int branch_length, int mode,
+                 int idx, int final, void *stream);
+/* Tree.put (lookahead_cache.py:33-63) on the tree keyed by `tree_token` alone (created when absent). */
+int pia_trie_tree_put(pia_trie_t *t, int tree_token, const int32_t *d_tokens, int n, int mode, int idx, void *stream);
+/* LookaheadCache.stream_put (lookahead_cache.py:375-406); the per-idx carry buffer lives on the device. */
+int pia_trie_stream_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n, int branch_length, int idx,
+                        int final, void *stream);
+
+/* LookaheadCache.hier_get / one_get -> Tree.get / get_one_branch (lookahead_cache.py:408-439, 490-517,
+ * 65-144, 171-222), `batch` independent queries in one launch.
+ *   d_queries : [batch, q_stride] int32;  d_qlen : [batch] valid tokens per row
+ *   d_idx     : [batch] request idx per row, or NULL -> `idx` for all rows
+ *   max_seq_length > 0 (PIA_GET_TAIL only): branch_length is clamped on the device to
+ *               min(branch_length, max_seq_length - len - 1)   (pretrained_model.py:680)
+ * outputs (per row b):
+ *   d_out_ids  [batch, decoding_length] ; d_out_mask [batch, decoding_length, W], W = ceil(decoding_length/64)
+ *   d_out_n    [batch] number of nodes incl. the root (>= 1 unless the query was empty)
+ *   d_out_sizes[batch, 2] ; d_out_nsizes[batch] length of python's `sizes` list (0, 1 or 2)
+ *   d_status   [batch] PIA_OK or PIA_ERR_INDEX / PIA_ERR_CAPACITY for that row */
+int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32_t *d_qlen, int batch, int q_stride,
+                 int max_query_length, const int32_t *d_idx, int idx, int decoding_length, int branch_length,
+                 int min_input_size, int min_output_size, int mode, int kind, int flags, int max_seq_length,
+                 int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n, int32_t *d_out_sizes,
+                 int32_t *d_out_nsizes, int32_t *d_status, void *stream);
+
+/* reset_input_freqs :566-570 ; squeeze_branch_counts :572-576 ; fresh :563-564 */
+int pia_trie_reset_input_freqs(pia_trie_t *t, int idx, void *stream);
+int pia_trie_squeeze_branch_counts(pia_trie_t *t, void *stream);
+int pia_trie_fresh(pia_trie_t *t, void *stream);
+/* Synchronises `stream`. */
+int pia_trie_stats(pia_trie_t *t, pia_trie_stats_t *h_out, void *stream);
+/* per-tree counters Tree.n_node / n_output_node (lookahead_cache.py:29-30); -1 when the tree is absent. Synchronous. */
+int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_node, int64_t *h_n_output_node, void *stream);
+
+/* ============================================================================================
+ * Tree-masked attention (verify forward)
+ *   models/llama/modeling_llama.py:584-588 (mask -> positions) and :243-308 (eager attention);
+ *   mistral/modeling_mistral.py:979-982,241-320; pretrained_model.py:725-734 (mask builder).
+ * The [n, P+n] 0/1 mask is never materialised: prefix columns [pad_len, P) are visible to every
+ * row, the last n columns follow the per-row ancestor bit mask.
+ * ============================================================================================ */
+typedef struct pia_attn_plan pia_attn_plan_t;
+
+typedef struct {
+  int32_t n_q_heads, n_kv_heads, head_dim; /* head_dim 128 or 64                                     */
+  int32_t max_seq;                         /* rows of the KV cache (max_length + decoding_length + 1) */
+  int32_t max_nodes;                       /* 64 (W=1) or 128 (W=2)                                  */
+  int32_t n_layers;
+  int32_t kv_split_max;                    /* upper bound of KV splits per head (0 = auto)            */
+} pia_attn_config_t;
+
+/* d_k_cache / d_v_cache : [n_layers, n_kv_heads, max_seq, head_dim] bf16, owned by the caller for the
+ * plan's lifetime (TMA descriptors are encoded over them). Synchronous; not capturable. */
+int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cache, void *d_v_cache, pia_attn_plan_t **out);
+int pia_attn_plan_destroy(pia_attn_plan_t *p);
+/* bytes of fp32 workspace the forward needs (split-KV partials) */
+int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p);
+
+/* One layer of tree attention over the cache (rows [0, P+n) must already hold K/V, RoPE applied).
+ *   d_q    : [max_nodes, n_q_heads, head_dim] bf16 (rows >= n ignored)
+ *   d_mask : [max_nodes, W] uint64 ancestor rows;  d_n : device int, number of draft nodes
+ *   d_prefix_len : device int P (tokens already in the cache before this step's nodes)
+ *   pad_len : left-pad columns [0, pad_len) are masked for every row (pretrained_model.py:1123-1131)
+ *   d_out  : [max_nodes, n_q_heads, head_dim] bf16
+ * softmax scale = 1/sqrt(head_dim) * `scale_mul` (1.0 for the reference models). */
+int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask, const int32_t *d_n,
+                      const int32_t *d_prefix_len, int pad_len, float scale_mul, void *d_out, void *d_workspace,
+                      void *stream);
+
+/* ============================================================================================
+ * Fused elementwise pieces of the verify forward (all bf16 I/O, fp32 math)
+ * ============================================================================================ */
+/* RMSNorm (modeling_llama.py:76-90): y = (w * (x * rsqrt(mean(x^2)+eps)).to(bf16)) ; rows x hidden.
+ * If d_residual_in != NULL: x <- x + residual_in first and the sum is written to d_residual_out. */
+int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows, int hidden,
+                void *d_residual_out, void *d_y, void *stream);
+/* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; positions = P - pad_len + depth
+ * = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection output).
+ * Writes q (rotated) to d_q_out [rows, Hq, D] and K (rotated) / V to cache rows P + i of `layer`. */
+int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const int32_t *d_n,
+                       const int32_t *d_prefix_len, int pad_len, int rows, int n_q_heads, int n_kv_heads, int head_dim,
+                       float rope_theta, void *d_q_out, void *d_k_cache_layer, void *d_v_cache_layer, int max_seq,
+                       void *stream);
+/* SiLU(gate) * up (modeling_llama.py:185-186). d_gate_up : [rows, 2*inter] (gate | up) -> d_out [rows, inter] */
+int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *stream);
+/* embedding gather for the draft nodes: d_out[i] = table[d_ids[i]] (rows >= *d_n are zero filled) */
+int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden, void *d_out,
+                     void *stream);
+
+/* ============================================================================================
+ * Accept + KV compaction + sequence update
+ *   pretrained_model.py:764-892 (longest-prefix accept walk, greedy), :894-945 (KV compaction),
+ *   RepetitionPenaltyLogitsProcessor semantics of the installed transformers (call sites :786,:834).
+ * ============================================================================================ */
+typedef struct {
+  int32_t vocab;               /* logits row length                                              */
+  int32_t max_nodes;
+  float repetition_penalty;    /* 1.0 = none                                                     */
+  int32_t n_eos; int32_t eos[8];
+  int32_t max_length;          /* generation stops when seq_len >= max_length (MaxLengthCriteria) */
+} pia_accept_config_t;
+
+/* Row arg-max of the (penalised) logits of every draft node, then the walk of :827-860.
+ *   d_logits : [max_nodes, vocab] bf16 ; d_ids/d_mask/d_n : the draft (as produced by pia_trie_get)
+ *   d_seq : [seq_capacity] int32 token sequence (prompt + generated), d_seq_len : its length; the
+ *           accepted tokens are appended and *d_seq_len advanced.
+ *   d_accept_tokens [max_nodes] accepted tokens (draft matches + bonus); d_accept_count their number (edl)
+ *   d_accept_nodes  [max_nodes] draft node index whose logits produced each token (logit_indices :845)
+ *   d_prefix_len    : P, advanced to P + count on return
+ *   d_finished      : set to 1 when an eos was accepted or max_length reached (:1225-1231)          */
+int pia_accept(const pia_accept_config_t *cfg, const void *d_logits, const int32_t *d_ids, const uint64_t *d_mask,
+               int mask_words, const int32_t *d_n, int32_t *d_seq, int32_t *d_seq_len, int seq_capacity, int pad_len,
+               int32_t *d_accept_tokens, int32_t *d_accept_count, int32_t *d_accept_nodes, int32_t *d_prefix_len,
+               int32_t *d_finished, void *d_workspace, void *stream);
+int64_t pia_accept_workspace_bytes(const pia_accept_config_t *cfg);
+
+/* KV compaction (pretrained_model.py:863-875, 894-907) in place: cache row P_old + node -> row P_old + k for the
+ * k-th accepted draft node, all layers, K and V.  d_prefix_len is the value *after* pia_accept. */
+int pia_kv_compact(void *d_k_cache, void *d_v_cache, int n_layers, int n_kv_heads, int max_seq, int head_dim,
+                   const int32_t *d_accept_nodes, const int32_t *d_accept_count, const int32_t *d_prefix_len,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIA_B200_H_ */

@@ -1,0 +1,379 @@
+# -*- coding: utf-8 -*-
+"""LookaheadCache / Tree with the reference's method surface
+(/root/reference/lookahead/lookahead/common/lookahead_cache.py: Tree :24, LookaheadCache :336), backed by the
+GPU-resident trie of libpia_b200.so (csrc/trie.cu).  put/stream_put/hier_get/one_get run as CUDA kernels;
+par_get (:441-488) and bat_get (:519-561) are thin host compositions over the batched get kernel.
+
+Host-facing calls take Python lists and return ``(ids: list, mask: np.int64[n, n], sizes: list)`` exactly like
+the reference.  The generation loop does not use them: it calls the ``*_device`` methods, which read the query
+from the device-resident token sequence and leave the draft in HBM (no host round trip per step)."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+
+def _bits_to_mask(rows, n):
+    """uint64 bit rows [n, W] -> np.int64 [n, n]"""
+    rows = np.ascontiguousarray(rows[:n]).astype('<u8')
+    bits = np.unpackbits(rows.view(np.uint8).reshape(n, -1), axis=1, bitorder='little')
+    return bits[:, :n].astype(np.int64)
+
+
+class _DeviceTrie(object):
+    """owner of one pia_trie_t handle plus its small staging buffers"""
+
+    def __init__(self, device, eos_ids, stop_words, max_node, max_output_node, vocab_capacity, node_capacity,
+                 edge_capacity, n_input_slots, max_put_tokens, frontier_capacity, max_resident_queries):
+        if not torch.cuda.is_available():
+            raise RuntimeError('LookaheadCache needs a CUDA device (B200); there is no CPU fallback')
+        self.lib = L.load()
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        cfg = L.TrieConfig(vocab_capacity, node_capacity, edge_capacity, n_input_slots, max_node, max_output_node,
+                           max_put_tokens, frontier_capacity, max_resident_queries)
+        self.cfg = cfg
+        h = L.vp()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.pia_trie_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._out = {}
+
+    def close(self):
+        if getattr(self, 'h', None):
+            with torch.cuda.device(self.device):
+                self.lib.pia_trie_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def out_buffers(self, batch, dl):
+        key = (batch, dl)
+        if key not in self._out:
+            W = (dl + 63) // 64
+            dev = self.device
+            self._out[key] = dict(ids=torch.empty((batch, dl), dtype=torch.int32, device=dev),
+                                  mask=torch.empty((batch, dl, W), dtype=torch.int64, device=dev),
+                                  n=torch.empty((batch,), dtype=torch.int32, device=dev),
+                                  sizes=torch.empty((batch, 2), dtype=torch.int32, device=dev),
+                                  nsizes=torch.empty((batch,), dtype=torch.int32, device=dev),
+                                  status=torch.empty((batch,), dtype=torch.int32, device=dev))
+        return self._out[key]
+
+
+class LookaheadCache(object):
+    """Drop-in for lookahead.common.lookahead_cache.LookaheadCache (reference :336-587)."""
+
+    def __init__(self, debug=False, eos_ids=(2,), stop_words=None, max_node=65536, max_output_node=512, device=None,
+                 vocab_capacity=262144, node_capacity=1 << 24, edge_capacity=None, n_input_slots=8,
+                 max_put_tokens=16384, frontier_capacity=1 << 18, max_resident_queries=296):
+        self.debug = debug
+        self._t = _DeviceTrie(device, eos_ids, stop_words, max_node, max_output_node, vocab_capacity, node_capacity,
+                              edge_capacity if edge_capacity is not None else node_capacity, n_input_slots,
+                              max_put_tokens, frontier_capacity, max_resident_queries)
+        self._max_node, self._max_output_node = max_node, max_output_node
+        self._eos_ids = None
+        self._stop_words = None
+        self.eos_ids = eos_ids if eos_ids is not None else [None]
+        self.stop_words = stop_words if stop_words is not None else {}
+        self.default_mask = np.ones((1, 1), dtype=np.int64)
+
+    # ---- attributes the callers read/write (benchmark.py:270-273, pretrained_model.py:1088-1089)
+    @property
+    def device(self):
+        return self._t.device
+
+    @property
+    def eos_ids(self):
+        return self._eos_ids
+
+    @eos_ids.setter
+    def eos_ids(self, v):
+        v = list(v) if v is not None else [None]
+        if v == self._eos_ids:
+            return
+        ids = [int(e) for e in v if e is not None]
+        arr = (C.c_int32 * max(len(ids), 1))(*ids)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_set_eos(self._t.h, arr, len(ids)))
+        self._eos_ids = v
+
+    @property
+    def stop_words(self):
+        return self._stop_words
+
+    @stop_words.setter
+    def stop_words(self, v):
+        v = v if v is not None else {}
+        if self._stop_words is not None and set(v) == set(self._stop_words):
+            self._stop_words = v
+            return
+        ids = sorted(int(x) for x in v)
+        arr = (C.c_int32 * max(len(ids), 1))(*ids)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_set_stop_words(self._t.h, arr, len(ids)))
+        self._stop_words = v
+
+    @property
+    def max_node(self):
+        return self._max_node
+
+    @max_node.setter
+    def max_node(self, v):
+        self._max_node = int(v)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_set_limits(self._t.h, self._max_node, self._max_output_node))
+
+    @property
+    def max_output_node(self):
+        return self._max_output_node
+
+    @max_output_node.setter
+    def max_output_node(self, v):
+        self._max_output_node = int(v)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_set_limits(self._t.h, self._max_node, self._max_output_node))
+
+    # ---- helpers
+    def _tokens(self, token_ids):
+        n = len(token_ids)
+        t = torch.tensor(list(token_ids) if n else [0], dtype=torch.int32).pin_memory() if n > 64 else \
+            torch.tensor(list(token_ids) if n else [0], dtype=torch.int32)
+        return t.to(self._t.device, non_blocking=True), n
+
+    # ---- writes
+    def put(self, token_ids, branch_length=8, final=False, mode='output', idx=0):
+        """reference :349-373"""
+        assert mode in ('input', 'output')
+        d, n = self._tokens(token_ids)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_put(self._t.h, d.data_ptr(), n, None, branch_length, L.MODE[mode], idx,
+                                             int(final), self._t.stream()))
+
+    def stream_put(self, token_ids, branch_length=8, final=False, mode='output', idx=0):
+        """reference :375-406"""
+        assert mode == 'output' and idx >= 0
+        d, n = self._tokens(token_ids)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_stream_put(self._t.h, d.data_ptr(), n, None, branch_length, idx, int(final),
+                                                    self._t.stream()))
+
+    def put_device(self, d_tokens, n_max, d_n=None, branch_length=8, final=False, mode='output', idx=0):
+        """put() on tokens already in HBM (int32 tensor); the live length may itself be a device scalar"""
+        L.check(self._t.lib.pia_trie_put(self._t.h, d_tokens.data_ptr(), n_max,
+                                         d_n.data_ptr() if d_n is not None else None, branch_length, L.MODE[mode],
+                                         idx, int(final), self._t.stream()))
+
+    def stream_put_device(self, d_tokens, n_max, d_n=None, branch_length=8, final=False, idx=0):
+        L.check(self._t.lib.pia_trie_stream_put(self._t.h, d_tokens.data_ptr(), n_max,
+                                                d_n.data_ptr() if d_n is not None else None, branch_length, idx,
+                                                int(final), self._t.stream()))
+
+    # ---- reads
+    def _get_batch(self, queries, decoding_length, branch_length, min_input_size, min_output_size, mode, indices,
+                   kind, flags=0):
+        bs = len(queries)
+        stride = max(max(len(q) for q in queries), 1)
+        assert stride <= 16, 'query longer than 16 tokens'
+        host = np.zeros((bs, stride), dtype=np.int32)
+        qlen = np.zeros((bs,), dtype=np.int32)
+        for b, q in enumerate(queries):
+            host[b, :len(q)] = q
+            qlen[b] = len(q)
+        dev = self._t.device
+        dq = torch.from_numpy(host).to(dev)
+        dl = torch.from_numpy(qlen).to(dev)
+        didx = torch.tensor(list(indices), dtype=torch.int32, device=dev)
+        cap = max(decoding_length, 1)
+        o = self._t.out_buffers(bs, cap)
+        with torch.cuda.device(dev):
+            L.check(self._t.lib.pia_trie_get(self._t.h, dq.data_ptr(), dl.data_ptr(), bs, stride, stride,
+                                             didx.data_ptr(), 0, cap, branch_length, min_input_size, min_output_size,
+                                             L.MODE[mode], kind, flags, 0, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                             o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
+                                             o['status'].data_ptr(), self._t.stream()))
+        ids = o['ids'].cpu().numpy()
+        mask = o['mask'].cpu().numpy().view(np.uint64)
+        ns = o['n'].cpu().numpy()
+        sizes = o['sizes'].cpu().numpy()
+        nsizes = o['nsizes'].cpu().numpy()
+        status = o['status'].cpu().numpy()
+        out = []
+        for b in range(bs):
+            if status[b] != 0:
+                L.check(int(status[b]))
+            n = int(ns[b])
+            m = _bits_to_mask(mask[b], n) if n > 0 else self.default_mask
+            out.append((ids[b, :n].tolist(), m, sizes[b, :int(nsizes[b])].tolist()))
+        return out
+
+    def hier_get(self, token_ids, decoding_length=64, branch_length=8, min_input_size=0, min_output_size=0,
+                 mode='mix', idx=0):
+        """reference :408-439"""
+        assert mode in ('input', 'output', 'mix')
+        return self._get_batch([list(token_ids)], decoding_length, branch_length, min_input_size, min_output_size,
+                               mode, [idx], L.GET_HIER)[0]
+
+    def one_get(self, token_ids, decoding_length=64, branch_length=8, min_input_size=0, min_output_size=0,
+                mode='mix', idx=0):
+        """reference :490-517"""
+        assert mode in ('input', 'output', 'mix')
+        return self._get_batch([list(token_ids)], decoding_length, branch_length, min_input_size, min_output_size,
+                               mode, [idx], L.GET_ONE)[0]
+
+    def par_get(self, token_ids, decoding_length=16, branch_length=8, min_input_size=0, min_output_size=0,
+                mode='mix', idx=0):
+        """reference :441-488: re-express hier_get's tree as independent root-to-leaf branches"""
+        tree_ids, tree_mask, _ = self.hier_get(token_ids, decoding_length=decoding_length,
+                                               branch_length=branch_length, min_input_size=min_input_size,
+                                               min_output_size=min_output_size, mode=mode, idx=idx)
+        n_draft = len(tree_ids) - 1
+        paths = []
+        for row in range(n_draft, 0, -1):
+            anc = frozenset(np.flatnonzero(tree_mask[row, 1:]).tolist())
+            if not any(anc <= seen for seen in paths):
+                paths.append(anc)
+        paths.reverse()
+        used, ids, spans = 0, [tree_ids[0]], []
+        for anc in paths:
+            cols = sorted(anc)[:n_draft - used]
+            ids.extend(tree_ids[c + 1] for c in cols)
+            spans.append(len(cols))
+            used += len(cols)
+            if used >= n_draft:
+                break
+        masks = np.tril(np.ones((used + 1, used + 1)), 0)
+        at = 1
+        for span in spans:
+            masks[at:at + span, 1:at] = 0
+            at += span
+        return ids, masks, [at - 1]
+
+    def bat_get(self, token_id_list, decoding_length=64, branch_length=8, decoding_cursors=None, mode='output',
+                indices=None, decoding_mode='hier'):
+        """reference :519-561 -- all rows go to the GPU in ONE batched get launch"""
+        assert mode in ('input', 'output', 'mix')
+        assert decoding_mode in ('hier', 'one')
+        bs = len(token_id_list)
+        assert bs == len(decoding_cursors) and bs == len(indices), \
+            f'{bs=} {len(decoding_cursors)=} {len(indices)=}'
+        share = decoding_length // bs
+        rows = self._get_batch([list(q) for q in token_id_list], share, branch_length, 0, max(share // 2, 1), mode,
+                               indices, L.GET_HIER if decoding_mode == 'hier' else L.GET_ONE)
+        lo, hi = min(decoding_cursors), max(decoding_cursors)
+        widest = max(len(r[0]) for r in rows)
+        masks = np.zeros((bs, widest, hi - lo + widest), dtype=np.int64)
+        id_list, size_list = [], []
+        for b, (ids, m, sizes) in enumerate(rows):
+            k = len(ids)
+            shift = decoding_cursors[b] - lo
+            masks[b, :k, shift:shift + k] = m
+            masks[b, :, :shift + 1] = 1
+            id_list.append(ids + [0] * (widest - k))
+            size_list.append(sizes)
+        return id_list, masks, size_list
+
+    def get_device(self, d_seq, d_seq_len, decoding_length, branch_length, max_query_length=2, min_input_size=0,
+                   min_output_size=0, mode='mix', idx=0, kind='hier', max_seq_length=0, out=None):
+        """hier_get/one_get for the generation loop: the query is the tail of the device token sequence
+        (pretrained_model.py:708) and the draft stays in HBM. `out` is the dict of out_buffers(1, dl)."""
+        o = out if out is not None else self._t.out_buffers(1, max(decoding_length, 1))
+        L.check(self._t.lib.pia_trie_get(self._t.h, d_seq.data_ptr(), d_seq_len.data_ptr(), 1, d_seq.numel(),
+                                         max_query_length, None, idx, decoding_length, branch_length, min_input_size,
+                                         min_output_size, L.MODE[mode], L.GET_HIER if kind == 'hier' else L.GET_ONE,
+                                         L.GET_TAIL, max_seq_length, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                         o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
+                                         o['status'].data_ptr(), self._t.stream()))
+        return o
+
+    # ---- maintenance
+    def fresh(self):
+        """reference :563-564"""
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_fresh(self._t.h, self._t.stream()))
+
+    def reset_input_freqs(self, idx):
+        """reference :566-570"""
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_reset_input_freqs(self._t.h, idx, self._t.stream()))
+
+    def squeeze_branch_counts(self):
+        """reference :572-576"""
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_squeeze_branch_counts(self._t.h, self._t.stream()))
+
+    def stats(self):
+        s = L.TrieStats()
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_stats(self._t.h, C.byref(s), self._t.stream()))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def tree_counters(self, token_id):
+        a, b = C.c_int64(0), C.c_int64(0)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_tree_counters(self._t.h, int(token_id), C.byref(a), C.byref(b),
+                                                       self._t.stream()))
+        return a.value, b.value
+
+    def save_mem(self, save_dir):
+        raise NotImplementedError('trie persistence is SURVEY 8f-2 (next row); not built in this round')
+
+    def load_mem(self, load_dir):
+        raise NotImplementedError('trie persistence is SURVEY 8f-2 (next row); not built in this round')
+
+
+class Tree(object):
+    """Drop-in for the reference's Tree (:24-333) for callers/tests that build a single tree by hand.
+    Backed by a private one-tree device trie."""
+
+    def __init__(self, token_id, max_node=65536, max_output_node=512, device=None):
+        self.token_id = token_id
+        self.max_node = max_node
+        self.max_output_node = max_output_node
+        self._c = LookaheadCache(eos_ids=None, max_node=max_node, max_output_node=max_output_node, device=device,
+                                 node_capacity=1 << 20, max_resident_queries=4, frontier_capacity=1 << 16)
+
+    def put(self, token_ids, mode='output', idx=0, freq=1.0):
+        """reference :33-37"""
+        assert mode in ('input', 'output')
+        assert freq == 1.0, 'only unit increments exist on the reference path'
+        d, n = self._c._tokens(token_ids)
+        t = self._c._t
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_tree_put(t.h, int(self.token_id), d.data_ptr(), n, L.MODE[mode],
+                                            max(idx, 0), t.stream()))
+
+    def get(self, token_ids, max_size=64, max_length=8, min_input_size=0, min_output_size=0, output_weight=1e-4,
+            mode='mix', idx=0):
+        """reference :65-144"""
+        assert mode in ('input', 'output', 'mix')
+        assert output_weight == 1e-4, 'the kernels implement the reference default output_weight=1e-4'
+        return self._c._get_batch([[self.token_id] + list(token_ids)], max_size, max_length, min_input_size,
+                                  min_output_size, mode, [idx], L.GET_HIER, flags=L.GET_FIRST_ONLY)[0]
+
+    def get_one_branch(self, token_ids, max_length=8, mode='mix', idx=0):
+        """reference :171-222"""
+        return self._c._get_batch([[self.token_id] + list(token_ids)], 64, max_length, 0, 0, mode, [idx],
+                                  L.GET_ONE, flags=L.GET_FIRST_ONLY)[0]
+
+    def squeeze(self):
+        raise NotImplementedError('use LookaheadCache.squeeze_branch_counts()')
+
+    def reset_input_freq(self, idx):
+        raise NotImplementedError('use LookaheadCache.reset_input_freqs()')
+
+    @property
+    def n_node(self):
+        return self._c.tree_counters(self.token_id)[0]
+
+    @property
+    def n_output_node(self):
+        return self._c.tree_counters(self.token_id)[1]

@@ -1,0 +1,1218 @@
+// GPU-resident trie draft cache for PIA LOOKAHEAD (sm_100a).
+//
+// Takes over common/lookahead_cache.py of the reference (Tree :24-333, LookaheadCache :336-587): the
+// reference keeps one Python dict-of-dicts per first token; here the whole forest lives in HBM as
+//   * 32-byte node records (one DRAM sector each): {token, n_child, child, cap, fo(f64), fi(f32), aux}
+//   * 8-byte (token,node) child entries in insertion order for nodes with >= 2 children
+//     (a single child is stored inline, so n-gram chains cost one sector per node)
+//   * per-first-token root table, per-tree counters and the two "touched trees" lists.
+// Child ORDER is part of the contract: the reference sorts children by fm with Python's stable sort, so
+// ties fall back to dict insertion order (lookahead_cache.py:254-258); child lists therefore only ever
+// append, and squeeze compacts them in place.
+//
+// Frequencies: fo = freqs[-1] is an IEEE double exactly as in Python (squeeze halves it, :306-307);
+// fi = freqs[idx] only ever counts +1.0 and is reset to 0, so fp32 holds it exactly.  fm is evaluated
+// as (1-w)*fi + w*fo with two rounded multiplies and one rounded add (__dmul_rn/__dadd_rn, no FMA).
+//
+// Kernels: k_put_prepare / k_put_insert / k_put_finish (put, stream_put :349-406),
+//          k_get (hier_get / one_get -> Tree.get :65-144, 224-293, 171-222),
+//          k_reset_input (:320-333, 566-570), k_squeeze (:295-318, 572-576), k_fresh (:563-564).
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pia {
+namespace trie {
+
+struct __align__(32) Node {
+  int token;
+  int n_child;
+  int child;  // cap == 0: node id of the only child (n_child <= 1); cap > 0: offset of the child block
+  int cap;    // capacity of the child block in the edge pool (0 = inline)
+  double fo;
+  float fi;   // input slot 0
+  int aux;
+};
+static_assert(sizeof(Node) == 32, "node record must be one 32-byte sector");
+
+struct Hdr {
+  unsigned long long node_top, edge_top;
+  unsigned long long nodes_visited, edges_visited;
+  int n_trees, n_upd, n_updin, n_upd_stale;
+  int err;
+  int n_eos;
+  int eos[8];
+  int max_node, max_out;
+  int put_len, put_npos;
+};
+
+struct Dev {
+  Node *nodes;
+  int2 *edges;
+  float *fi_extra;  // [(n_slots-1), node_cap]
+  Hdr *hdr;
+  int *root_of, *tree_n_node, *tree_n_out, *tree_flags;
+  int *upd_list, *updin_list;
+  unsigned *stop_bits;
+  int *out_buf, *out_len;
+  int out_cap;
+  long long node_cap, edge_cap;
+  int vocab, n_slots;
+  int *frontier;
+  int fr_cap, max_resident;
+};
+
+constexpr int ERR_NODE_POOL = 1, ERR_EDGE_POOL = 2, ERR_FRONTIER = 4, ERR_OUTBUF = 8, ERR_HIST = 16, ERR_TOKEN = 32;
+constexpr int FLAG_UPD = 1, FLAG_UPDIN = 2;
+constexpr int NT = 256;  // threads per CTA of every trie kernel
+
+__device__ __forceinline__ float load_fi(const Dev &D, const Node &nd, int id, int idx) {
+  return idx == 0 ? nd.fi : D.fi_extra[(long long)(idx - 1) * D.node_cap + id];
+}
+__device__ __forceinline__ bool is_stop(const Dev &D, int tok) { return (D.stop_bits[tok >> 5] >> (tok & 31)) & 1u; }
+__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+// fm = (1-w)*fi + w*fo, IEEE double, no contraction (lookahead_cache.py:151, :254)
+__device__ __forceinline__ double mix_freq(double one_minus_w, double w, double fi, double fo) {
+  return __dadd_rn(__dmul_rn(one_minus_w, fi), __dmul_rn(w, fo));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// warp-cooperative child lookup: dict.get(token) on a node's children
+// ---------------------------------------------------------------------------------------------------
+__device__ int find_child(const Dev &D, const Node &p, int token) {
+  if (p.n_child == 0) return -1;
+  if (p.cap == 0) {
+    int c = p.child;
+    return D.nodes[c].token == token ? c : -1;
+  }
+  const int lane = lane_id();
+  for (int base = 0; base < p.n_child; base += 32) {
+    int i = base + lane;
+    int2 e = make_int2(-1, -1);
+    if (i < p.n_child) e = D.edges[p.child + i];
+    unsigned m = __ballot_sync(FULL, i < p.n_child && e.x == token);
+    if (m) return __shfl_sync(FULL, e.y, __ffs(m) - 1);
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// put / stream_put
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_put_prepare(Dev D, const int *tokens, int n, const int *d_n, int B,
+                                                    int is_stream, int final, int slot) {
+  __shared__ int s_cut;
+  const int tid = threadIdx.x;
+  int n_in = n;
+  if (d_n != nullptr) { int v = *d_n; n_in = v < n ? v : n; }
+  if (n_in < 0) n_in = 0;
+  if (tid == 0) s_cut = n_in;
+  __syncthreads();
+  // eos truncation: cut at the first occurrence of any eos id (lookahead_cache.py:350-352, 378-380)
+  const int n_eos = D.hdr->n_eos;
+  for (int i = tid; i < n_in; i += NT) {
+    int t = tokens[i];
+    bool hit = false;
+    for (int e = 0; e < n_eos; ++e) hit |= (t == D.hdr->eos[e]);
+    if (t < 0 || t >= D.vocab) { atomicOr(&D.hdr->err, ERR_TOKEN); hit = true; }
+    if (hit) atomicMin(&s_cut, i);
+  }
+  __syncthreads();
+  const int n_eff = s_cut;
+  if (is_stream) {
+    int *buf = D.out_buf + (long long)slot * D.out_cap;
+    int have = D.out_len[slot];
+    int room = D.out_cap - have;
+    int take = n_eff;
+    if (take > room) { take = room > 0 ? room : 0; if (tid == 0) atomicOr(&D.hdr->err, ERR_OUTBUF); }
+    for (int i = tid; i < take; i += NT) buf[have + i] = tokens[i];
+    __syncthreads();
+    if (tid == 0) {
+      int ts = have + take;
+      int min_bl = final ? 1 : B;
+      D.out_len[slot] = ts;
+      D.hdr->put_len = ts;
+      D.hdr->put_npos = ts > min_bl ? ts - min_bl : 0;
+    }
+  } else if (tid == 0) {
+    D.hdr->put_len = n_eff;
+    D.hdr->put_npos = n_eff >= 2 ? n_eff - 1 : 0;
+  }
+}
+
+// one warp: Tree.put of `path[0..len)` into the tree keyed by `key` (lookahead_cache.py:33-63)
+__device__ void warp_insert(const Dev &D, int key, const int *path, int len, bool out_mode, int idx) {
+  const int lane = lane_id();
+  int root = D.root_of[key];
+  if (root < 0) {
+    if (lane == 0) {
+      unsigned long long id = atomicAdd(&D.hdr->node_top, 1ull);
+      if (id >= (unsigned long long)D.node_cap) { atomicOr(&D.hdr->err, ERR_NODE_POOL); root = -1; }
+      else {
+        root = (int)id;
+        Node r; r.token = key; r.n_child = 0; r.child = -1; r.cap = 0; r.fo = 0.0; r.fi = 0.f; r.aux = 0;
+        D.nodes[root] = r;
+        D.root_of[key] = root;
+        D.tree_n_node[key] = 0; D.tree_n_out[key] = 0;
+        atomicAdd(&D.hdr->n_trees, 1);
+      }
+    }
+    root = __shfl_sync(FULL, root, 0);
+    if (root < 0) return;
+  }
+  __syncwarp();
+  int cur = root;
+  for (int j = 0; j < len; ++j) {
+    Node pn = D.nodes[cur];
+    const int tok = path[j];
+    int c = find_child(D, pn, tok);
+    if (c >= 0) {  // existing node: freqs[idx] += 1 (:53)
+      if (lane == 0) {
+        if (out_mode) D.nodes[c].fo += 1.0;
+        else if (idx == 0) D.nodes[c].fi += 1.0f;
+        else D.fi_extra[(long long)(idx - 1) * D.node_cap + c] += 1.0f;
+      }
+      __syncwarp();
+      cur = c;
+      continue;
+    }
+    // missing suffix: _pack a chain of r new nodes (:57-63) and hang it under `cur` as its LAST child
+    const int r = len - j;
+    long long base = -1;
+    if (lane == 0) {
+      unsigned long long b = atomicAdd(&D.hdr->node_top, (unsigned long long)r);
+      if (b + r > (unsigned long long)D.node_cap) atomicOr(&D.hdr->err, ERR_NODE_POOL);
+      else base = (long long)b;
+    }
+    base = __shfl_sync(FULL, base, 0);
+    if (base < 0) return;
+    for (int k = lane; k < r; k += 32) {
+      Node nn;
+      nn.token = path[j + k];
+      nn.n_child = (k < r - 1) ? 1 : 0;
+      nn.child = (k < r - 1) ? (int)(base + k + 1) : -1;
+      nn.cap = 0;
+      nn.fo = out_mode ? 1.0 : 0.0;
+      nn.fi = (!out_mode && idx == 0) ? 1.0f : 0.0f;
+      nn.aux = 0;
+      D.nodes[base + k] = nn;
+      for (int s = 1; s < D.n_slots; ++s)
+        D.fi_extra[(long long)(s - 1) * D.node_cap + base + k] = (!out_mode && idx == s) ? 1.0f : 0.0f;
+    }
+    // link
+    if (pn.n_child == 0) {
+      if (lane == 0) { D.nodes[cur].child = (int)base; D.nodes[cur].n_child = 1; }
+    } else if (pn.cap == 0) {  // inline -> block of 4
+      long long off = -1;
+      if (lane == 0) {
+        unsigned long long o = atomicAdd(&D.hdr->edge_top, 4ull);
+        if (o + 4 > (unsigned long long)D.edge_cap) atomicOr(&D.hdr->err, ERR_EDGE_POOL);
+        else {
+          off = (long long)o;
+          D.edges[off] = make_int2(D.nodes[pn.child].token, pn.child);
+          D.edges[off + 1] = make_int2(tok, (int)base);
+          D.nodes[cur].child = (int)off; D.nodes[cur].cap = 4; D.nodes[cur].n_child = 2;
+        }
+      }
+      off = __shfl_sync(FULL, off, 0);
+      if (off < 0) return;
+    } else if (pn.n_child < pn.cap) {
+      if (lane == 0) { D.edges[pn.child + pn.n_child] = make_int2(tok, (int)base); D.nodes[cur].n_child = pn.n_child + 1; }
+    } else {  // grow: copy into a block of twice the capacity (the old block is abandoned)
+      long long off = -1;
+      const int ncap = pn.cap * 2;
+      if (lane == 0) {
+        unsigned long long o = atomicAdd(&D.hdr->edge_top, (unsigned long long)ncap);
+        if (o + ncap > (unsigned long long)D.edge_cap) atomicOr(&D.hdr->err, ERR_EDGE_POOL);
+        else off = (long long)o;
+      }
+      off = __shfl_sync(FULL, off, 0);
+      if (off < 0) return;
+      for (int k = lane; k < pn.n_child; k += 32) D.edges[off + k] = D.edges[pn.child + k];
+      if (lane == 0) {
+        D.edges[off + pn.n_child] = make_int2(tok, (int)base);
+        D.nodes[cur].child = (int)off; D.nodes[cur].cap = ncap; D.nodes[cur].n_child = pn.n_child + 1;
+      }
+    }
+    if (lane == 0) {  // counters (:48-50)
+      D.tree_n_node[key] += r;
+      if (out_mode) D.tree_n_out[key] += r;
+    }
+    __syncwarp();
+    return;
+  }
+}
+
+__device__ void add_update(const Dev &D, int key, int flag, int *list, int *count) {
+  int old = atomicOr(&D.tree_flags[key], flag);
+  if (!(old & flag)) { int p = atomicAdd(count, 1); list[p] = key; }
+}
+
+// One warp per position p.  Positions that share their key token touch the same tree and must be applied
+// in list order (child insertion order is observable), so the first occurrence of a key is the "leader"
+// and replays every later occurrence itself; distinct keys own disjoint trees and run concurrently.
+__global__ void __launch_bounds__(NT) k_put_insert(Dev D, const int *tokens, int B, int mode, int idx, int is_stream,
+                                                   int slot) {
+  const int lane = lane_id();
+  const int p = blockIdx.x * (NT / 32) + warp_id();
+  const int npos = D.hdr->put_npos, len = D.hdr->put_len;
+  if (p >= npos) return;
+  const int *src = is_stream ? D.out_buf + (long long)slot * D.out_cap : tokens;
+  const int key = src[p];
+  if (key < 0 || key >= D.vocab) return;
+  if (is_stream && is_stop(D, key)) return;  // stop words never become tree keys (:388-389)
+  for (int q0 = 0; q0 < p; q0 += 32) {
+    int q = q0 + lane;
+    if (__any_sync(FULL, q < p && src[q] == key)) return;  // not the leader
+  }
+  const bool existed = D.root_of[key] >= 0;
+  const bool out_mode = (mode == PIA_MODE_OUTPUT);
+  int count = 0;
+  for (int q0 = p; q0 < npos; q0 += 32) {
+    int q = q0 + lane;
+    unsigned m = __ballot_sync(FULL, q < npos && src[q] == key);
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      int qq = q0 + b;
+      int plen = len - (qq + 1);
+      if (plen > B) plen = B;
+      warp_insert(D, key, src + qq + 1, plen, out_mode, idx);
+      ++count;
+    }
+  }
+  if (lane == 0) {
+    // put(): only a tree that already existed when a position reached it joins _update_trees (:361-367);
+    // stream_put(): always (:400)
+    if (is_stream || existed || count >= 2) add_update(D, key, FLAG_UPD, D.upd_list, &D.hdr->n_upd);
+    if (mode == PIA_MODE_INPUT) add_update(D, key, FLAG_UPDIN, D.updin_list, &D.hdr->n_updin);
+  }
+}
+
+// Tree.put on one tree (:33-37)
+__global__ void k_tree_put(Dev D, int key, const int *tokens, int n, int mode, int idx) {
+  if (n > 0) warp_insert(D, key, tokens, n, mode == PIA_MODE_OUTPUT, idx);
+}
+
+__global__ void k_put_finish(Dev D, int B, int final, int slot) {
+  // stream_put tail: keep the last B tokens as carry (:401-402) or clear on final (:404)
+  __shared__ int tmp[128];
+  const int tid = threadIdx.x;
+  int *buf = D.out_buf + (long long)slot * D.out_cap;
+  const int ts = D.hdr->put_len, npos = D.hdr->put_npos;
+  if (final) { if (tid == 0) D.out_len[slot] = 0; return; }
+  if (npos > 0) {  // ts > B
+    if (tid < B) tmp[tid] = buf[ts - B + tid];
+    __syncthreads();
+    if (tid < B) buf[tid] = tmp[tid];
+    if (tid == 0) D.out_len[slot] = B;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CTA-wide breadth-first walk below `start`; visit(id, node) -> descend?
+// ---------------------------------------------------------------------------------------------------
+struct BfsShared { int next_cnt; int err; };
+
+template <class Visit>
+__device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared *sh, Visit &&visit,
+                          unsigned long long &nv, unsigned long long &ne) {
+  const int tid = threadIdx.x, lane = lane_id();
+  const Node s = D.nodes[start];
+  if (tid == 0) sh->next_cnt = 0;
+  int cnt = s.n_child;
+  if (s.cap == 0) {
+    if (tid == 0 && cnt == 1) fr0[0] = s.child;
+  } else {
+    if (cnt > D.fr_cap) { if (tid == 0) atomicOr(&sh->err, ERR_FRONTIER); cnt = 0; }
+    for (int i = tid; i < cnt; i += NT) fr0[i] = D.edges[s.child + i].y;
+    if (tid == 0) ne += cnt;
+  }
+  __syncthreads();
+  int *cur = fr0, *nxt = fr1;
+  while (cnt > 0) {
+    for (int base = 0; base < cnt; base += NT) {
+      const int e = base + tid;
+      int push = 0;
+      Node nd;
+      nd.child = -1; nd.cap = 0;
+      if (e < cnt) {
+        const int id = cur[e];
+        nd = D.nodes[id];
+        ++nv;
+        if (visit(id, nd) && nd.n_child > 0) push = nd.n_child;
+      }
+      int incl = push;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      const int total = __shfl_sync(FULL, incl, 31);
+      int wbase = 0;
+      if (lane == 31 && total > 0) wbase = atomicAdd(&sh->next_cnt, total);
+      wbase = __shfl_sync(FULL, wbase, 31);
+      if (push) {
+        const int pos = wbase + incl - push;
+        if (pos + push > D.fr_cap) atomicOr(&sh->err, ERR_FRONTIER);
+        else if (nd.cap == 0) nxt[pos] = nd.child;
+        else { for (int k = 0; k < push; ++k) nxt[pos + k] = D.edges[nd.child + k].y; ne += push; }
+      }
+    }
+    __syncthreads();
+    cnt = sh->next_cnt;
+    if (cnt > D.fr_cap) cnt = 0;  // overflowed level: err already set
+    __syncthreads();
+    if (tid == 0) sh->next_cnt = 0;
+    __syncthreads();
+    int *t = cur; cur = nxt; nxt = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// get
+// ---------------------------------------------------------------------------------------------------
+constexpr int HCAP = 1024;                       // distinct frequency values per histogram
+constexpr unsigned long long HEMPTY = ~0ull;
+
+struct Hist { unsigned long long key[HCAP]; unsigned cnt[HCAP]; };
+
+__device__ __forceinline__ void hist_add(Hist *h, unsigned long long bits, int *ovf) {
+  unsigned s = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 54) & (HCAP - 1);
+  for (int probe = 0; probe < HCAP; ++probe) {
+    unsigned long long old = atomicCAS(&h->key[s], HEMPTY, bits);
+    if (old == HEMPTY || old == bits) { atomicAdd(&h->cnt[s], 1u); return; }
+    s = (s + 1) & (HCAP - 1);
+  }
+  *ovf = 1;
+}
+
+// sorted(values, reverse=True)[rank-1] from the histogram; `found` stays 0 if rank is out of range
+__device__ void hist_kth(const Hist *h, long long rank, unsigned long long *result, int *found) {
+  for (int s = threadIdx.x; s < HCAP; s += NT) {
+    const unsigned long long k = h->key[s];
+    if (k == HEMPTY) continue;
+    long long greater = 0;
+    for (int j = 0; j < HCAP; ++j) {
+      const unsigned long long kj = h->key[j];
+      if (kj != HEMPTY && kj > k) greater += h->cnt[j];
+    }
+    if (greater < rank && rank <= greater + (long long)h->cnt[s]) { *result = k; *found = 1; }
+  }
+}
+
+struct GetParams {
+  const int *queries, *qlen, *d_idx;
+  int batch, q_stride, max_query, idx, dl, bl, min_in, min_out, mode, kind, flags, max_seq;
+  int *out_ids; unsigned long long *out_mask; int *out_n, *out_sizes, *out_nsizes, *status;
+};
+
+template <int MAXS, int MAXD>
+struct GetSmem {
+  Hist hin, hout;
+  // merge pool for frame construction
+  unsigned long long pkey[MAXS + NT];
+  int pord[MAXS + NT], pnode[MAXS + NT], ptok[MAXS + NT], pflag[MAXS + NT];
+  unsigned long long qkey[MAXS];
+  int qord[MAXS], qnode[MAXS], qtok[MAXS], qflag[MAXS];
+  // DFS frames
+  int fnode[MAXD][MAXS], ftok[MAXD][MAXS];
+  unsigned char fflag[MAXD][MAXS];
+  int fcnt[MAXD], fcur[MAXD], fpid[MAXD];
+  // outputs
+  unsigned long long mask[MAXS][(MAXS + 63) / 64];
+  int ids[MAXS];
+  int q[16];
+  BfsShared bfs;
+  int hist_ovf;
+  long long n_live, n_in, n_out;
+  unsigned long long thr_bits; int thr_found;
+  int pool_n, match_node, n, sizes0, sizes1, depth, state;
+  int best_node, best_tok; unsigned long long best_key; int best_ord;
+};
+
+constexpr int CF_FI = 1, CF_FO = 2, CF_KIDS = 4;
+
+// Builds the sorted candidate list of `parent`'s children for one DFS frame: children that pass the
+// threshold filter (lookahead_cache.py:264-272), ordered by fm descending, ties by insertion order (:254-258),
+// truncated to K (no more than K can still be emitted).
+template <int MAXS, int MAXD>
+__device__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int K, int idx, int mode, double omw,
+                           double w, double min_in, double min_out, double min_mix, int *onode, int *otok,
+                           unsigned char *oflag, unsigned long long &nv, unsigned long long &ne) {
+  const int tid = threadIdx.x;
+  const Node p = D.nodes[parent];
+  const int C = p.n_child;
+  int m = 0;  // current size of the running top list (uniform)
+  for (int base = 0; base < C; base += NT) {
+    if (tid == 0) S->pool_n = m;
+    __syncthreads();
+    const int i = base + tid;
+    if (i < C) {
+      int cid;
+      if (p.cap == 0) cid = p.child; else { cid = D.edges[p.child + i].y; ++ne; }
+      const Node c = D.nodes[cid];
+      ++nv;
+      const double fi = (double)load_fi(D, c, cid, idx), fo = c.fo;
+      const double fm = mix_freq(omw, w, fi, fo);
+      bool skip;
+      if (mode == PIA_MODE_MIX) skip = (fi < min_in && fo < min_out && fm < min_mix);
+      else if (mode == PIA_MODE_INPUT) skip = fi < min_in;
+      else skip = fo < min_out;
+      if (!skip) {
+        const int slot = atomicAdd(&S->pool_n, 1);
+        S->pkey[slot] = dbits(fm);
+        S->pord[slot] = i;
+        S->pnode[slot] = cid;
+        S->ptok[slot] = c.token;
+        S->pflag[slot] = (fi > 0.0 ? CF_FI : 0) | (fo > 0.0 ? CF_FO : 0) | (c.n_child > 0 ? CF_KIDS : 0);
+      }
+    }
+    __syncthreads();
+    const int total = S->pool_n;
+    // rank every pool element; the first K in (key desc, ord asc) order survive
+    for (int e = tid; e < total; e += NT) {
+      const unsigned long long k = S->pkey[e];
+      const int o = S->pord[e];
+      int rank = 0;
+      for (int j = 0; j < total; ++j) {
+        const unsigned long long kj = S->pkey[j];
+        rank += (kj > k) || (kj == k && S->pord[j] < o);
+      }
+      if (rank < K) {
+        S->qkey[rank] = k; S->qord[rank] = o; S->qnode[rank] = S->pnode[e]; S->qtok[rank] = S->ptok[e];
+        S->qflag[rank] = S->pflag[e];
+      }
+    }
+    __syncthreads();
+    m = total < K ? total : K;
+    for (int e = tid; e < m; e += NT) {
+      S->pkey[e] = S->qkey[e]; S->pord[e] = S->qord[e]; S->pnode[e] = S->qnode[e]; S->ptok[e] = S->qtok[e];
+      S->pflag[e] = S->qflag[e];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < m; e += NT) { onode[e] = S->pnode[e]; otok[e] = S->ptok[e]; oflag[e] = (unsigned char)S->pflag[e]; }
+  __syncthreads();
+  return m;
+}
+
+// Tree.get (lookahead_cache.py:65-144) for the tree rooted at `root`, query suffix q[0..nq).
+// Result is left in S->ids / S->mask / S->n / S->sizes*.  returns PIA_OK / PIA_ERR_INDEX / PIA_ERR_CAPACITY.
+template <int MAXS, int MAXD>
+__device__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree_token, const int *q, int nq,
+                        int max_size, int max_length, int min_in_sz, int min_out_sz, int mode, int idx, int *fr0,
+                        int *fr1, unsigned long long &nv, unsigned long long &ne) {
+  const int tid = threadIdx.x;
+  constexpr int W = (MAXS + 63) / 64;
+  // ---- _match (:224-246), one warp
+  if (tid < 32) {
+    int cur = root;
+    for (int j = 0; j < nq && cur >= 0; ++j) {
+      const Node pn = D.nodes[cur];
+      const int c = find_child(D, pn, q[j]);
+      if (c < 0) { cur = -1; break; }
+      const Node cn = D.nodes[c];
+      const float fi = load_fi(D, cn, c, idx);
+      bool live;
+      if (mode == PIA_MODE_INPUT) live = fi > 0.f;
+      else if (mode == PIA_MODE_OUTPUT) live = cn.fo > 0.0;
+      else live = fi > 0.f || cn.fo > 0.0;
+      cur = live ? c : -1;
+    }
+    if (cur >= 0 && D.nodes[cur].n_child == 0) cur = -1;  // len(nodes) == 0 (:70)
+    if (tid == 0) {
+      S->match_node = cur;
+      S->sizes0 = 0; S->sizes1 = 0;
+      S->hist_ovf = 0; S->n_live = 0; S->n_in = 0; S->n_out = 0; S->thr_found = 0;
+    }
+  }
+  for (int s = tid; s < HCAP; s += NT) { S->hin.key[s] = HEMPTY; S->hin.cnt[s] = 0; S->hout.key[s] = HEMPTY; S->hout.cnt[s] = 0; }
+  __syncthreads();
+  const int start = S->match_node;
+  if (start < 0) {  // miss: ([last query token or tree token], ones(1,1), [0,0])  (:70-72)
+    if (tid == 0) {
+      S->ids[0] = nq > 0 ? q[nq - 1] : tree_token;
+      for (int w = 0; w < W; ++w) S->mask[0][w] = 0;
+      S->mask[0][0] = 1ull;
+      S->n = 1;
+    }
+    __syncthreads();
+    return PIA_OK;
+  }
+  // ---- _dfs_get_freqs (:146-154): every live node below the match, any order
+  const bool need_in = (mode == PIA_MODE_INPUT) || (mode == PIA_MODE_MIX && min_in_sz > 0);
+  const bool need_out = (mode == PIA_MODE_OUTPUT) || (mode == PIA_MODE_MIX && min_out_sz > 0);
+  {
+    long long my_live = 0, my_in = 0, my_out = 0;
+    auto visit = [&](int id, const Node &nd) -> bool {
+      const float fi = load_fi(D, nd, id, idx);
+      const double fo = nd.fo;
+      if (!(fo > 0.0 || fi > 0.f)) return false;
+      ++my_live; my_in += fi > 0.f; my_out += fo > 0.0;
+      if (need_in) hist_add(&S->hin, dbits((double)fi), &S->hist_ovf);
+      if (need_out) hist_add(&S->hout, dbits(fo), &S->hist_ovf);
+      return true;
+    };
+    bfs_below(D, start, fr0, fr1, &S->bfs, visit, nv, ne);
+    if (my_live) { atomicAdd((unsigned long long *)&S->n_live, (unsigned long long)my_live);
+                   atomicAdd((unsigned long long *)&S->n_in, (unsigned long long)my_in);
+                   atomicAdd((unsigned long long *)&S->n_out, (unsigned long long)my_out); }
+    __syncthreads();
+  }
+  if (S->bfs.err) return PIA_ERR_CAPACITY;
+  // ---- thresholds (:78-125)
+  double min_in = 1e9, min_out = 1e9, min_mix = 1e9, w = 1e-4;
+  const long long N = S->n_live;
+  long long size;
+  if (mode == PIA_MODE_INPUT) { w = 0.0; size = S->n_in; }
+  else if (mode == PIA_MODE_OUTPUT) { w = 1.0; size = S->n_out; }
+  else size = N;
+  if (size > max_size) {
+    if (S->hist_ovf) return PIA_ERR_CAPACITY;
+    // python index k-1 with negative wrap: k == 0 -> the smallest value (rank N)
+    if (need_in) {
+      long long rank = min_in_sz >= 1 ? min_in_sz : N;
+      hist_kth(&S->hin, rank, &S->thr_bits, &S->thr_found);
+      __syncthreads();
+      if (!S->thr_found) return PIA_ERR_INDEX;
+      min_in = __longlong_as_double((long long)S->thr_bits);
+      __syncthreads();
+      if (tid == 0) S->thr_found = 0;
+      __syncthreads();
+    }
+    if (need_out) {
+      long long rank = min_out_sz >= 1 ? min_out_sz : N;
+      hist_kth(&S->hout, rank, &S->thr_bits, &S->thr_found);
+      __syncthreads();
+      if (!S->thr_found) return PIA_ERR_INDEX;
+      min_out = __longlong_as_double((long long)S->thr_bits);
+      __syncthreads();
+    }
+    // mix mode: the reference's refinement loop never lowers min_mix_freq (every record carries None in
+    // slot 0, :100-123), so it stays 1e9
+  } else {
+    if (mode == PIA_MODE_INPUT) min_in = 0.0;
+    else if (mode == PIA_MODE_OUTPUT) min_out = 0.0;
+    else min_mix = 0.0;
+  }
+  const double omw = __dsub_rn(1.0, w);
+  // ---- _ravel (:248-293): DFS pre-order, iterative with one sorted frame per depth
+  if (tid == 0) {
+    const int mt = nq > 0 ? q[nq - 1] : 0;
+    S->ids[0] = (nq > 0 && mt != 0) ? mt : tree_token;  // `match_token_id or self.token_id` (:129)
+    for (int w2 = 0; w2 < W; ++w2) S->mask[0][w2] = 0;
+    S->mask[0][0] = 1ull;
+    S->n = 1;
+    S->depth = -1;
+  }
+  __syncthreads();
+  if (max_size > 1 && max_length > 0) {
+    int cnt0 = build_frame(D, S, start, max_size - 1, idx, mode, omw, w, min_in, min_out, min_mix, S->fnode[0],
+                           S->ftok[0], S->fflag[0], nv, ne);
+    if (tid == 0) { S->fcnt[0] = cnt0; S->fcur[0] = 0; S->fpid[0] = -1; S->depth = 0; }
+    __syncthreads();
+    while (true) {
+      // thread 0 advances the DFS until a new frame must be built (state 1) or the walk ends (state 0)
+      if (tid == 0) {
+        int st = 0;
+        while (S->depth >= 0 && S->n < max_size) {
+          const int d = S->depth;
+          if (S->fcur[d] >= S->fcnt[d]) { S->depth = d - 1; continue; }
+          const int e = S->fcur[d]++;
+          const int rid = S->n;
+          S->ids[rid] = S->ftok[d][e];
+          const int fl = S->fflag[d][e];
+          S->sizes0 += (fl & CF_FI) ? 1 : 0;
+          S->sizes1 += (fl & CF_FO) ? 1 : 0;
+          const int pid = S->fpid[d];
+          for (int w2 = 0; w2 < W; ++w2) S->mask[rid][w2] = pid >= 0 ? S->mask[pid][w2] : (w2 == 0 ? 1ull : 0ull);
+          S->mask[rid][rid >> 6] |= 1ull << (rid & 63);
+          S->n = rid + 1;
+          // recurse (:283-293): children exist, depth budget max_length-1-d > 0, room left
+          if ((fl & CF_KIDS) && (max_length - 1 - d) > 0 && S->n < max_size && d + 1 < MAXD) {
+            S->best_node = S->fnode[d][e];
+            S->fpid[d + 1] = rid;
+            st = 1;
+            break;
+          }
+        }
+        S->state = st;
+      }
+      __syncthreads();
+      if (S->state == 0) break;
+      const int d1 = S->depth + 1;
+      const int cnt = build_frame(D, S, S->best_node, max_size - S->n, idx, mode, omw, w, min_in, min_out, min_mix,
+                                  S->fnode[d1], S->ftok[d1], S->fflag[d1], nv, ne);
+      if (tid == 0) { S->fcnt[d1] = cnt; S->fcur[d1] = 0; S->depth = d1; }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  return PIA_OK;
+}
+
+// Tree.get_one_branch (lookahead_cache.py:171-222): greedy single chain
+template <int MAXS, int MAXD>
+__device__ int tree_get_one(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree_token, const int *q, int nq,
+                            int max_length, int mode, int idx, int *miss, unsigned long long &nv,
+                            unsigned long long &ne) {
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    int cur = root;
+    for (int j = 0; j < nq && cur >= 0; ++j) {
+      const Node pn = D.nodes[cur];
+      const int c = find_child(D, pn, q[j]);
+      if (c < 0) { cur = -1; break; }
+      const Node cn = D.nodes[c];
+      const float fi = load_fi(D, cn, c, idx);
+      bool live;
+      if (mode == PIA_MODE_INPUT) live = fi > 0.f;
+      else if (mode == PIA_MODE_OUTPUT) live = cn.fo > 0.0;
+      else live = fi > 0.f || cn.fo > 0.0;
+      cur = live ? c : -1;
+    }
+    if (cur >= 0 && D.nodes[cur].n_child == 0) cur = -1;
+    if (tid == 0) S->match_node = cur;
+  }
+  __syncthreads();
+  int cur = S->match_node;
+  if (cur < 0) {
+    if (tid == 0) { S->ids[0] = nq > 0 ? q[nq - 1] : tree_token; S->n = 1; }
+    *miss = 1;
+    __syncthreads();
+    return PIA_OK;
+  }
+  *miss = 0;
+  if (tid == 0) {
+    const int mt = nq > 0 ? q[nq - 1] : 0;
+    S->ids[0] = (nq > 0 && mt != 0) ? mt : tree_token;
+    S->n = 1;
+  }
+  __syncthreads();
+  for (int length = 0; length < max_length; ++length) {
+    const Node p = D.nodes[cur];
+    if (p.n_child == 0) break;
+    if (tid == 0) { S->best_node = -1; S->best_key = 0; S->best_ord = 0x7fffffff; }
+    __syncthreads();
+    // argmax of freq over the children, strict '>' keeps the earliest child on ties, freq must be > 0
+    for (int base = 0; base < p.n_child; base += NT) {
+      const int i = base + tid;
+      if (i < p.n_child) {
+        int cid;
+        if (p.cap == 0) cid = p.child; else { cid = D.edges[p.child + i].y; ++ne; }
+        const Node c = D.nodes[cid];
+        ++nv;
+        const double a = (double)load_fi(D, c, cid, idx), b = c.fo;
+        double freq; bool ok;
+        if (mode == PIA_MODE_MIX) { ok = a > 0 || b > 0; freq = __dadd_rn(__dmul_rn(10000.0, b), a); }
+        else if (mode == PIA_MODE_INPUT) { freq = a; ok = a > 0; }
+        else { freq = b; ok = b > 0; }
+        if (ok && freq > 0.0) {
+          const unsigned long long k = dbits(freq);
+          atomicMax(&S->best_key, k);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long bk = S->best_key;
+    if (bk == 0) break;
+    for (int base = 0; base < p.n_child; base += NT) {
+      const int i = base + tid;
+      if (i < p.n_child) {
+        int cid = p.cap == 0 ? p.child : D.edges[p.child + i].y;
+        const Node c = D.nodes[cid];
+        const double a = (double)load_fi(D, c, cid, idx), b = c.fo;
+        double freq; bool ok;
+        if (mode == PIA_MODE_MIX) { ok = a > 0 || b > 0; freq = __dadd_rn(__dmul_rn(10000.0, b), a); }
+        else if (mode == PIA_MODE_INPUT) { freq = a; ok = a > 0; }
+        else { freq = b; ok = b > 0; }
+        if (ok && dbits(freq) == bk) atomicMin(&S->best_ord, i);
+      }
+    }
+    __syncthreads();
+    const int bo = S->best_ord;
+    const int cid = p.cap == 0 ? p.child : D.edges[p.child + bo].y;
+    if (tid == 0) { S->ids[S->n] = D.nodes[cid].token; S->n += 1; }
+    cur = cid;
+    __syncthreads();
+  }
+  __syncthreads();
+  return PIA_OK;
+}
+
+// LookaheadCache.hier_get / one_get (lookahead_cache.py:408-439, 490-517): one CTA per query row
+template <int MAXS, int MAXD>
+__global__ void __launch_bounds__(NT) k_get(Dev D, GetParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GetSmem<MAXS, MAXD> *S = reinterpret_cast<GetSmem<MAXS, MAXD> *>(smem_raw);
+  constexpr int W = (MAXS + 63) / 64;
+  const int tid = threadIdx.x;
+  int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
+  int *fr1 = fr0 + D.fr_cap;
+  unsigned long long nv = 0, ne = 0;
+  const int Wout = (P.dl + 63) / 64;
+  for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+    __syncthreads();
+    const int len = P.qlen[b];
+    int nq, bl = P.bl;
+    const int *qsrc;
+    if (P.flags & PIA_GET_TAIL) {
+      nq = len < P.max_query ? len : P.max_query;
+      qsrc = P.queries + (long long)b * P.q_stride + (len - nq);
+      if (P.max_seq > 0) { int lim = P.max_seq - len - 1; if (lim < 0) lim = 0; if (bl > lim) bl = lim; }
+    } else {
+      nq = len < P.q_stride ? len : P.q_stride;
+      qsrc = P.queries + (long long)b * P.q_stride;
+    }
+    if (nq > 16) { qsrc += nq - 16; nq = 16; }
+    if (nq < 0) nq = 0;
+    if (tid < nq) S->q[tid] = qsrc[tid];
+    if (tid == 0) { S->bfs.err = 0; S->bfs.next_cnt = 0; }
+    __syncthreads();
+    const int idx = P.d_idx ? P.d_idx[b] : P.idx;
+    int status = PIA_OK, n_out = 0, nsizes = 2, sz0 = 0, sz1 = 0;
+    bool have = false;
+    if (P.dl <= 1 || bl == 0) {  // (:413-414, :495-496)
+      nsizes = 0;
+    } else {
+      const int n_iter = (P.flags & PIA_GET_FIRST_ONLY) ? (nq < 1 ? nq : 1) : nq;
+      for (int i = 0; i < n_iter; ++i) {
+        const int t = S->q[i];
+        if (t < 0 || t >= D.vocab) continue;
+        const int root = D.root_of[t];
+        if (root < 0) continue;
+        const int rest = nq - (i + 1);
+        if (rest == 0 && is_stop(D, t)) continue;  // (:422-423)
+        int rc, miss = 0;
+        if (P.kind == PIA_GET_ONE) rc = tree_get_one<MAXS, MAXD>(D, S, root, t, S->q + i + 1, rest, bl, P.mode, idx, &miss, nv, ne);
+        else rc = tree_get<MAXS, MAXD>(D, S, root, t, S->q + i + 1, rest, P.dl, bl, P.min_in, P.min_out, P.mode, idx, fr0, fr1, nv, ne);
+        if (rc != PIA_OK) { status = rc; break; }
+        have = true;
+        n_out = S->n;
+        if (P.kind == PIA_GET_ONE) { if (miss) { nsizes = 2; sz0 = sz1 = 0; } else { nsizes = 1; sz0 = n_out - 1; sz1 = 0; } }
+        else { nsizes = 2; sz0 = S->sizes0; sz1 = S->sizes1; }
+        if (P.kind == PIA_GET_ONE ? (n_out >= bl / 2) : (n_out >= bl)) break;  // (:433-434, :512)
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+    int *oid = P.out_ids + (long long)b * P.dl;
+    unsigned long long *om = P.out_mask + (long long)b * P.dl * Wout;
+    if (status == PIA_OK && have) {
+      for (int i = tid; i < n_out; i += NT) {
+        oid[i] = S->ids[i];
+        if (P.kind == PIA_GET_ONE) {  // lower-triangular mask (:222)
+          for (int w = 0; w < Wout; ++w) {
+            unsigned long long v = 0;
+            if (i >= 64 * (w + 1) - 1) v = ~0ull; else if (i >= 64 * w) v = (i - 64 * w) == 63 ? ~0ull : ((1ull << (i - 64 * w + 1)) - 1);
+            om[(long long)i * Wout + w] = v;
+          }
+        } else {
+          for (int w = 0; w < Wout; ++w) om[(long long)i * Wout + w] = w < W ? S->mask[i][w] : 0ull;
+        }
+      }
+    } else if (status == PIA_OK) {  // token_ids[-1:], default mask (:414, :436-437)
+      n_out = nq > 0 ? 1 : 0;
+      if (tid == 0 && nq > 0) { oid[0] = S->q[nq - 1]; for (int w = 0; w < Wout; ++w) om[w] = w == 0 ? 1ull : 0ull; }
+    } else {
+      n_out = 0;
+    }
+    if (tid == 0) {
+      P.out_n[b] = n_out;
+      P.out_sizes[2 * b] = sz0; P.out_sizes[2 * b + 1] = sz1;
+      P.out_nsizes[b] = nsizes;
+      P.status[b] = status;
+      if (status == PIA_ERR_CAPACITY) atomicOr(&D.hdr->err, S->hist_ovf ? ERR_HIST : ERR_FRONTIER);
+    }
+  }
+  // roofline accounting: node records / child entries read
+  for (int o = 16; o > 0; o >>= 1) { nv += __shfl_down_sync(FULL, nv, o); ne += __shfl_down_sync(FULL, ne, o); }
+  if (lane_id() == 0) { if (nv) atomicAdd(&D.hdr->nodes_visited, nv); if (ne) atomicAdd(&D.hdr->edges_visited, ne); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reset_input_freqs (:320-333, :566-570)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx) {
+  __shared__ BfsShared sh;
+  int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
+  int *fr1 = fr0 + D.fr_cap;
+  unsigned long long nv = 0, ne = 0;
+  const int n = D.hdr->n_updin;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int key = D.updin_list[i];
+    const int root = D.root_of[key];
+    if (threadIdx.x == 0) { sh.err = 0; sh.next_cnt = 0; D.tree_flags[key] &= ~FLAG_UPDIN; }
+    __syncthreads();
+    if (root < 0) continue;
+    auto visit = [&](int id, const Node &nd) -> bool {
+      const float f = load_fi(D, nd, id, idx);
+      if (f == 0.f) return false;
+      if (idx == 0) D.nodes[id].fi = 0.f; else D.fi_extra[(long long)(idx - 1) * D.node_cap + id] = 0.f;
+      return true;
+    };
+    bfs_below(D, root, fr0, fr1, &sh, visit, nv, ne);
+    if (threadIdx.x == 0 && sh.err) atomicOr(&D.hdr->err, ERR_FRONTIER);
+    __syncthreads();
+  }
+}
+__global__ void k_reset_finish(Dev D) { D.hdr->n_updin = 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// squeeze_branch_counts (:295-318, :572-576): one CTA per touched tree, one warp per surviving parent
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_squeeze(Dev D) {
+  __shared__ int s_next, s_count, s_err;
+  const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
+  int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
+  int *fr1 = fr0 + D.fr_cap;
+  const int n_listed = D.hdr->n_upd;
+  if (n_listed + D.hdr->n_upd_stale < 1024) return;
+  for (int i = blockIdx.x; i < n_listed; i += gridDim.x) {
+    const int key = D.upd_list[i];
+    const int root = D.root_of[key];
+    __syncthreads();
+    if (tid == 0) { s_next = 0; s_count = 0; s_err = 0; D.tree_flags[key] &= ~FLAG_UPD; }
+    __syncthreads();
+    if (root < 0) continue;
+    if (!(D.tree_n_node[key] > D.hdr->max_node || D.tree_n_out[key] > D.hdr->max_out)) continue;
+    if (tid == 0) fr0[0] = root;
+    __syncthreads();
+    int cnt = 1;
+    int *cur = fr0, *nxt = fr1;
+    while (cnt > 0) {
+      for (int e = wid; e < cnt; e += NT / 32) {
+        const int pid = cur[e];
+        const Node p = D.nodes[pid];
+        if (p.cap == 0) {
+          if (p.n_child == 1 && lane == 0) {
+            const int c = p.child;
+            const double fo = D.nodes[c].fo;
+            if (fo > 1.0) {
+              D.nodes[c].fo = fo * 0.5;
+              atomicAdd(&s_count, 1);
+              if (D.nodes[c].n_child > 0) { int pos = atomicAdd(&s_next, 1); if (pos < D.fr_cap) nxt[pos] = c; else s_err = 1; }
+            } else {
+              D.nodes[pid].n_child = 0; D.nodes[pid].child = -1;
+            }
+          }
+        } else {
+          int wr = 0;
+          for (int base = 0; base < p.n_child; base += 32) {
+            const int k = base + lane;
+            int2 en = make_int2(-1, -1);
+            bool keep = false; bool kids = false;
+            if (k < p.n_child) {
+              en = D.edges[p.child + k];
+              const double fo = D.nodes[en.y].fo;
+              keep = fo > 1.0;
+              if (keep) { D.nodes[en.y].fo = fo * 0.5; kids = D.nodes[en.y].n_child > 0; }
+            }
+            const unsigned m = __ballot_sync(FULL, keep);
+            const int off = __popc(m & ((1u << lane) - 1));
+            __syncwarp();
+            if (keep) D.edges[p.child + wr + off] = en;
+            const unsigned mk = __ballot_sync(FULL, kids);
+            int nb = 0;
+            if (lane == 0 && mk) nb = atomicAdd(&s_next, __popc(mk));
+            nb = __shfl_sync(FULL, nb, 0);
+            if (kids) { int pos = nb + __popc(mk & ((1u << lane) - 1)); if (pos < D.fr_cap) nxt[pos] = en.y; else s_err = 1; }
+            wr += __popc(m);
+          }
+          if (lane == 0) { D.nodes[pid].n_child = wr; atomicAdd(&s_count, wr); }
+        }
+      }
+      __syncthreads();
+      cnt = s_next;
+      if (cnt > D.fr_cap) cnt = 0;
+      __syncthreads();
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      int *t = cur; cur = nxt; nxt = t;
+    }
+    if (tid == 0) {
+      D.tree_n_node[key] = s_count; D.tree_n_out[key] = s_count;  // (:298-301)
+      if (s_err) atomicOr(&D.hdr->err, ERR_FRONTIER);
+    }
+  }
+}
+__global__ void k_squeeze_finish(Dev D) {
+  if (D.hdr->n_upd + D.hdr->n_upd_stale >= 1024) { D.hdr->n_upd = 0; D.hdr->n_upd_stale = 0; }
+}
+
+// fresh(): mem = {} (:563-564).  Trees pending in the update sets keep counting towards the 1024 threshold
+// exactly as the orphaned Python objects do, but their storage is reclaimed.
+__global__ void __launch_bounds__(NT) k_fresh(Dev D) {
+  const int gid = blockIdx.x * NT + threadIdx.x;
+  const int stride = gridDim.x * NT;
+  for (int t = gid; t < D.vocab; t += stride) { D.root_of[t] = -1; D.tree_flags[t] = 0; D.tree_n_node[t] = 0; D.tree_n_out[t] = 0; }
+}
+__global__ void k_fresh_finish(Dev D) {
+  Hdr *h = D.hdr;
+  h->n_upd_stale += h->n_upd; h->n_upd = 0;
+  h->n_updin = 0;  // resetting orphaned trees is unobservable
+  h->node_top = 0; h->edge_top = 0; h->n_trees = 0;
+}
+
+}  // namespace trie
+}  // namespace pia
+
+// =====================================================================================================
+// host side / C ABI
+// =====================================================================================================
+using namespace pia;
+using namespace pia::trie;
+
+struct pia_trie {
+  Dev dev;
+  pia_trie_config_t cfg;
+  std::vector<void *> allocs;
+  int n_sm;
+};
+
+template <class T>
+static cudaError_t dalloc(pia_trie *t, T **p, size_t count, bool zero) {
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+  if (e != cudaSuccess) return e;
+  t->allocs.push_back((void *)*p);
+  if (zero) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+extern "C" int pia_trie_create(const pia_trie_config_t *c, pia_trie_t **out) {
+  PIA_REQUIRE(c && out, "null argument");
+  pia_trie_config_t cfg = *c;
+  if (cfg.vocab_capacity <= 0) cfg.vocab_capacity = 65536;
+  if (cfg.node_capacity <= 0) cfg.node_capacity = 1 << 24;
+  if (cfg.edge_capacity <= 0) cfg.edge_capacity = cfg.node_capacity;
+  if (cfg.n_input_slots <= 0) cfg.n_input_slots = 1;
+  if (cfg.max_node <= 0) cfg.max_node = 65536;
+  if (cfg.max_output_node <= 0) cfg.max_output_node = 512;
+  if (cfg.max_put_tokens <= 0) cfg.max_put_tokens = 8192;
+  if (cfg.frontier_capacity <= 0) cfg.frontier_capacity = 1 << 18;
+  if (cfg.max_resident_queries <= 0) cfg.max_resident_queries = 296;
+  PIA_REQUIRE(cfg.node_capacity < (1ll << 31) && cfg.edge_capacity < (1ll << 31), "pools are indexed with int32");
+  pia_trie *t = new (std::nothrow) pia_trie();
+  PIA_REQUIRE(t, "out of host memory");
+  t->cfg = cfg;
+  Dev &D = t->dev;
+  memset(&D, 0, sizeof(D));
+  cudaError_t e = cudaSuccess;
+  auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  ok(dalloc(t, &D.nodes, (size_t)cfg.node_capacity, false));
+  ok(dalloc(t, &D.edges, (size_t)cfg.edge_capacity, false));
+  if (cfg.n_input_slots > 1) ok(dalloc(t, &D.fi_extra, (size_t)(cfg.n_input_slots - 1) * cfg.node_capacity, false));
+  ok(dalloc(t, &D.hdr, 1, true));
+  ok(dalloc(t, &D.root_of, (size_t)cfg.vocab_capacity, false));
+  ok(dalloc(t, &D.tree_n_node, (size_t)cfg.vocab_capacity, true));
+  ok(dalloc(t, &D.tree_n_out, (size_t)cfg.vocab_capacity, true));
+  ok(dalloc(t, &D.tree_flags, (size_t)cfg.vocab_capacity, true));
+  ok(dalloc(t, &D.upd_list, (size_t)cfg.vocab_capacity, true));
+  ok(dalloc(t, &D.updin_list, (size_t)cfg.vocab_capacity, true));
+  ok(dalloc(t, &D.stop_bits, (size_t)(cfg.vocab_capacity + 31) / 32, true));
+  D.out_cap = cfg.max_put_tokens + 128;
+  ok(dalloc(t, &D.out_buf, (size_t)cfg.n_input_slots * D.out_cap, true));
+  ok(dalloc(t, &D.out_len, (size_t)cfg.n_input_slots, true));
+  ok(dalloc(t, &D.frontier, (size_t)cfg.max_resident_queries * 2 * cfg.frontier_capacity, false));
+  if (e == cudaSuccess) e = cudaMemset(D.root_of, 0xff, sizeof(int) * (size_t)cfg.vocab_capacity);
+  D.node_cap = cfg.node_capacity; D.edge_cap = cfg.edge_capacity; D.vocab = cfg.vocab_capacity;
+  D.n_slots = cfg.n_input_slots; D.fr_cap = cfg.frontier_capacity; D.max_resident = cfg.max_resident_queries;
+  if (e == cudaSuccess) {
+    Hdr h; memset(&h, 0, sizeof(h));
+    h.max_node = cfg.max_node; h.max_out = cfg.max_output_node; h.n_eos = 1; h.eos[0] = 2;
+    e = cudaMemcpy(D.hdr, &h, sizeof(h), cudaMemcpyHostToDevice);
+  }
+  int dev_id = 0;
+  if (e == cudaSuccess) e = cudaGetDevice(&dev_id);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->n_sm, cudaDevAttrMultiProcessorCount, dev_id);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GetSmem<64, 16>));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GetSmem<128, 32>));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("pia_trie_create: %s", cudaGetErrorString(e));
+    for (void *p : t->allocs) cudaFree(p);
+    delete t;
+    return PIA_ERR_CUDA;
+  }
+  *out = t;
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_destroy(pia_trie_t *t) {
+  if (!t) return PIA_OK;
+  cudaDeviceSynchronize();
+  for (void *p : t->allocs) cudaFree(p);
+  delete t;
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_set_eos(pia_trie_t *t, const int32_t *h_eos, int n) {
+  PIA_REQUIRE(t && n >= 0 && n <= 8 && (n == 0 || h_eos), "eos: at most 8 ids");
+  int buf[9]; buf[0] = n;
+  for (int i = 0; i < 8; ++i) buf[1 + i] = i < n ? h_eos[i] : -1;
+  PIA_CUDA_CHECK(cudaDeviceSynchronize());
+  PIA_CUDA_CHECK(cudaMemcpy((char *)t->dev.hdr + offsetof(Hdr, n_eos), buf, sizeof(buf), cudaMemcpyHostToDevice));
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_set_stop_words(pia_trie_t *t, const int32_t *h_words, int n) {
+  PIA_REQUIRE(t && n >= 0 && (n == 0 || h_words), "bad stop words");
+  const size_t words = (size_t)(t->cfg.vocab_capacity + 31) / 32;
+  std::vector<unsigned> bits(words, 0u);
+  for (int i = 0; i < n; ++i) {
+    PIA_REQUIRE(h_words[i] >= 0 && h_words[i] < t->cfg.vocab_capacity, "stop word %d outside vocab_capacity", h_words[i]);
+    bits[h_words[i] >> 5] |= 1u << (h_words[i] & 31);
+  }
+  PIA_CUDA_CHECK(cudaDeviceSynchronize());
+  PIA_CUDA_CHECK(cudaMemcpy(t->dev.stop_bits, bits.data(), words * sizeof(unsigned), cudaMemcpyHostToDevice));
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_set_limits(pia_trie_t *t, int max_node, int max_output_node) {
+  PIA_REQUIRE(t, "null trie");
+  int v[2] = {max_node, max_output_node};
+  PIA_CUDA_CHECK(cudaDeviceSynchronize());
+  PIA_CUDA_CHECK(cudaMemcpy((char *)t->dev.hdr + offsetof(Hdr, max_node), v, sizeof(v), cudaMemcpyHostToDevice));
+  t->cfg.max_node = max_node; t->cfg.max_output_node = max_output_node;
+  return PIA_OK;
+}
+
+static int launch_reset(pia_trie *t, int idx, cudaStream_t s) {
+  const int grid = t->dev.max_resident < 4 * t->n_sm ? t->dev.max_resident : 4 * t->n_sm;
+  k_reset_input<<<grid, NT, 0, s>>>(t->dev, idx);
+  PIA_LAUNCH_CHECK();
+  k_reset_finish<<<1, 1, 0, s>>>(t->dev);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+static int launch_squeeze(pia_trie *t, cudaStream_t s) {
+  const int grid = t->dev.max_resident < 4 * t->n_sm ? t->dev.max_resident : 4 * t->n_sm;
+  k_squeeze<<<grid, NT, 0, s>>>(t->dev);
+  PIA_LAUNCH_CHECK();
+  k_squeeze_finish<<<1, 1, 0, s>>>(t->dev);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+static int put_common(pia_trie *t, const int32_t *d_tokens, int n, const int32_t *d_n, int B, int mode, int idx,
+                      int final, int is_stream, cudaStream_t s) {
+  PIA_REQUIRE(t, "null trie");
+  PIA_REQUIRE(n >= 0 && n <= t->cfg.max_put_tokens, "token list of %d exceeds max_put_tokens=%d", n, t->cfg.max_put_tokens);
+  PIA_REQUIRE(n == 0 || d_tokens, "null tokens");
+  PIA_REQUIRE(B >= 1 && B <= 64, "branch_length %d outside [1,64]", B);
+  PIA_REQUIRE(mode == PIA_MODE_INPUT || mode == PIA_MODE_OUTPUT, "put mode must be input or output");
+  if (mode == PIA_MODE_INPUT) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
+  const int slot = is_stream ? idx : 0;
+  if (is_stream) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "stream idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
+  k_put_prepare<<<1, NT, 0, s>>>(t->dev, d_tokens, n, d_n, B, is_stream, final, slot);
+  PIA_LAUNCH_CHECK();
+  const int max_pos = is_stream ? n + 64 : n;
+  if (max_pos > 0) {
+    const int grid = (max_pos + (NT / 32) - 1) / (NT / 32);
+    k_put_insert<<<grid, NT, 0, s>>>(t->dev, d_tokens, B, mode, idx, is_stream, slot);
+    PIA_LAUNCH_CHECK();
+  }
+  if (is_stream) {
+    k_put_finish<<<1, 128, 0, s>>>(t->dev, B, final, slot);
+    PIA_LAUNCH_CHECK();
+  }
+  if (final) {
+    int rc = launch_reset(t, idx < 0 ? 0 : idx, s);
+    if (rc) return rc;
+    rc = launch_squeeze(t, s);
+    if (rc) return rc;
+  }
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n, int branch_length,
+                            int mode, int idx, int final, void *stream) {
+  return put_common(t, d_tokens, n, d_n, branch_length, mode, idx, final, 0, (cudaStream_t)stream);
+}
+extern "C" int pia_trie_tree_put(pia_trie_t *t, int tree_token, const int32_t *d_tokens, int n, int mode, int idx,
+                                 void *stream) {
+  PIA_REQUIRE(t && tree_token >= 0 && tree_token < t->cfg.vocab_capacity, "bad tree token");
+  PIA_REQUIRE(n >= 0 && (n == 0 || d_tokens), "bad tokens");
+  PIA_REQUIRE(mode == PIA_MODE_INPUT || mode == PIA_MODE_OUTPUT, "put mode must be input or output");
+  if (mode == PIA_MODE_INPUT) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "bad idx");
+  k_tree_put<<<1, 32, 0, (cudaStream_t)stream>>>(t->dev, tree_token, d_tokens, n, mode, idx);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+extern "C" int pia_trie_stream_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n,
+                                   int branch_length, int idx, int final, void *stream) {
+  return put_common(t, d_tokens, n, d_n, branch_length, PIA_MODE_OUTPUT, idx, final, 1, (cudaStream_t)stream);
+}
+
+extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32_t *d_qlen, int batch, int q_stride,
+                            int max_query_length, const int32_t *d_idx, int idx, int decoding_length,
+                            int branch_length, int min_input_size, int min_output_size, int mode, int kind, int flags,
+                            int max_seq_length, int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n,
+                            int32_t *d_out_sizes, int32_t *d_out_nsizes, int32_t *d_status, void *stream) {
+  PIA_REQUIRE(t, "null trie");
+  PIA_REQUIRE(batch >= 1 && d_queries && d_qlen, "bad query batch");
+  PIA_REQUIRE(decoding_length >= 1 && decoding_length <= 128, "decoding_length %d outside [1,128]", decoding_length);
+  PIA_REQUIRE(branch_length >= 0 && branch_length <= 32, "branch_length %d outside [0,32]", branch_length);
+  PIA_REQUIRE(mode >= 0 && mode <= 2 && (kind == PIA_GET_HIER || kind == PIA_GET_ONE), "bad mode/kind");
+  PIA_REQUIRE(min_input_size >= 0 && min_output_size >= 0, "negative min sizes");
+  PIA_REQUIRE(d_idx || (idx >= 0 && idx < t->cfg.n_input_slots), "idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
+  PIA_REQUIRE(d_out_ids && d_out_mask && d_out_n && d_out_sizes && d_out_nsizes && d_status, "null output");
+  GetParams P;
+  P.queries = d_queries; P.qlen = d_qlen; P.d_idx = d_idx; P.batch = batch; P.q_stride = q_stride;
+  P.max_query = max_query_length > 0 ? max_query_length : q_stride; P.idx = idx; P.dl = decoding_length;
+  P.bl = branch_length; P.min_in = min_input_size; P.min_out = min_output_size; P.mode = mode; P.kind = kind;
+  P.flags = flags; P.max_seq = max_seq_length;
+  P.out_ids = d_out_ids; P.out_mask = (unsigned long long *)d_out_mask; P.out_n = d_out_n; P.out_sizes = d_out_sizes;
+  P.out_nsizes = d_out_nsizes; P.status = d_status;
+  const int grid = batch < t->dev.max_resident ? batch : t->dev.max_resident;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (decoding_length <= 64 && branch_length <= 16) k_get<64, 16><<<grid, NT, sizeof(GetSmem<64, 16>), s>>>(t->dev, P);
+  else k_get<128, 32><<<grid, NT, sizeof(GetSmem<128, 32>), s>>>(t->dev, P);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_reset_input_freqs(pia_trie_t *t, int idx, void *stream) {
+  PIA_REQUIRE(t && idx >= 0 && idx < t->cfg.n_input_slots, "bad idx");
+  return launch_reset(t, idx, (cudaStream_t)stream);
+}
+extern "C" int pia_trie_squeeze_branch_counts(pia_trie_t *t, void *stream) {
+  PIA_REQUIRE(t, "null trie");
+  return launch_squeeze(t, (cudaStream_t)stream);
+}
+extern "C" int pia_trie_fresh(pia_trie_t *t, void *stream) {
+  PIA_REQUIRE(t, "null trie");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_fresh<<<t->n_sm, NT, 0, s>>>(t->dev);
+  PIA_LAUNCH_CHECK();
+  k_fresh_finish<<<1, 1, 0, s>>>(t->dev);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_stats(pia_trie_t *t, pia_trie_stats_t *o, void *stream) {
+  PIA_REQUIRE(t && o, "null argument");
+  Hdr h;
+  PIA_CUDA_CHECK(cudaMemcpyAsync(&h, t->dev.hdr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PIA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  o->nodes_used = (int64_t)h.node_top; o->edges_used = (int64_t)h.edge_top; o->n_trees = h.n_trees;
+  o->n_update_trees = h.n_upd + h.n_upd_stale; o->n_update_input_trees = h.n_updin; o->error_flags = h.err;
+  o->nodes_visited = (int64_t)h.nodes_visited; o->edges_visited = (int64_t)h.edges_visited;
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_node, int64_t *h_n_output_node,
+                                      void *stream) {
+  PIA_REQUIRE(t && token >= 0 && token < t->cfg.vocab_capacity, "bad token");
+  cudaStream_t s = (cudaStream_t)stream;
+  int root = -1, a = 0, b = 0;
+  PIA_CUDA_CHECK(cudaMemcpyAsync(&root, t->dev.root_of + token, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(&a, t->dev.tree_n_node + token, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(&b, t->dev.tree_n_out + token, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h_n_node) *h_n_node = root < 0 ? -1 : a;
+  if (h_n_output_node) *h_n_output_node = root < 0 ? -1 : b;
+  return PIA_OK;
+}

@@ -1,0 +1,130 @@
+# -*- coding: utf-8 -*-
+"""Parity of the CUDA trie (csrc/trie.cu through the C ABI) with the reference:
+ * the reference's own unit vectors (lookahead/tests/test_lookahead_cache.py:16-45) through the Tree mirror,
+ * op streams recorded from the live reference (tests/golden/*.json),
+ * seeded differential streams against the CPU oracle at sizes the fixtures cannot hold."""
+import numpy as np
+import pytest
+
+from tests import replay as R
+
+pytestmark = pytest.mark.gpu
+
+STREAMS = ['trie_survey_a1.json', 'trie_small_v12.json', 'trie_small_v6_stop.json', 'trie_small_v30_batch.json',
+           'trie_small_v8_dl128.json', 'trie_squeeze.json', 'trie_zipf.json']
+
+
+def _gpu_cache_cls():
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    return LookaheadCache
+
+
+def _stats(c):
+    s = c.stats()
+    assert s['error_flags'] == 0, s
+    return {'n_trees': s['n_trees'], 'n_update_trees': s['n_update_trees']}
+
+
+def test_reference_unit_vectors_literal():
+    from painlessinferenceacceleration_b200.common.lookahead_cache import Tree
+    tree = Tree(1)
+    tree.put([1, 2, 3, 4], mode='output', idx=-1)
+    ids, mask, sizes = tree.get([1], max_size=63, max_length=8, min_input_size=0, min_output_size=0,
+                                output_weight=1e-4, mode='mix', idx=0)
+    assert ids == [1, 2, 3, 4], ids
+    assert mask.shape == (4, 4)
+    assert np.sum(np.abs(mask - np.array([[1, 0, 0, 0], [1, 1, 0, 0], [1, 1, 1, 0], [1, 1, 1, 1]]))) == 0, mask
+    tree = Tree(1)
+    tree.put([1, 2, 3], mode='output', idx=-1)
+    tree.put([1, 2, 4], mode='output', idx=-1)
+    ids, mask, sizes = tree.get([1], max_size=63, max_length=8, min_input_size=0, min_output_size=0,
+                                output_weight=1e-4, mode='mix', idx=0)
+    assert ids == [1, 2, 3, 4], ids
+    assert np.sum(np.abs(mask - np.array([[1, 0, 0, 0], [1, 1, 0, 0], [1, 1, 1, 0], [1, 1, 0, 1]]))) == 0, mask
+    assert tree.n_node == 4 and tree.n_output_node == 4
+
+
+@pytest.mark.parametrize('name', STREAMS)
+def test_recorded_streams(name):
+    fx = R.load(name)
+    cache = R.make_cache(_gpu_cache_cls(), fx['ctor'])
+    n = R.replay(cache, fx['ops'], stats_fn=_stats, tag=name)
+    assert n > 0
+    assert cache.stats()['error_flags'] == 0
+
+
+def _random_stream(seed, V, n_req, stop=(), dl=64, bl=8, zipf=False):
+    """yields op tuples; the same generator drives oracle and GPU"""
+    rng = np.random.default_rng(seed)
+
+    def toks(k):
+        if zipf:
+            return np.clip(rng.zipf(1.3, size=k), 3, V - 1).tolist()
+        return rng.integers(0, V, size=k).tolist()
+
+    ops = []
+    for req in range(n_req):
+        prompt = toks(int(rng.integers(2, 200)))
+        ops.append(('put', prompt[1:], bl + 1, False, 'input', 0))
+        seq = list(prompt)
+        for _ in range(int(rng.integers(1, 30))):
+            ops.append(('hier_get', seq[-2:], dl, bl, 0, dl // 2, 'mix', 0))
+            if rng.random() < 0.1:
+                ops.append(('hier_get', seq[-2:], dl, bl, 0, 0, str(rng.choice(['input', 'output'])), 0))
+            if rng.random() < 0.1:
+                ops.append(('one_get', seq[-2:], dl, bl, 0, 0, 'mix', 0))
+            new = toks(int(rng.integers(1, bl + 2)))
+            seq.extend(new)
+            ops.append(('stream_put', new, bl + 1, False, 'output', 0))
+        ops.append(('stream_put', [], bl + 1, True, 'output', 0))
+        if req % 5 == 0:
+            ops.append(('put', toks(int(rng.integers(2, 300))), bl + 1, False, 'output', -1))
+    return ops
+
+
+@pytest.mark.parametrize('seed,V,n_req,zipf', [(11, 9, 60, False), (12, 300, 60, False), (13, 32000, 80, True),
+                                               (14, 5, 40, False)])
+def test_differential_vs_oracle(seed, V, n_req, zipf):
+    from oracle.trie import OracleLookaheadCache
+    gpu = _gpu_cache_cls()(eos_ids=[2])
+    cpu = OracleLookaheadCache(eos_ids=[2])
+    checked = 0
+    for k, op in enumerate(_random_stream(seed, V, n_req, zipf=zipf)):
+        name = op[0]
+        if name in ('put', 'stream_put'):
+            _, ids, b, final, mode, idx = op
+            for c in (cpu, gpu):
+                getattr(c, name)(list(ids), branch_length=b, final=final, mode=mode, idx=idx)
+        else:
+            _, q, dl, b, mi, mo, mode, idx = op
+            outs = []
+            for c in (cpu, gpu):
+                ids, m, sizes = getattr(c, name)(list(q), decoding_length=dl, branch_length=b, min_input_size=mi,
+                                                 min_output_size=mo, mode=mode, idx=idx)
+                outs.append(([int(x) for x in ids], R.mask_rows(m), [int(x) for x in sizes]))
+            assert outs[0] == outs[1], f'op#{k} {op}\n cpu={outs[0]}\n gpu={outs[1]}'
+            checked += 1
+    assert checked > 50
+    s = gpu.stats()
+    assert s['error_flags'] == 0 and s['n_trees'] == cpu.n_trees()
+
+
+def test_batched_get_matches_single():
+    """4096 concurrent hier_get rows in one launch give the same rows as one-at-a-time calls (the roofline
+    benchmark's batched scan uses this path)"""
+    LookaheadCache = _gpu_cache_cls()
+    rng = np.random.default_rng(5)
+    c = LookaheadCache(eos_ids=[2])
+    docs = [np.clip(rng.zipf(1.3, size=256), 3, 31999).tolist() for _ in range(64)]
+    for d in docs:
+        c.put(d, branch_length=9, mode='output', idx=-1)
+    qs = []
+    for _ in range(512):
+        d = docs[int(rng.integers(0, len(docs)))]
+        j = int(rng.integers(0, len(d) - 2))
+        qs.append(d[j:j + 2])
+    from painlessinferenceacceleration_b200 import _lib as L
+    rows = c._get_batch(qs, 64, 8, 0, 32, 'mix', [0] * len(qs), L.GET_HIER)
+    for q, row in zip(qs[:64], rows[:64]):
+        ids, m, sizes = c.hier_get(q, decoding_length=64, branch_length=8, min_output_size=32)
+        assert ids == row[0] and np.array_equal(m, row[1]) and sizes == row[2]
