@@ -165,13 +165,15 @@ int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint
  * If d_residual_in != NULL: x <- x + residual_in first and the sum is written to d_residual_out. */
 int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows, int hidden,
                 void *d_residual_out, void *d_y, void *stream);
-/* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; positions = P - pad_len + depth
- * = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection output).
- * Writes q (rotated) to d_q_out [rows, Hq, D] and K (rotated) / V to cache rows P + i of `layer`. */
+/* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; position of node i =
+ * P - pad_len + depth_i = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection
+ * output).  d_cos / d_sin : [max_pos, D/2] bf16 tables (cos/sin already rounded to the model dtype exactly as
+ * LlamaRotaryEmbedding.forward :111-127 returns them).  Writes q (rotated) to d_q_out [rows, Hq, D] and
+ * K (rotated) / V to cache rows P + i of the layer's [Hkv, max_seq, D] planes. */
 int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const int32_t *d_n,
                        const int32_t *d_prefix_len, int pad_len, int rows, int n_q_heads, int n_kv_heads, int head_dim,
-                       float rope_theta, void *d_q_out, void *d_k_cache_layer, void *d_v_cache_layer, int max_seq,
-                       void *stream);
+                       const void *d_cos, const void *d_sin, int max_pos, void *d_q_out, void *d_k_cache_layer,
+                       void *d_v_cache_layer, int max_seq, void *stream);
 /* SiLU(gate) * up (modeling_llama.py:185-186). d_gate_up : [rows, 2*inter] (gate | up) -> d_out [rows, inter] */
 int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *stream);
 /* embedding gather for the draft nodes: d_out[i] = table[d_ids[i]] (rows >= *d_n are zero filled) */

@@ -66,8 +66,8 @@ SYMBOLS = {
     'pia_attn_workspace_bytes': (C.c_int64, [vp]),
     'pia_tree_attn_fwd': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp, vp]),
     'pia_rmsnorm': (C.c_int, [vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
-    'pia_rope_kv_append': (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                     vp, vp, vp, C.c_int, vp]),
+    'pia_rope_kv_append': (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                     C.c_int, vp, vp, vp, C.c_int, vp]),
     'pia_silu_mul': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     'pia_embed_gather': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     'pia_accept': (C.c_int, [C.POINTER(AcceptConfig), vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp,

@@ -1,0 +1,194 @@
+// Elementwise pieces of the LOOKAHEAD verify forward (sm_100a), all HBM-bound, 16-byte vectorised:
+//   k_rmsnorm           models/llama/modeling_llama.py:76-90   (+ the residual add of the decoder layer :340-352)
+//   k_rope_kv_append    :156-169 apply_rotary_pos_emb at the tree positions of :587, and the KV-cache append
+//                       that replaces the reference's per-step torch.cat (:265-268)
+//   k_silu_mul          :185-186
+//   k_embed_gather      :582
+// Rounding points follow the reference's bf16 eager arithmetic (each torch op rounds to bf16) so that
+// the verify logits stay as close to the reference's as a different GEMM order allows.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace pia {
+namespace fused {
+
+__device__ __forceinline__ float bf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+union Pack8 { uint4 u; __nv_bfloat16 h[8]; };
+
+// one CTA per row; hidden % 8 == 0
+__global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const __nv_bfloat16 *res_in,
+                                                 const __nv_bfloat16 *w, float eps, int hidden,
+                                                 __nv_bfloat16 *res_out, __nv_bfloat16 *y) {
+  __shared__ float red[16];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int nvec = hidden >> 3;
+  const uint4 *xv = reinterpret_cast<const uint4 *>(x + (long long)row * hidden);
+  const uint4 *rv = res_in ? reinterpret_cast<const uint4 *>(res_in + (long long)row * hidden) : nullptr;
+  uint4 *rov = res_out ? reinterpret_cast<uint4 *>(res_out + (long long)row * hidden) : nullptr;
+  float ss = 0.f;
+  // hidden <= 8 * 512 * 2 : keep up to two vectors per thread in registers
+  Pack8 keep[2];
+  int cnt = 0;
+  for (int v = tid; v < nvec; v += 512) {
+    Pack8 a; a.u = xv[v];
+    if (rv) {
+      Pack8 r; r.u = rv[v];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a.h[j] = __float2bfloat16_rn(__bfloat162float(a.h[j]) + __bfloat162float(r.h[j]));
+    }
+    if (rov) rov[v] = a.u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float f = __bfloat162float(a.h[j]); ss += f * f; }
+    if (cnt < 2) keep[cnt] = a;
+    ++cnt;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)hidden + eps);
+  const uint4 *wv = reinterpret_cast<const uint4 *>(w);
+  uint4 *yv = reinterpret_cast<uint4 *>(y + (long long)row * hidden);
+  cnt = 0;
+  for (int v = tid; v < nvec; v += 512) {
+    Pack8 a;
+    if (cnt < 2) a = keep[cnt];
+    else {  // (only for hidden > 8192) recompute the residual sum
+      a.u = xv[v];
+      if (rv) { Pack8 r; r.u = rv[v];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a.h[j] = __float2bfloat16_rn(__bfloat162float(a.h[j]) + __bfloat162float(r.h[j])); }
+    }
+    ++cnt;
+    Pack8 ww; ww.u = wv[v];
+    Pack8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.h[j] = __float2bfloat16_rn(__bfloat162float(ww.h[j]) * (__bfloat162float(a.h[j]) * inv));
+    yv[v] = o.u;
+  }
+}
+
+// grid = rows; thread = one (head, 8-wide d chunk) of q | k | v
+__global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv, const unsigned long long *mask,
+                                                        int mask_words, const int *d_n, const int *d_prefix, int pad_len,
+                                                        int hq, int hkv, int hd, const __nv_bfloat16 *cos_t,
+                                                        const __nv_bfloat16 *sin_t, int max_pos, __nv_bfloat16 *q_out,
+                                                        __nv_bfloat16 *kc, __nv_bfloat16 *vc, int max_seq) {
+  const int i = blockIdx.x;
+  const int n = *d_n, P = *d_prefix;
+  if (i >= n) return;
+  int depth = -1;
+  for (int w = 0; w < mask_words; ++w) depth += __popcll(mask[(long long)i * mask_words + w]);
+  int pos = P - pad_len + depth;  // rowsum(attention_mask) - 1  (modeling_llama.py:587)
+  if (pos < 0) pos = 0;
+  if (pos >= max_pos) pos = max_pos - 1;
+  const int half = hd >> 1, cpr = hd >> 3;  // 16-byte chunks per head row
+  const int row_elems = (hq + 2 * hkv) * hd;
+  const __nv_bfloat16 *src = qkv + (long long)i * row_elems;
+  const int cache_row = P + i;
+  const int total = (hq + 2 * hkv) * cpr;
+  for (int c = threadIdx.x; c < total; c += blockDim.x) {
+    const int head = c / cpr, ch = c % cpr;
+    const int d0 = ch * 8;
+    Pack8 a; a.u = *reinterpret_cast<const uint4 *>(src + head * hd + d0);
+    if (head < hq + hkv) {  // q or k: x*cos + rotate_half(x)*sin, every product/sum rounded to bf16 like eager torch
+      const int dp = d0 < half ? d0 + half : d0 - half;
+      Pack8 b; b.u = *reinterpret_cast<const uint4 *>(src + head * hd + dp);
+      Pack8 cs, sn;
+      const int f0 = d0 % half;
+      cs.u = *reinterpret_cast<const uint4 *>(cos_t + (long long)pos * half + f0);
+      sn.u = *reinterpret_cast<const uint4 *>(sin_t + (long long)pos * half + f0);
+      Pack8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = __bfloat162float(a.h[j]);
+        const float r = d0 < half ? -__bfloat162float(b.h[j]) : __bfloat162float(b.h[j]);
+        o.h[j] = __float2bfloat16_rn(bf(x * __bfloat162float(cs.h[j])) + bf(r * __bfloat162float(sn.h[j])));
+      }
+      if (head < hq) *reinterpret_cast<uint4 *>(q_out + ((long long)i * hq + head) * hd + d0) = o.u;
+      else *reinterpret_cast<uint4 *>(kc + ((long long)(head - hq) * max_seq + cache_row) * hd + d0) = o.u;
+    } else {
+      *reinterpret_cast<uint4 *>(vc + ((long long)(head - hq - hkv) * max_seq + cache_row) * hd + d0) = a.u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_silu_mul(const __nv_bfloat16 *gu, int inter, __nv_bfloat16 *out) {
+  const int row = blockIdx.y;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v * 8 >= inter) return;
+  Pack8 g, u, o;
+  g.u = *reinterpret_cast<const uint4 *>(gu + (long long)row * 2 * inter + v * 8);
+  u.u = *reinterpret_cast<const uint4 *>(gu + (long long)row * 2 * inter + inter + v * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = __bfloat162float(g.h[j]);
+    const float s = bf(x / (1.f + expf(-x)));
+    o.h[j] = __float2bfloat16_rn(s * __bfloat162float(u.h[j]));
+  }
+  *reinterpret_cast<uint4 *>(out + (long long)row * inter + v * 8) = o.u;
+}
+
+__global__ void __launch_bounds__(256) k_embed_gather(const __nv_bfloat16 *table, const int *ids, const int *d_n,
+                                                      int hidden, __nv_bfloat16 *out) {
+  const int row = blockIdx.x;
+  const int n = *d_n;
+  const int nvec = hidden >> 3;
+  uint4 *dst = reinterpret_cast<uint4 *>(out + (long long)row * hidden);
+  if (row >= n) { for (int v = threadIdx.x; v < nvec; v += 256) dst[v] = make_uint4(0, 0, 0, 0); return; }
+  const uint4 *src = reinterpret_cast<const uint4 *>(table + (long long)ids[row] * hidden);
+  for (int v = threadIdx.x; v < nvec; v += 256) dst[v] = src[v];
+}
+
+}  // namespace fused
+}  // namespace pia
+
+using namespace pia;
+using namespace pia::fused;
+
+extern "C" int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows,
+                           int hidden, void *d_residual_out, void *d_y, void *stream) {
+  PIA_REQUIRE(d_x && d_weight && d_y && rows > 0 && hidden > 0 && hidden % 8 == 0, "bad rmsnorm arguments");
+  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, (const __nv_bfloat16 *)d_residual_in,
+                                                   (const __nv_bfloat16 *)d_weight, eps, hidden,
+                                                   (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const int32_t *d_n,
+                                  const int32_t *d_prefix_len, int pad_len, int rows, int n_q_heads, int n_kv_heads,
+                                  int head_dim, const void *d_cos, const void *d_sin, int max_pos, void *d_q_out,
+                                  void *d_k_cache_layer, void *d_v_cache_layer, int max_seq, void *stream) {
+  PIA_REQUIRE(d_qkv && d_mask && d_n && d_prefix_len && d_cos && d_sin && d_q_out && d_k_cache_layer && d_v_cache_layer,
+              "null argument");
+  PIA_REQUIRE(head_dim % 16 == 0 && rows > 0 && mask_words >= 1 && mask_words <= 2, "bad rope arguments");
+  k_rope_kv_append<<<rows, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)d_qkv, (const unsigned long long *)d_mask, mask_words, d_n, d_prefix_len, pad_len,
+      n_q_heads, n_kv_heads, head_dim, (const __nv_bfloat16 *)d_cos, (const __nv_bfloat16 *)d_sin, max_pos,
+      (__nv_bfloat16 *)d_q_out, (__nv_bfloat16 *)d_k_cache_layer, (__nv_bfloat16 *)d_v_cache_layer, max_seq);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *stream) {
+  PIA_REQUIRE(d_gate_up && d_out && rows > 0 && inter > 0 && inter % 8 == 0, "bad silu_mul arguments");
+  dim3 grid((inter / 8 + 255) / 256, rows);
+  k_silu_mul<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_gate_up, inter, (__nv_bfloat16 *)d_out);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden,
+                                void *d_out, void *stream) {
+  PIA_REQUIRE(d_table && d_ids && d_n && d_out && rows > 0 && hidden % 8 == 0, "bad embed arguments");
+  k_embed_gather<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_table, d_ids, d_n, hidden,
+                                                        (__nv_bfloat16 *)d_out);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}

@@ -1,0 +1,467 @@
+// Tree-masked attention for the LOOKAHEAD verify forward (sm_100a: TMA + tcgen05 + TMEM).
+//
+// Takes over the eager attention of the reference's patched models
+//   models/llama/modeling_llama.py:243-308 (QK^T/sqrt(d) + mask, fp32 softmax, PV) with the lookahead mask of
+//   :584-588 and common/pretrained_model.py:725-734 ([n, P+n] = visible prefix || tree mask).
+// The mask is never materialised: prefix keys [pad_len, P) are visible to every row, the n draft keys follow the
+// row's ancestor bit set (uint64 words, produced by the trie kernel) held in registers.
+//
+// One CTA = (KV split, head group).  A head group is one KV head's worth of rows packed into a single
+// UMMA M=128 tile: 2 query heads x 64 draft rows under GQA, 1 head otherwise (rows 64..127 idle for MHA/64).
+// Warp roles (192 threads):  warp 0 = TMA producer (K/V tiles of 128 keys, 2-stage ring),
+//                            warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
+//                            warps 2-5 = softmax / accumulate, one thread per row (TMEM lane == row).
+// Per 128-key tile:  S = Q K^T (8 x UMMA 128x128x16, fp32 in TMEM, double buffered)
+//                    -> thread-local online softmax in fp32 (no shuffles: a thread owns its row)
+//                    -> P (bf16) to shared memory in the UMMA K-major SWIZZLE_128B layout
+//                    -> O_tile = P V (8 x UMMA, V consumed MN-major straight from the TMA tile)
+//                    -> acc = acc * alpha + O_tile in registers.
+// Split partials (acc, m, l) go to a workspace; k_combine merges the splits and writes bf16.
+// HBM-bound by design (arithmetic intensity = rows per KV byte: 64 FLOP/B for MHA, 256 for GQA-4;
+// DESIGN.md gives the roofline).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace pia {
+namespace attn {
+
+constexpr int BM = 128;      // rows per CTA (UMMA M)
+constexpr int BN = 128;      // keys per tile (UMMA N of QK^T, K extent of PV)
+constexpr int HD = 128;      // head dim
+constexpr int NSTAGE = 2;
+constexpr int NTHREADS = 192;
+constexpr int SUB = 128 * 128;             // bytes of one [128 rows x 64 bf16] swizzle-128B sub-tile
+constexpr int TILE_BYTES = 2 * SUB;        // one 128 x 128 bf16 operand tile
+constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_K = 2 * TILE_BYTES, SMEM_V = SMEM_K + NSTAGE * TILE_BYTES;
+constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + alignment slack
+constexpr int TMEM_COLS = 512;
+constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M=128, N=128
+__device__ __forceinline__ constexpr uint32_t make_idesc(int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(BN >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Params {
+  const __nv_bfloat16 *q;  // [max_nodes, Hq, HD]
+  const unsigned long long *mask;
+  const int *d_n, *d_prefix;
+  float *ws_acc;           // [n_split, Hq, np, HD]
+  float *ws_m, *ws_l;      // [n_split, Hq, np]
+  int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  const uint32_t bar0 = base + SMEM_BAR;
+  const uint32_t bar_kv_full = bar0, bar_kv_empty = bar0 + 8 * NSTAGE, bar_s_full = bar0 + 16 * NSTAGE,
+                 bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 32);
+
+  const int split = blockIdx.x, group = blockIdx.y;
+  const int n = *p.d_n, P = *p.d_prefix;
+  const int L = P + n;
+  const int hq0 = group * p.heads_per_cta;
+  const int hkv = hq0 / (p.n_q_heads / p.n_kv_heads);
+  const int tiles_total = (L + BN - 1) / BN;
+  const int tps = (tiles_total + p.n_split - 1) / p.n_split;
+  const int t0 = split * tps;
+  int t1 = t0 + tps;
+  if (t1 > tiles_total) t1 = tiles_total;
+  const int ntile = t1 - t0;
+
+  const bool is_sm_thread = warp >= 2;
+  const int row = ((warp & 3) << 5) | lane;  // TMEM lane this softmax thread owns
+  const int hs = row / p.np, node = row % p.np;
+  const bool row_live = is_sm_thread && hs < p.heads_per_cta && node < n;
+
+  if (ntile <= 0) {  // nothing for this split: leave an empty partial
+    if (row_live) {
+      const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
+      p.ws_m[o] = -INFINITY;
+      p.ws_l[o] = 0.f;
+    }
+    return;
+  }
+
+  // ---- setup
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    mbar_init(bar_s_full, 1); mbar_init(bar_s_full + 8, 1);
+    mbar_init(bar_p_full, 128);
+    mbar_init(bar_o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // Q tile -> shared memory, UMMA K-major SWIZZLE_128B ([128 rows x 64] sub-tiles per d-half); idle rows = 0
+  for (int c = tid; c < BM * (HD / 8); c += NTHREADS) {
+    const int r = c >> 4, ch = c & 15;
+    const int rhs = r / p.np, rnode = r % p.np;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (rhs < p.heads_per_cta && rnode < n)
+      v = *reinterpret_cast<const uint4 *>(p.q + ((long long)rnode * p.n_q_heads + hq0 + rhs) * HD + ch * 8);
+    *reinterpret_cast<uint4 *>(sm + SMEM_Q + (ch >> 3) * SUB + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      const int plane = p.layer * p.n_kv_heads + hkv;
+      for (int i = 0; i < ntile; ++i) {
+        const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
+        const int key0 = (t0 + i) * BN;
+        const uint32_t kd = base + SMEM_K + s * TILE_BYTES, vd = base + SMEM_V + s * TILE_BYTES;
+        tma_load_3d(kd, &map_k, bar_kv_full + 8 * s, 0, key0, plane);
+        tma_load_3d(kd + SUB, &map_k, bar_kv_full + 8 * s, 64, key0, plane);
+        tma_load_3d(vd, &map_v, bar_kv_full + 8 * s, 0, key0, plane);
+        tma_load_3d(vd + SUB, &map_v, bar_kv_full + 8 * s, 64, key0, plane);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = make_idesc(0), IDESC_PV = make_idesc(1);
+      auto issue_qk = [&](int i) {
+        const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        mbar_wait(bar_kv_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t qa = base + SMEM_Q, ka = base + SMEM_K + s * TILE_BYTES;
+        const uint32_t d = tmem + ((i & 1) ? TM_S1 : TM_S0);
+#pragma unroll
+        for (int j = 0; j < HD / 16; ++j) {  // K-major operands: 32 B per k-block inside the 128 B swizzle row
+          const uint32_t off = (j >> 2) * SUB + (j & 3) * 32;
+          umma_bf16(d, make_desc(qa + off, 16, 1024), make_desc(ka + off, 16, 1024), IDESC_QK, j > 0);
+        }
+        umma_commit(bar_s_full + 8 * (i & 1));
+      };
+      issue_qk(0);
+      for (int i = 0; i < ntile; ++i) {
+        if (i + 1 < ntile) issue_qk(i + 1);  // S is double buffered: next QK^T overlaps this tile's softmax
+        const int s = i % NSTAGE;
+        mbar_wait(bar_p_full, i & 1);
+        tc_fence_after();
+        const uint32_t pa = base + SMEM_P, va = base + SMEM_V + s * TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < BN / 16; ++j) {
+          // A = P, K-major over keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (SBO 1024 B), d-halves 16 KB apart (LBO)
+          const uint32_t aoff = (j >> 2) * SUB + (j & 3) * 32;
+          umma_bf16(tmem + TM_O, make_desc(pa + aoff, 16, 1024), make_desc(va + j * 2048, SUB, 1024), IDESC_PV, j > 0);
+        }
+        umma_commit(bar_o_full);
+        umma_commit(bar_kv_empty + 8 * s);
+      }
+    }
+  } else {
+    // ================================================================ softmax + accumulate (one row per thread)
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    unsigned long long mrow[2] = {0ull, 0ull};
+    if (row_live) for (int w = 0; w < p.mask_words; ++w) mrow[w] = p.mask[(long long)node * p.mask_words + w];
+    float acc[HD];
+#pragma unroll
+    for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t v[32];
+    for (int i = 0; i < ntile; ++i) {
+      const int key0 = (t0 + i) * BN;
+      const uint32_t s_addr = tmem + lane_addr + ((i & 1) ? TM_S1 : TM_S0);
+      mbar_wait(bar_s_full + 8 * (i & 1), (i >> 1) & 1);
+      tc_fence_after();
+      const bool all_visible = (key0 >= p.pad_len) && (key0 + BN <= P);
+      auto visible = [&](int kk) -> bool {
+        if (kk < P) return kk >= p.pad_len;
+        const int j = kk - P;
+        return j < n && ((mrow[j >> 6] >> (j & 63)) & 1ull);
+      };
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]);
+          if (all_visible || visible(key0 + c * 32 + j)) m_tile = fmaxf(m_tile, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
+      // pass 2: p = exp2(s*scale - m), P -> smem (bf16, swizzled), row sum
+      float l_tile = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (all_visible || visible(key0 + c * 32 + j)) p0 = exp2f(__uint_as_float(v[j]) * p.scale_log2 - m_use);
+          if (all_visible || visible(key0 + c * 32 + j + 1)) p1 = exp2f(__uint_as_float(v[j + 1]) * p.scale_log2 - m_use);
+          const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+          // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
+          l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
+          pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&b);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {  // 4 x 16 B chunks = 32 keys
+          const int ch = c * 4 + q4;      // 16 B chunk index along the 128-key row
+          uint8_t *dst = sm + SMEM_P + (ch >> 3) * SUB + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
+          *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      fence_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
+      tc_fence_before();    // order our tcgen05.ld of S before the issuer's next MMA into this S buffer
+      mbar_arrive(bar_p_full);
+      // accumulate this tile's PV
+      mbar_wait(bar_o_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(tmem + lane_addr + TM_O + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = acc[c * 32 + j] * alpha + __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+    }
+    if (row_live) {
+      const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
+      p.ws_m[o] = m_run;
+      p.ws_l[o] = l_run;
+      float4 *dst = reinterpret_cast<float4 *>(p.ws_acc + o * HD);
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+  }
+}
+
+// merge the KV splits: out[node, head, :] = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)
+__global__ void __launch_bounds__(128) k_combine(const float *ws_acc, const float *ws_m, const float *ws_l,
+                                                 const int *d_n, int n_split, int n_q_heads, int np,
+                                                 __nv_bfloat16 *out) {
+  const int head = blockIdx.x, node = blockIdx.y * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (node >= *d_n) return;
+  float M = -INFINITY;
+  for (int s = 0; s < n_split; ++s) M = fmaxf(M, ws_m[((long long)s * n_q_heads + head) * np + node]);
+  float den = 0.f;
+  float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < n_split; ++s) {
+    const long long o = ((long long)s * n_q_heads + head) * np + node;
+    const float m = ws_m[o];
+    if (m == -INFINITY) continue;
+    const float w = exp2f(m - M);
+    den += ws_l[o] * w;
+    const float4 a = reinterpret_cast<const float4 *>(ws_acc + o * HD)[lane];
+    num.x += a.x * w; num.y += a.y * w; num.z += a.z * w; num.w += a.w * w;
+  }
+  const float inv = den > 0.f ? 1.f / den : 0.f;
+  __nv_bfloat162 lo = __floats2bfloat162_rn(num.x * inv, num.y * inv), hi = __floats2bfloat162_rn(num.z * inv, num.w * inv);
+  uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+  reinterpret_cast<uint2 *>(out + ((long long)node * n_q_heads + head) * HD)[lane] = pk;
+}
+
+}  // namespace attn
+}  // namespace pia
+
+// =====================================================================================================
+using namespace pia;
+using namespace pia::attn;
+
+struct pia_attn_plan {
+  pia_attn_config_t cfg;
+  CUtensorMap map_k, map_v;
+  int heads_per_cta, n_groups, n_split, mask_words;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_kv_map(CUtensorMap *m, void *base, const pia_attn_config_t &c) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void *ptr = nullptr;
+    PIA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    PIA_REQUIRE(ptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    fn = (EncodeTiledFn)ptr;
+  }
+  // cache viewed as [planes = n_layers * n_kv_heads][max_seq][head_dim] bf16, box = 64 d x 128 keys x 1 plane
+  cuuint64_t dims[3] = {(cuuint64_t)c.head_dim, (cuuint64_t)c.max_seq, (cuuint64_t)c.n_layers * c.n_kv_heads};
+  cuuint64_t strides[2] = {(cuuint64_t)c.head_dim * 2, (cuuint64_t)c.max_seq * c.head_dim * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PIA_ERR_CUDA; }
+  return PIA_OK;
+}
+
+extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cache, void *d_v_cache,
+                                    pia_attn_plan_t **out) {
+  PIA_REQUIRE(cfg && d_k_cache && d_v_cache && out, "null argument");
+  if (cfg->head_dim != HD) { set_error("head_dim %d: only 128 is built in this round", cfg->head_dim); return PIA_ERR_UNSUPPORTED; }
+  PIA_REQUIRE(cfg->max_nodes == 64 || cfg->max_nodes == 128, "max_nodes must be 64 or 128");
+  PIA_REQUIRE(cfg->n_q_heads > 0 && cfg->n_kv_heads > 0 && cfg->n_q_heads % cfg->n_kv_heads == 0, "bad head counts");
+  PIA_REQUIRE(cfg->max_seq > 0 && cfg->n_layers > 0, "bad cache shape");
+  PIA_REQUIRE((reinterpret_cast<uintptr_t>(d_k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_v_cache) & 15) == 0, "cache must be 16-byte aligned");
+  pia_attn_plan *p = new (std::nothrow) pia_attn_plan();
+  PIA_REQUIRE(p, "out of host memory");
+  p->cfg = *cfg;
+  const int G = cfg->n_q_heads / cfg->n_kv_heads;
+  p->heads_per_cta = (cfg->max_nodes == 64 && G % 2 == 0) ? 2 : 1;
+  p->n_groups = cfg->n_q_heads / p->heads_per_cta;
+  p->mask_words = cfg->max_nodes / 64;
+  int n_sm = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int max_tiles = (cfg->max_seq + BN - 1) / BN;
+  int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : (n_sm + p->n_groups - 1) / p->n_groups;
+  if (ns > max_tiles) ns = max_tiles;
+  if (ns < 1) ns = 1;
+  if (ns > 64) ns = 64;
+  p->n_split = ns;
+  int rc = encode_kv_map(&p->map_k, d_k_cache, *cfg);
+  if (rc == PIA_OK) rc = encode_kv_map(&p->map_v, d_v_cache, *cfg);
+  if (rc == PIA_OK) {
+    cudaError_t e = cudaFuncSetAttribute(k_tree_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
+  }
+  if (rc != PIA_OK) { delete p; return rc; }
+  *out = p;
+  return PIA_OK;
+}
+
+extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) { delete p; return PIA_OK; }
+
+extern "C" int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p) {
+  if (!p) return 0;
+  const int64_t rows = (int64_t)p->n_split * p->cfg.n_q_heads * p->cfg.max_nodes;
+  return rows * (HD + 2) * (int64_t)sizeof(float);
+}
+
+extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask,
+                                 const int32_t *d_n, const int32_t *d_prefix_len, int pad_len, float scale_mul,
+                                 void *d_out, void *d_workspace, void *stream) {
+  PIA_REQUIRE(p && d_q && d_mask && d_n && d_prefix_len && d_out && d_workspace, "null argument");
+  PIA_REQUIRE(layer >= 0 && layer < p->cfg.n_layers, "layer %d outside [0,%d)", layer, p->cfg.n_layers);
+  Params a;
+  const int64_t rows = (int64_t)p->n_split * p->cfg.n_q_heads * p->cfg.max_nodes;
+  a.q = (const __nv_bfloat16 *)d_q;
+  a.mask = (const unsigned long long *)d_mask;
+  a.d_n = d_n; a.d_prefix = d_prefix_len;
+  a.ws_acc = (float *)d_workspace;
+  a.ws_m = a.ws_acc + rows * HD;
+  a.ws_l = a.ws_m + rows;
+  a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
+  a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.pad_len = pad_len; a.max_seq = p->cfg.max_seq;
+  a.n_split = p->n_split;
+  a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_tree_attn<<<dim3(p->n_split, p->n_groups), NTHREADS, SMEM_TOTAL, s>>>(p->map_k, p->map_v, a);
+  PIA_LAUNCH_CHECK();
+  k_combine<<<dim3(p->cfg.n_q_heads, (p->cfg.max_nodes + 3) / 4), 128, 0, s>>>(a.ws_acc, a.ws_m, a.ws_l, d_n, p->n_split,
+                                                                              p->cfg.n_q_heads, p->cfg.max_nodes,
+                                                                              (__nv_bfloat16 *)d_out);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
