@@ -1,0 +1,98 @@
+# -*- coding: utf-8 -*-
+"""Thin typed wrappers over the C ABI (include/pia_b200.h) for torch tensors: raw device pointers + the current
+torch stream, nothing else. Every call is asynchronous and CUDA-graph capturable."""
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def rmsnorm(x, residual_in, weight, eps, residual_out, y):
+    rows, hidden = x.shape
+    L.check(L.load().pia_rmsnorm(_p(x), _p(residual_in), _p(weight), float(eps), rows, hidden, _p(residual_out),
+                                 _p(y), _s()))
+
+
+def rope_kv_append(qkv, mask, n, prefix_len, pad_len, n_q_heads, n_kv_heads, head_dim, cos, sin, q_out, k_layer,
+                   v_layer, max_seq):
+    rows = qkv.shape[0]
+    L.check(L.load().pia_rope_kv_append(_p(qkv), _p(mask), mask.shape[1], _p(n), _p(prefix_len), int(pad_len), rows,
+                                        n_q_heads, n_kv_heads, head_dim, _p(cos), _p(sin), cos.shape[0], _p(q_out),
+                                        _p(k_layer), _p(v_layer), max_seq, _s()))
+
+
+def silu_mul(gate_up, out):
+    rows, two_inter = gate_up.shape
+    L.check(L.load().pia_silu_mul(_p(gate_up), rows, two_inter // 2, _p(out), _s()))
+
+
+def embed_gather(table, ids, n, out):
+    rows, hidden = out.shape
+    L.check(L.load().pia_embed_gather(_p(table), _p(ids), _p(n), rows, hidden, _p(out), _s()))
+
+
+class AttnPlan(object):
+    """pia_attn_plan_t: TMA descriptors over one model's KV cache + split-KV workspace"""
+
+    def __init__(self, k_cache, v_cache, n_q_heads, n_kv_heads, head_dim, max_nodes, kv_split_max=0):
+        n_layers, hkv, max_seq, hd = k_cache.shape
+        assert hkv == n_kv_heads and hd == head_dim and k_cache.is_contiguous() and v_cache.is_contiguous()
+        self.cfg = L.AttnConfig(n_q_heads, n_kv_heads, head_dim, max_seq, max_nodes, n_layers, kv_split_max)
+        self.h = L.vp()
+        self.lib = L.load()
+        with torch.cuda.device(k_cache.device):
+            L.check(self.lib.pia_attn_plan_create(C.byref(self.cfg), _p(k_cache), _p(v_cache), C.byref(self.h)))
+            nbytes = self.lib.pia_attn_workspace_bytes(self.h)
+        self.workspace = torch.empty((nbytes // 4,), dtype=torch.float32, device=k_cache.device)
+        self._keep = (k_cache, v_cache)
+
+    def forward(self, layer, q, mask, n, prefix_len, pad_len, out, scale_mul=1.0):
+        L.check(self.lib.pia_tree_attn_fwd(self.h, layer, _p(q), _p(mask), _p(n), _p(prefix_len), int(pad_len),
+                                           float(scale_mul), _p(out), _p(self.workspace), _s()))
+
+    def close(self):
+        if self.h:
+            self.lib.pia_attn_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Accept(object):
+    """pia_accept + pia_kv_compact with their config/workspace"""
+
+    def __init__(self, vocab, max_nodes, repetition_penalty, eos_ids, max_length, device):
+        eos = [int(e) for e in (eos_ids or []) if e is not None][:8]
+        arr = (C.c_int32 * 8)(*(eos + [-1] * (8 - len(eos))))
+        self.cfg = L.AcceptConfig(vocab, max_nodes, float(repetition_penalty), len(eos), arr, int(max_length))
+        self.lib = L.load()
+        self.workspace = torch.empty((max(self.lib.pia_accept_workspace_bytes(C.byref(self.cfg)) // 4, 1),),
+                                     dtype=torch.int32, device=device)
+
+    def run(self, logits, ids, mask, n, seq, seq_len, pad_len, acc_tokens, acc_count, acc_nodes, prefix_len, finished):
+        L.check(self.lib.pia_accept(C.byref(self.cfg), _p(logits), _p(ids), _p(mask), mask.shape[1], _p(n), _p(seq),
+                                    _p(seq_len), seq.numel(), int(pad_len), _p(acc_tokens), _p(acc_count),
+                                    _p(acc_nodes), _p(prefix_len), _p(finished), _p(self.workspace), _s()))
+
+
+def kv_compact(k_cache, v_cache, acc_nodes, acc_count, prefix_len):
+    n_layers, hkv, max_seq, hd = k_cache.shape
+    L.check(L.load().pia_kv_compact(_p(k_cache), _p(v_cache), n_layers, hkv, max_seq, hd, _p(acc_nodes), _p(acc_count),
+                                    _p(prefix_len), _s()))
+
+
+def launch_count():
+    return int(L.load().pia_launch_count())

@@ -1,0 +1,379 @@
+# -*- coding: utf-8 -*-
+"""LookaheadPreTrainedModel: the reference's generation surface
+(/root/reference/lookahead/lookahead/common/pretrained_model.py: class :48, generate :108, lookahead_prepare_inputs
+:666-756, _lookahead_update_model_kwargs :764-892, _update_cache :894-945, lookahead_generation :947-1268,
+stream_generate :1323-1350) re-built B200-first.
+
+The reference loop crosses the host/device boundary several times per step (draft ids + n x n mask H2D, one argmax
++ .tolist() sync per accepted token, kv_idx H2D, a torch.cat of the whole KV cache per layer).  Here one decode step
+
+    trie get -> embed -> L x [rmsnorm, qkv GEMM, rope+kv-append, tree attention, o GEMM, rmsnorm, gate/up GEMM,
+    silu*mul, down GEMM] -> norm -> lm_head GEMM -> accept walk -> KV compaction -> trie stream_put
+
+runs entirely on the device from device-resident state (token sequence, lengths, KV cache, trie) and is replayed
+as ONE CUDA graph; the host reads back a single small pinned buffer (count, finished flag, accepted tokens) per
+step to drive streamers / stopping.  GEMMs are cuBLAS (plain library GEMMs); everything else is libpia_b200.so.
+There is no CPU fallback."""
+import time
+from threading import Thread
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .lookahead_cache import LookaheadCache
+from .lookahead_generation_utils import GenerationMode, LookaheadDecoderOnlyOutput
+
+
+class _Runtime(object):
+    """device-resident state of one model's draft-verify loop (built once per (max_seq, max_nodes))"""
+
+    def __init__(self, model, max_seq, max_nodes):
+        dev = model.device
+        self.device = dev
+        self.max_seq, self.max_nodes = int(max_seq), int(max_nodes)
+        g = model.geometry()
+        self.g = g
+        i32 = dict(dtype=torch.int32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        W = self.max_nodes // 64
+        R = self.max_nodes
+        self.k_cache = torch.zeros((g['n_layers'], g['n_kv_heads'], self.max_seq, g['head_dim']), **bf)
+        self.v_cache = torch.zeros_like(self.k_cache)
+        self.plan = ops.AttnPlan(self.k_cache, self.v_cache, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], R)
+        # draft (filled by the trie kernel or, for prefill chunks, by the host)
+        self.ids = torch.zeros((1, R), **i32)
+        self.mask = torch.zeros((1, R, W), dtype=torch.int64, device=dev)
+        self.n = torch.ones((1,), **i32)
+        self.sizes = torch.zeros((1, 2), **i32)
+        self.nsizes = torch.zeros((1,), **i32)
+        self.status = torch.zeros((1,), **i32)
+        self.draft = dict(ids=self.ids, mask=self.mask, n=self.n, sizes=self.sizes, nsizes=self.nsizes,
+                          status=self.status)
+        # sequence state
+        self.seq = torch.zeros((self.max_seq + 8,), **i32)
+        self.seq_len = torch.zeros((1,), **i32)
+        self.prefix_len = torch.zeros((1,), **i32)
+        self.finished = torch.zeros((1,), **i32)
+        self.acc_tokens = torch.zeros((R,), **i32)
+        self.acc_count = torch.zeros((1,), **i32)
+        self.acc_nodes = torch.zeros((R,), **i32)
+        # host-visible step record: [count, finished, n, status, tokens...]
+        self.record = torch.zeros((4 + R,), **i32)
+        self.record_host = torch.zeros((4 + R,), dtype=torch.int32).pin_memory()
+        # activations
+        hid, qkv_dim = g['hidden'], (g['n_q_heads'] + 2 * g['n_kv_heads']) * g['head_dim']
+        self.h = torch.zeros((R, hid), **bf)
+        self.resid = torch.zeros((R, hid), **bf)
+        self.y = torch.zeros((R, hid), **bf)
+        self.qkv = torch.zeros((R, qkv_dim), **bf)
+        self.q = torch.zeros((R, g['n_q_heads'], g['head_dim']), **bf)
+        self.attn = torch.zeros((R, g['n_q_heads'] * g['head_dim']), **bf)
+        self.logits = torch.zeros((R, g['vocab']), **bf)
+        self.rope_cos, self.rope_sin = model.rope_tables(self.max_seq + 8)
+        self.graphs = {}
+        self.accepts = {}
+        self.pad_len = 0
+
+    # -- prefill: the prompt is fed as chain drafts of <= max_nodes tokens through the same verify kernels
+    def chain_mask_rows(self):
+        R = self.max_nodes
+        rows = np.zeros((R, R // 64), dtype=np.uint64)
+        for i in range(R):
+            for w in range(R // 64):
+                lo = 64 * w
+                if i >= lo + 63:
+                    rows[i, w] = np.uint64(0xFFFFFFFFFFFFFFFF)
+                elif i >= lo:
+                    rows[i, w] = np.uint64((1 << (i - lo + 1)) - 1)
+        return torch.from_numpy(rows.view(np.int64)).to(self.device)
+
+
+class LookaheadPreTrainedModel(nn.Module):
+    """Base class of the patched models (reference :48). Subclasses implement geometry(), rope_tables() and
+    _verify_layers(rt) (the per-model forward over the static draft buffers)."""
+    _batch_generation = False
+    _stream_generation = False
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self._rt = None
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _runtime(self, max_seq, max_nodes):
+        rt = self._rt
+        if rt is None or rt.max_seq < max_seq or rt.max_nodes != max_nodes:
+            self._rt = None
+            rt = _Runtime(self, max(max_seq, 128), max_nodes)
+            self._rt = rt
+        return rt
+
+    def _decoding_args(self):
+        return ['decoding_kwargs']
+
+    def _get_generation_mode(self, do_sample, use_cache, decoding_kwargs):
+        """reference :55-106 (the branches reachable from this surface)"""
+        if use_cache and decoding_kwargs.get('use_lookahead', False) and decoding_kwargs.get('decoding_length', 64) > 1 \
+                and decoding_kwargs.get('branch_length', 12) > 0:
+            return GenerationMode.LOOKAHEAD_GENERATION
+        return GenerationMode.SAMPLE if do_sample else GenerationMode.GREEDY_SEARCH
+
+    # ------------------------------------------------------------------ generate (reference :108-664)
+    @torch.no_grad()
+    def generate(self, inputs=None, generation_config=None, logits_processor=None, stopping_criteria=None,
+                 prefix_allowed_tokens_fn=None, synced_gpus=None, assistant_model=None, streamer=None, **kwargs):
+        allowed = {'input_ids', 'attention_mask', 'position_ids', 'max_new_tokens', 'max_length', 'pad_token_id',
+                   'eos_token_id', 'use_cache', 'repetition_penalty', 'do_sample', 'return_dict_in_generate',
+                   'output_scores', 'decoding_kwargs', 'num_beams', 'temperature', 'top_k', 'top_p'}
+        unknown = [k for k in kwargs if k not in allowed]
+        if unknown:  # reference :1309-1317
+            raise ValueError(f'The following `model_kwargs` are not used by the model: {unknown} (note: typos in the'
+                             ' generate arguments will also show up in this list)')
+        if logits_processor or prefix_allowed_tokens_fn or assistant_model is not None:
+            raise NotImplementedError('custom logits processors / assistant models are outside the B200 hot path; '
+                                      'repetition_penalty is built in')
+        if kwargs.get('num_beams', 1) != 1:
+            raise NotImplementedError('beam search is not on the lookahead path')
+        input_ids = kwargs.get('input_ids', inputs)
+        assert input_ids is not None and input_ids.dim() == 2
+        gc = generation_config if generation_config is not None else getattr(self, 'generation_config', None)
+
+        def opt(name, default=None):
+            if name in kwargs and kwargs[name] is not None:
+                return kwargs[name]
+            v = getattr(gc, name, None) if gc is not None else None
+            return v if v is not None else default
+
+        decoding_kwargs = kwargs.get('decoding_kwargs', None)
+        if decoding_kwargs is None:
+            decoding_kwargs = getattr(gc, 'decoding_kwargs', None) if gc is not None else None
+        if decoding_kwargs is None:
+            decoding_kwargs = {}
+        do_sample = bool(opt('do_sample', False))
+        use_cache = bool(opt('use_cache', True))
+        max_new = opt('max_new_tokens')
+        max_length = input_ids.shape[1] + int(max_new) if max_new is not None else int(opt('max_length', 20))
+        eos = opt('eos_token_id', getattr(self.config, 'eos_token_id', None))
+        pad = opt('pad_token_id', getattr(self.config, 'pad_token_id', None))
+        mode = self._get_generation_mode(do_sample, use_cache, decoding_kwargs)
+        if mode == GenerationMode.SAMPLE or do_sample:
+            raise NotImplementedError('multinomial accept (pretrained_model.py:835-837) is SURVEY 8f-3, not built yet')
+        # the reference mutates the caller's dict (:362-372)
+        decoding_kwargs['generation_mode'] = mode
+        decoding_kwargs['do_sample'] = do_sample
+        decoding_kwargs['max_length'] = max_length
+        dl = decoding_kwargs.get('decoding_length', 64) if mode == GenerationMode.LOOKAHEAD_GENERATION else 0
+        decoding_kwargs['decoding_max_length'] = max_length + dl + (1 if dl else 0)
+        crit_max = getattr(stopping_criteria, 'max_length', None) if stopping_criteria is not None else None
+        if crit_max is not None:
+            max_length = min(max_length, int(crit_max))
+        return self.lookahead_generation(input_ids, logits_processor=None, stopping_criteria=None, max_length=max_length,
+                                         pad_token_id=pad, eos_token_id=eos,
+                                         output_scores=opt('output_scores', False),
+                                         return_dict_in_generate=opt('return_dict_in_generate', False),
+                                         streamer=streamer, attention_mask=kwargs.get('attention_mask'),
+                                         decoding_kwargs=decoding_kwargs,
+                                         repetition_penalty=float(opt('repetition_penalty', 1.0)))
+
+    # ------------------------------------------------------------------ the loop (reference :947-1268)
+    def _capture_step(self, rt, key, use_trie, dl, bl, mql, min_out, tmode, kind, max_length, accept):
+        """one decode step as a CUDA graph over the static buffers"""
+        trie = self.lookahead_cache
+
+        def step():
+            if use_trie:
+                # lookahead_prepare_inputs_for_generation :708-723 (query = last tokens of the device sequence)
+                trie.get_device(rt.seq, rt.seq_len, dl, bl, max_query_length=mql, min_input_size=0,
+                                min_output_size=min_out, mode=tmode, idx=0, kind=kind, max_seq_length=max_length,
+                                out=rt.draft)
+            else:  # plain greedy: the draft is the last token alone
+                rt.ids[0, 0:1] = rt.seq.gather(0, (rt.seq_len - 1).long())
+                rt.n.fill_(1)
+                rt.mask[0, 0, 0] = 1
+            self._verify_layers(rt)
+            accept.run(rt.logits, rt.ids, rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens,
+                       rt.acc_count, rt.acc_nodes, rt.prefix_len, rt.finished)
+            ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len)
+            if use_trie:  # :1203
+                trie.stream_put_device(rt.acc_tokens, rt.max_nodes, rt.acc_count, branch_length=self._put_bl,
+                                       final=False, idx=0)
+            rt.record[0:1] = rt.acc_count
+            rt.record[1:2] = rt.finished
+            rt.record[2:3] = rt.n
+            rt.record[3:4] = rt.status
+            rt.record[4:] = rt.acc_tokens
+            rt.record_host.copy_(rt.record, non_blocking=True)
+
+        # warm up (cuBLAS handles/workspaces, lazy attributes) on a side stream, then capture
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        rt.graphs[key] = g
+        return g
+
+    @torch.no_grad()
+    def lookahead_generation(self, input_ids, logits_processor=None, stopping_criteria=None, max_length=None,
+                             pad_token_id=None, eos_token_id=None, output_attentions=None, output_hidden_states=None,
+                             output_scores=None, return_dict_in_generate=None, synced_gpus=False, streamer=None,
+                             attention_mask=None, decoding_kwargs=None, repetition_penalty=1.0, **model_kwargs):
+        assert input_ids.size(0) == 1, 'the lookahead loop is per request (reference :1152)'
+        dev = self.device
+        torch.cuda.set_device(dev)
+        decoding_kwargs = decoding_kwargs if decoding_kwargs is not None else {}
+        if isinstance(eos_token_id, int):
+            eos_token_id = [eos_token_id]
+        use_trie = decoding_kwargs.get('generation_mode', GenerationMode.LOOKAHEAD_GENERATION) == \
+            GenerationMode.LOOKAHEAD_GENERATION and decoding_kwargs.get('use_lookahead', True)
+        dl = int(decoding_kwargs.get('decoding_length', 64)) if use_trie else 1
+        bl = int(decoding_kwargs.get('branch_length', 12)) if use_trie else 1
+        dmode = decoding_kwargs.get('decoding_mode', 'hier')
+        mql = int(decoding_kwargs.get('max_query_length', 2))
+        if dmode in ('hier', 'par', 'one'):
+            dmode = dmode + '_mix'  # :712-713
+        fmt, tmode = dmode.split('_')
+        if fmt == 'par':
+            raise NotImplementedError('par_get drafts are host-composed (lookahead_cache.py:441-488); SURVEY 8f-3')
+        assert dl <= 128 and bl <= 32, 'decoding_length <= 128 and branch_length <= 32 are built'
+        if max_length is None:
+            max_length = int(decoding_kwargs.get('max_length', 2048))
+        max_nodes = 64 if dl <= 64 else 128
+        prompt_len = input_ids.shape[1]
+        max_seq = max_length + dl + 1  # decoding_max_length (:1115)
+        rt = self._runtime(max_seq, max_nodes)
+
+        # init lookahead cache (:1086-1089)
+        if not hasattr(self, 'lookahead_cache') or self.lookahead_cache is None:
+            self.lookahead_cache = LookaheadCache(device=dev, vocab_capacity=max(self.geometry()['vocab'], 1024))
+        trie = self.lookahead_cache
+        trie.eos_ids = eos_token_id
+        trie.stop_words = decoding_kwargs.get('stop_words', {})
+        decoding_kwargs.update({'eos': eos_token_id[0] if eos_token_id is not None else 2, 'edls': [], 'dls': [],
+                                'fts': [], 'qts': []})
+        decoding_kwargs['max_length'] = max_length
+        decoding_kwargs['decoding_max_length'] = max_seq
+        self._put_bl = bl + 1
+
+        # left padding (:1123-1131): bs == 1, so a 2-D mask can only mark a padded prefix
+        pad_len = 0
+        if attention_mask is not None:
+            am = attention_mask.reshape(-1)[:prompt_len] if attention_mask.dim() == 2 else None
+            if am is not None:
+                nz = torch.nonzero(am.to('cpu') != 0)
+                pad_len = int(nz[0]) if nz.numel() else 0
+        rt.pad_len = pad_len
+
+        ts = time.time()
+        prompt = input_ids[0].to(device=dev, dtype=torch.int32)
+        rt.seq[:prompt_len] = prompt
+        rt.finished.zero_()
+        if use_trie:  # (:1153-1156)
+            trie.put_device(rt.seq[1:], max(prompt_len - 1, 0), None, branch_length=bl + 1, final=False, mode='input',
+                            idx=0)
+        key = (use_trie, dl, bl, mql, tmode, fmt, max_length, float(repetition_penalty),
+               tuple(eos_token_id or ()), pad_len)
+        # the accept config/workspace is referenced by the captured graph: it lives as long as the runtime
+        accept = rt.accepts.get(key)
+        if accept is None:
+            accept = ops.Accept(self.geometry()['vocab'], max_nodes, repetition_penalty, eos_token_id, max_length, dev)
+            rt.accepts[key] = accept
+        first = self._prefill(rt, prompt_len, accept)
+        new_tokens = [first]
+        decoding_kwargs['dls'].append(1)  # the prefill step counts as one fed token (:797-798)
+        decoding_kwargs['edls'].append(1)
+        if streamer is not None:
+            streamer.put(input_ids.cpu())
+            streamer.put(np.array([[first]]))
+        if use_trie:
+            trie.stream_put_device(rt.seq[prompt_len:], 1, None, branch_length=bl + 1, final=False, idx=0)
+        finished = (eos_token_id is not None and first in eos_token_id) or prompt_len + 1 >= max_length
+        te = time.time()
+        decoding_kwargs['fts'].append(te - ts)
+        ts = te
+
+        graph = rt.graphs.get(key)
+        min_out = max(dl // 2, 1)  # :710
+        while not finished:
+            if graph is None:
+                graph = self._capture_step(rt, key, use_trie, dl, bl, mql, min_out, tmode,
+                                           'hier' if fmt == 'hier' else 'one', max_length, accept)
+            graph.replay()
+            torch.cuda.current_stream().synchronize()
+            rec = rt.record_host
+            count, fin, n, status = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])
+            if status != 0:
+                from .. import _lib as L
+                L.check(status)
+            toks = rec[4:4 + count].tolist()
+            new_tokens.extend(toks)
+            decoding_kwargs['dls'].append(n)
+            decoding_kwargs['edls'].append(count)
+            decoding_kwargs['qts'].append(0.0)
+            if streamer is not None:
+                streamer.put(np.array([toks]))
+            if decoding_kwargs.get('debug_lookahead', False):
+                tok = decoding_kwargs.get('tokenizer', None)
+                words = '' if tok is None else tok.decode(toks)
+                print(f'decoding_length:{n} accept_length:{count} accept_token:{toks} accept_word:{words}')
+            finished = bool(fin)
+            te = time.time()
+            decoding_kwargs['fts'].append(te - ts)
+            ts = te
+        if use_trie:  # :1237-1238
+            trie.stream_put([], branch_length=bl + 1, final=True, mode='output', idx=0)
+        if streamer is not None:
+            streamer.end()
+        out_ids = torch.cat([input_ids.to(dev), torch.tensor([new_tokens], dtype=input_ids.dtype, device=dev)], dim=1)
+        if return_dict_in_generate:
+            kw = {k: decoding_kwargs[k] for k in ('dls', 'edls', 'fts', 'qts')}
+            return LookaheadDecoderOnlyOutput(sequences=out_ids, scores=() if output_scores else None, kwargs=kw)
+        return out_ids
+
+    def _prefill(self, rt, prompt_len, accept):
+        """prompt -> KV rows [0, prompt_len) and the first generated token (argmax of the last prompt row).
+        The prompt goes through the verify kernels as chain drafts of <= max_nodes tokens."""
+        R = rt.max_nodes
+        if not hasattr(rt, 'chain'):
+            rt.chain = rt.chain_mask_rows()
+        rt.mask[0].copy_(rt.chain)
+        pos = 0
+        while pos < prompt_len:
+            m = min(R, prompt_len - pos)
+            rt.ids[0, :m] = rt.seq[pos:pos + m]
+            rt.n.fill_(m)
+            rt.prefix_len.fill_(pos)
+            self._verify_layers(rt, last_only=(pos + m < prompt_len))
+            pos += m
+        # first token: (penalised) arg-max of the last row
+        rt.seq_len.fill_(prompt_len)
+        last = m - 1
+        from .. import _lib as L
+        import ctypes as C
+        L.check(L.load().pia_accept(C.byref(accept.cfg), rt.logits[last:].data_ptr(), rt.ids[0, last:].data_ptr(),
+                                    rt.chain[0:].data_ptr(), rt.mask.shape[2], rt.n.fill_(1).data_ptr(),
+                                    rt.seq.data_ptr(), rt.seq_len.data_ptr(), rt.seq.numel(), rt.pad_len,
+                                    rt.acc_tokens.data_ptr(), rt.acc_count.data_ptr(), rt.acc_nodes.data_ptr(),
+                                    rt.prefix_len.data_ptr(), rt.finished.data_ptr(), accept.workspace.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+        rt.prefix_len.fill_(prompt_len)
+        return int(rt.acc_tokens[0].item())
+
+    # ------------------------------------------------------------------ streaming (reference :1323-1350)
+    @torch.no_grad()
+    def stream_generate(self, inputs=None, generation_config=None, logits_processor=None, stopping_criteria=None,
+                        prefix_allowed_tokens_fn=None, synced_gpus=None, assistant_model=None, streamer=None,
+                        **kwargs):
+        generation_kwargs = dict(inputs=inputs, generation_config=generation_config, logits_processor=logits_processor,
+                                 stopping_criteria=stopping_criteria,
+                                 prefix_allowed_tokens_fn=prefix_allowed_tokens_fn, synced_gpus=synced_gpus,
+                                 assistant_model=assistant_model, streamer=streamer)
+        generation_kwargs.update(kwargs)
+        thread = Thread(target=self.generate, kwargs=generation_kwargs)
+        thread.start()
+        for words in streamer:
+            yield words

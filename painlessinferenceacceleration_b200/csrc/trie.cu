@@ -204,7 +204,7 @@ __device__ void warp_insert(const Dev &D, int key, const int *path, int len, boo
         D.fi_extra[(long long)(s - 1) * D.node_cap + base + k] = (!out_mode && idx == s) ? 1.0f : 0.0f;
     }
     // link
-    if (pn.n_child == 0) {
+    if (pn.n_child == 0 && pn.cap == 0) {
       if (lane == 0) { D.nodes[cur].child = (int)base; D.nodes[cur].n_child = 1; }
     } else if (pn.cap == 0) {  // inline -> block of 4
       long long off = -1;

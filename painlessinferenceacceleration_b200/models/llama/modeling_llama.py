@@ -1,0 +1,239 @@
+# -*- coding: utf-8 -*-
+"""Llama with the lookahead patch, B200-native.
+
+Reference: /root/reference/lookahead/lookahead/models/llama/modeling_llama.py
+  patch :584-588 (rank-4 mask -> position_ids = rowsum-1, additive mask), attention :243-308, RoPE :93-169,
+  RMSNorm :76-90, MLP :172-186, LM head :768-769.
+The module tree and parameter names are HF's (so checkpoints load unchanged); the forward over a draft of
+<= 64/128 tree nodes runs on static buffers:  fused QKV / gate-up cuBLAS GEMMs + libpia_b200 kernels
+(rmsnorm+residual, rope+kv-append into a preallocated cache, tcgen05 tree attention, silu*mul).  The rank-4 mask
+is never built: `mask` is the per-node ancestor bit set, the prefix is implicit."""
+import glob
+import json
+import os
+
+import torch
+from torch import nn
+
+from ...common import ops
+from ...common.pretrained_model import LookaheadPreTrainedModel
+
+
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6, device=None, dtype=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+        self.variance_epsilon = eps
+
+
+class LlamaAttention(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        hd = cfg.hidden_size // cfg.num_attention_heads
+        kv = getattr(cfg, 'num_key_value_heads', None) or cfg.num_attention_heads
+        kw = dict(bias=False, device=device, dtype=dtype)
+        self.q_proj = nn.Linear(cfg.hidden_size, cfg.num_attention_heads * hd, **kw)
+        self.k_proj = nn.Linear(cfg.hidden_size, kv * hd, **kw)
+        self.v_proj = nn.Linear(cfg.hidden_size, kv * hd, **kw)
+        self.o_proj = nn.Linear(cfg.num_attention_heads * hd, cfg.hidden_size, **kw)
+
+
+class LlamaMLP(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        kw = dict(bias=False, device=device, dtype=dtype)
+        self.gate_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, **kw)
+        self.up_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, **kw)
+        self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, **kw)
+
+
+class LlamaDecoderLayer(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        self.self_attn = LlamaAttention(cfg, device, dtype)
+        self.mlp = self._make_mlp(cfg, device, dtype)
+        self.input_layernorm = LlamaRMSNorm(cfg.hidden_size, cfg.rms_norm_eps, device, dtype)
+        self.post_attention_layernorm = LlamaRMSNorm(cfg.hidden_size, cfg.rms_norm_eps, device, dtype)
+
+    def _make_mlp(self, cfg, device, dtype):
+        return LlamaMLP(cfg, device, dtype)
+
+
+class LlamaModel(nn.Module):
+    layer_cls = LlamaDecoderLayer
+
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=device, dtype=dtype)
+        self.layers = nn.ModuleList([self.layer_cls(cfg, device, dtype) for _ in range(cfg.num_hidden_layers)])
+        self.norm = LlamaRMSNorm(cfg.hidden_size, cfg.rms_norm_eps, device, dtype)
+
+
+class LlamaForCausalLM(LookaheadPreTrainedModel):
+    model_cls = LlamaModel
+
+    def __init__(self, config, device=None, dtype=torch.bfloat16):
+        super().__init__(config)
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else 'meta'
+        assert dtype == torch.bfloat16, 'the B200 path computes in bf16'
+        self.model = self.model_cls(config, device, dtype)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False, device=device, dtype=dtype)
+        self._fused = False
+
+    # ------------------------------------------------------------------ weights
+    @torch.no_grad()
+    def init_weights(self, seed=0, std=0.02):
+        """random-init weights of the configured shape (there are no checkpoints offline)"""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed)
+        for name, p in self.named_parameters():
+            if name.endswith('layernorm.weight') or name.endswith('norm.weight'):
+                p.fill_(1.0)
+            else:
+                p.normal_(0.0, std, generator=gen)
+        return self
+
+    @classmethod
+    def from_pretrained(cls, path, torch_dtype=torch.bfloat16, device=None, **kwargs):
+        """HF checkpoint directory (config.json + *.safetensors / pytorch_model*.bin) -> model on the GPU"""
+        from transformers import AutoConfig
+        config = AutoConfig.from_pretrained(path)
+        model = cls(config, device=device, dtype=torch_dtype)
+        files = sorted(glob.glob(os.path.join(path, '*.safetensors')))
+        own = dict(model.named_parameters())
+        seen = set()
+        if files:
+            from safetensors.torch import load_file
+            shards = (load_file(f) for f in files)
+        else:
+            shards = (torch.load(f, map_location='cpu') for f in sorted(glob.glob(os.path.join(path, 'pytorch_model*.bin'))))
+        with torch.no_grad():
+            for sd in shards:
+                for k, v in sd.items():
+                    if k in own:
+                        own[k].copy_(v.to(torch_dtype))
+                        seen.add(k)
+        if 'lm_head.weight' not in seen and getattr(config, 'tie_word_embeddings', False):
+            with torch.no_grad():
+                model.lm_head.weight.copy_(model.model.embed_tokens.weight)
+            seen.add('lm_head.weight')
+        missing = [k for k in own if k not in seen]
+        if missing:
+            raise RuntimeError(f'checkpoint is missing {len(missing)} tensors, e.g. {missing[:4]}')
+        return model
+
+    def fuse(self):
+        """QKV and gate/up weights into single GEMM operands; the HF-named parameters become views of them"""
+        if self._fused:
+            return
+        for layer in self.model.layers:
+            a = layer.self_attn
+            w = torch.cat([a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data], dim=0).contiguous()
+            nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
+            a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data = w[:nq], w[nq:nq + nk], w[nq + nk:]
+            a.qkv_weight = w
+            self._fuse_mlp(layer)
+        self._fused = True
+
+    def _fuse_mlp(self, layer):
+        m = layer.mlp
+        w = torch.cat([m.gate_proj.weight.data, m.up_proj.weight.data], dim=0).contiguous()
+        ni = m.gate_proj.weight.shape[0]
+        m.gate_proj.weight.data, m.up_proj.weight.data = w[:ni], w[ni:]
+        m.gate_up_weight = w
+
+    # ------------------------------------------------------------------ geometry / tables
+    def geometry(self):
+        c = self.config
+        hd = c.hidden_size // c.num_attention_heads
+        return dict(n_layers=c.num_hidden_layers, hidden=c.hidden_size, n_q_heads=c.num_attention_heads,
+                    n_kv_heads=getattr(c, 'num_key_value_heads', None) or c.num_attention_heads, head_dim=hd,
+                    inter=c.intermediate_size, vocab=c.vocab_size)
+
+    def rope_tables(self, max_pos):
+        """cos/sin exactly as LlamaRotaryEmbedding.forward returns them (reference :100, :111-127): fp32 angles,
+        then cast to the model dtype"""
+        c = self.config
+        hd = c.hidden_size // c.num_attention_heads
+        theta = float(getattr(c, 'rope_theta', None) or (getattr(c, 'rope_parameters', None) or {}).get('rope_theta', 10000.0))
+        dev = self.device
+        inv_freq = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float().to(dev) / hd))
+        pos = torch.arange(max_pos, device=dev).float()
+        freqs = pos[:, None] * inv_freq[None, :]
+        return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
+
+    # ------------------------------------------------------------------ the verify forward on static buffers
+    def _mlp(self, rt, layer, y):
+        m = layer.mlp
+        gu = torch.mm(y, m.gate_up_weight.t())
+        act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=gu.dtype, device=gu.device)
+        ops.silu_mul(gu, act)
+        return torch.mm(act, m.down_proj.weight.t())
+
+    def _verify_layers(self, rt, last_only=False):
+        """embed -> decoder layers -> final norm -> lm_head over the draft in rt.ids / rt.mask / rt.n with
+        rt.prefix_len tokens already cached.  Writes rt.logits [max_nodes, vocab] (skipped when last_only)."""
+        self.fuse()
+        g = rt.g
+        mask = rt.mask[0]
+        eps = self.config.rms_norm_eps
+        ops.embed_gather(self.model.embed_tokens.weight, rt.ids, rt.n, rt.h)
+        x, resid_in = rt.h, None  # rmsnorm(x, resid_in) -> (resid = x + resid_in, y = norm(resid))
+        for li, layer in enumerate(self.model.layers):
+            ops.rmsnorm(x, resid_in, layer.input_layernorm.weight, eps, rt.resid, rt.y)
+            a = layer.self_attn
+            torch.mm(rt.y, a.qkv_weight.t(), out=rt.qkv)
+            ops.rope_kv_append(rt.qkv, mask, rt.n, rt.prefix_len, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
+                               g['head_dim'], rt.rope_cos, rt.rope_sin, rt.q, rt.k_cache[li], rt.v_cache[li],
+                               rt.max_seq)
+            rt.plan.forward(li, rt.q, mask, rt.n, rt.prefix_len, rt.pad_len, rt.attn)
+            o = torch.mm(rt.attn, a.o_proj.weight.t())
+            ops.rmsnorm(o, rt.resid, layer.post_attention_layernorm.weight, eps, rt.resid, rt.y)
+            x = self._mlp(rt, layer, rt.y)
+            resid_in = rt.resid
+        if last_only:
+            return
+        ops.rmsnorm(x, resid_in, self.model.norm.weight, eps, rt.resid, rt.y)
+        torch.mm(rt.y, self.lm_head.weight.t(), out=rt.logits)
+
+    # ------------------------------------------------------------------ reference-shaped forward (API parity)
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, use_cache=True,
+                return_dict=True, **kwargs):
+        """The patched forward of the reference (:544-677, :710-790) for rank-4 lookahead masks
+        `[1, 1, n, P + n]` (visible prefix || tree).  `past_key_values` is the integer P returned by the previous
+        call (the KV cache itself is the model's preallocated device cache).  Returns (logits [1, n, V], P + n)."""
+        assert input_ids is not None and input_ids.shape[0] == 1
+        n = input_ids.shape[1]
+        P = int(past_key_values) if past_key_values is not None else 0
+        am = attention_mask
+        assert am is not None and am.dim() == 4 and am.shape[2] == n and am.shape[3] == P + n, \
+            'forward expects the lookahead mask [1,1,n,P+n] (modeling_llama.py:585-588)'
+        am = am[0, 0].to('cpu').long().numpy()
+        pad_len = 0
+        if P > 0:
+            nz = am[0, :P].nonzero()[0]
+            pad_len = int(nz[0]) if len(nz) else P
+        tree = am[:, P:]
+        rt = self._runtime(max(P + n + 1, 256), 64 if n <= 64 else 128)
+        assert n <= rt.max_nodes, 'at most 128 tree nodes per forward; prefill goes through generate()'
+        rows = torch.zeros((rt.max_nodes, rt.max_nodes // 64), dtype=torch.int64)
+        import numpy as np
+        bits = np.zeros((rt.max_nodes, rt.max_nodes // 64), dtype=np.uint64)
+        for i in range(n):
+            for j in np.flatnonzero(tree[i]):
+                bits[i, j >> 6] |= np.uint64(1) << np.uint64(j & 63)
+        rows = torch.from_numpy(bits.view(np.int64))
+        rt.mask[0].copy_(rows.to(rt.device))
+        rt.ids[0, :n] = input_ids[0].to(device=rt.device, dtype=torch.int32)
+        rt.n.fill_(n)
+        rt.prefix_len.fill_(P)
+        rt.pad_len = pad_len
+        self._verify_layers(rt)
+        logits = rt.logits[:n].clone()[None]
+        return logits, P + n
+
+
+class LlamaPreTrainedModel(LookaheadPreTrainedModel):
+    pass

@@ -1,0 +1,235 @@
+# -*- coding: utf-8 -*-
+"""Numerics of the verify-forward kernels against plain PyTorch fp32 restatements of the reference ops
+(models/llama/modeling_llama.py:76-90, 156-169, 185-186, 243-308; pretrained_model.py:764-892, 894-907)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _random_tree(rng, n, max_depth=8):
+    """parent array of a DFS-pre-order tree (like the trie emits) and its ancestor bit rows"""
+    parent = [-1]
+    depth = [0]
+    for i in range(1, n):
+        # attach to a node on the current rightmost path so that the order stays a valid pre-order
+        path = [i - 1]
+        while parent[path[-1]] >= 0:
+            path.append(parent[path[-1]])
+        cands = [p for p in path if depth[p] < max_depth]
+        p = cands[int(rng.integers(0, len(cands)))] if cands else 0
+        parent.append(p)
+        depth.append(depth[p] + 1)
+    rows = np.zeros((n,), dtype=np.uint64)
+    for i in range(n):
+        j = i
+        while j >= 0:
+            rows[i] |= np.uint64(1) << np.uint64(j)
+            j = parent[j]
+    return parent, depth, rows
+
+
+def _mask_tensor(rows, R):
+    m = np.zeros((R, max(R // 64, 1)), dtype=np.uint64)
+    m[:len(rows), 0] = rows
+    return torch.from_numpy(m.view(np.int64)).to(DEV)
+
+
+def _ref_attention(q, kc, vc, rows, n, P, pad_len, G):
+    """eager attention of the reference with the [n, P+n] lookahead mask; fp32 scores, probabilities rounded to
+    bf16 before PV exactly like modeling_llama.py:291-292"""
+    Hq, D = q.shape[1], q.shape[2]
+    L = P + n
+    vis = torch.zeros((n, L), dtype=torch.bool, device=q.device)
+    vis[:, pad_len:P] = True
+    for i in range(n):
+        for j in range(n):
+            if (int(rows[i]) >> j) & 1:
+                vis[i, P + j] = True
+    out = torch.zeros((n, Hq, D), dtype=torch.float32, device=q.device)
+    for h in range(Hq):
+        k = kc[h // G, :L].float()
+        v = vc[h // G, :L].float()
+        s = (q[:n, h].float() @ k.t()) / math.sqrt(D)
+        s = s.masked_fill(~vis, float('-inf'))
+        p = torch.softmax(s, dim=-1).to(torch.bfloat16).float()
+        out[:, h] = p @ v
+    return out
+
+
+@pytest.mark.parametrize('Hq,Hkv,P,n,pad', [(2, 2, 0, 64, 0), (4, 2, 37, 33, 0), (32, 32, 300, 64, 0),
+                                             (32, 8, 1000, 47, 5), (8, 2, 127, 1, 0), (8, 8, 129, 64, 3),
+                                             (32, 8, 2500, 64, 0)])
+def test_tree_attention(Hq, Hkv, P, n, pad):
+    from painlessinferenceacceleration_b200.common import ops
+    rng = np.random.default_rng(P + n)
+    torch.manual_seed(P * 7 + n)
+    D, R, n_layers = 128, 64, 2
+    max_seq = P + n + 70
+    kc = (torch.randn((n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    vc = (torch.randn((n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    q = (torch.randn((R, Hq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    _, _, rows = _random_tree(rng, n)
+    mask = _mask_tensor(rows, R)
+    plan = ops.AttnPlan(kc, vc, Hq, Hkv, D, R)
+    out = torch.zeros((R, Hq, D), dtype=torch.bfloat16, device=DEV)
+    dn = torch.tensor([n], dtype=torch.int32, device=DEV)
+    dP = torch.tensor([P], dtype=torch.int32, device=DEV)
+    for layer in (1, 0):
+        out.zero_()
+        plan.forward(layer, q, mask, dn, dP, pad, out)
+        torch.cuda.synchronize()
+        ref = _ref_attention(q, kc[layer], vc[layer], rows, n, P, pad, Hq // Hkv)
+        got = out[:n].float()
+        err = (got - ref).abs().max().item()
+        # tolerance: bf16 output rounding (2^-8 relative on |o| <~ 1) + fp32 accumulation order
+        assert torch.allclose(got, ref, atol=1.5e-2, rtol=2e-2), f'layer {layer} max abs err {err}'
+
+
+def test_rmsnorm_residual():
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(0)
+    for hidden in (256, 4096):
+        x = torch.randn((64, hidden), device=DEV).to(torch.bfloat16)
+        r = torch.randn((64, hidden), device=DEV).to(torch.bfloat16)
+        w = (1 + 0.1 * torch.randn((hidden,), device=DEV)).to(torch.bfloat16)
+        y = torch.empty_like(x)
+        ro = torch.empty_like(x)
+        ops.rmsnorm(x, r, w, 1e-6, ro, y)
+        s = (x.float() + r.float()).to(torch.bfloat16)
+        var = s.float().pow(2).mean(-1, keepdim=True)
+        ref = (w.float() * (s.float() * torch.rsqrt(var + 1e-6))).to(torch.bfloat16)  # modeling_llama.py:85-90
+        assert torch.equal(ro, s)
+        assert torch.allclose(y.float(), ref.float(), atol=1e-2, rtol=1e-2)
+        assert (y != ref).float().mean().item() < 0.01  # only last-bit rounding differences
+        ops.rmsnorm(x, None, w, 1e-6, ro, y)
+        assert torch.equal(ro, x)
+
+
+def test_rope_kv_append_and_silu():
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(1)
+    rng = np.random.default_rng(3)
+    Hq, Hkv, D, R, n, P, pad = 4, 2, 128, 64, 40, 77, 2
+    max_seq = 256
+    qkv = torch.randn((R, (Hq + 2 * Hkv) * D), device=DEV).to(torch.bfloat16)
+    _, depth, rows = _random_tree(rng, n)
+    mask = _mask_tensor(rows, R)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=DEV).float() / D))
+    ang = torch.arange(max_seq, device=DEV).float()[:, None] * inv[None]
+    cos, sin = ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous()
+    qo = torch.zeros((R, Hq, D), dtype=torch.bfloat16, device=DEV)
+    kc = torch.zeros((Hkv, max_seq, D), dtype=torch.bfloat16, device=DEV)
+    vc = torch.zeros_like(kc)
+    dn = torch.tensor([n], dtype=torch.int32, device=DEV)
+    dP = torch.tensor([P], dtype=torch.int32, device=DEV)
+    ops.rope_kv_append(qkv, mask, dn, dP, pad, Hq, Hkv, D, cos, sin, qo, kc, vc, max_seq)
+    torch.cuda.synchronize()
+    pos = torch.tensor([P - pad + d for d in depth], device=DEV)
+    c = torch.cat([cos[pos], cos[pos]], -1)[:, None]  # [n,1,D] bf16  (modeling_llama.py:124-127)
+    s = torch.cat([sin[pos], sin[pos]], -1)[:, None]
+
+    def rot(x):
+        return torch.cat([-x[..., D // 2:], x[..., :D // 2]], -1)
+
+    x = qkv[:n].view(n, Hq + 2 * Hkv, D)
+    qk = x[:, :Hq + Hkv]
+    ref = (qk * c) + (rot(qk) * s)  # bf16 eager arithmetic (:167-168)
+    assert torch.equal(qo[:n], ref[:, :Hq])
+    assert torch.equal(kc[:, P:P + n].transpose(0, 1), ref[:, Hq:])
+    assert torch.equal(vc[:, P:P + n].transpose(0, 1), x[:, Hq + Hkv:])
+    assert float(kc[:, :P].abs().sum()) == 0 and float(kc[:, P + n:].abs().sum()) == 0
+    gu = torch.randn((64, 2 * 1024), device=DEV).to(torch.bfloat16)
+    out = torch.empty((64, 1024), dtype=torch.bfloat16, device=DEV)
+    ops.silu_mul(gu, out)
+    ref = torch.nn.functional.silu(gu[:, :1024]) * gu[:, 1024:]
+    assert torch.allclose(out.float(), ref.float(), atol=1e-2, rtol=1e-2)
+    assert (out != ref).float().mean().item() < 0.01
+
+
+def _host_accept(ids, parent, row_tok):
+    cur, toks, nodes = 0, [], []
+    while True:
+        t = row_tok[cur]
+        toks.append(t)
+        nodes.append(cur)
+        nxt = [j for j in range(1, len(ids)) if parent[j] == cur and ids[j] == t]
+        if not nxt:
+            break
+        cur = nxt[0]
+    return toks, nodes
+
+
+@pytest.mark.parametrize('penalty', [1.0, 1.1])
+def test_accept_walk_and_kv_compact(penalty):
+    from painlessinferenceacceleration_b200.common import ops
+    rng = np.random.default_rng(17)
+    V, R = 1000, 64
+    for trial in range(12):
+        n = int(rng.integers(1, 65))
+        parent, depth, rows = _random_tree(rng, n)
+        ids = [int(rng.integers(3, 40))]
+        for j in range(1, n):  # siblings carry distinct tokens (dict keys)
+            used = {ids[k] for k in range(1, j) if parent[k] == parent[j]}
+            t = int(rng.integers(3, 40))
+            while t in used:
+                t = int(rng.integers(3, 40))
+            ids.append(t)
+        logits = torch.randn((R, V), device=DEV).to(torch.bfloat16)
+        # make the walk non-trivial: let most rows vote for one of their children
+        for j in range(n):
+            kids = [k for k in range(1, n) if parent[k] == j]
+            if kids and rng.random() < 0.8:
+                logits[j, ids[kids[int(rng.integers(0, len(kids)))]]] = 30.0
+        seq_len0 = 20
+        seq_host = rng.integers(3, 40, size=seq_len0).tolist()
+        seq = torch.zeros((256,), dtype=torch.int32, device=DEV)
+        seq[:seq_len0] = torch.tensor(seq_host, dtype=torch.int32)
+        seq[seq_len0 - 1] = ids[0]
+        seq_host[-1] = ids[0]
+        # host restatement of :827-860 with RepetitionPenaltyLogitsProcessor semantics
+        lf = logits.clone()
+        row_tok = []
+        for j in range(n):
+            sc = lf[j].clone()
+            if penalty != 1.0:
+                ctx = set(seq_host)
+                k = j
+                while k >= 1:
+                    ctx.add(ids[k])
+                    k = parent[k]
+                idx = torch.tensor(sorted(ctx), device=DEV)
+                v = sc[idx]
+                sc[idx] = torch.where(v < 0, v * penalty, v / penalty)
+            row_tok.append(int(torch.argmax(sc)))
+        toks, nodes = _host_accept(ids, parent, row_tok)
+        acc = ops.Accept(V, R, penalty, [2], 10 ** 6, DEV)
+        d = dict(ids=torch.zeros((R,), dtype=torch.int32, device=DEV), n=torch.tensor([n], dtype=torch.int32, device=DEV))
+        d['ids'][:n] = torch.tensor(ids, dtype=torch.int32)
+        mask = _mask_tensor(rows, R)
+        seq_len = torch.tensor([seq_len0], dtype=torch.int32, device=DEV)
+        P0 = seq_len0 - 1
+        prefix = torch.tensor([P0], dtype=torch.int32, device=DEV)
+        fin = torch.zeros((1,), dtype=torch.int32, device=DEV)
+        at = torch.zeros((R,), dtype=torch.int32, device=DEV)
+        ac = torch.zeros((1,), dtype=torch.int32, device=DEV)
+        an = torch.zeros((R,), dtype=torch.int32, device=DEV)
+        kc = torch.arange(2 * 2 * 128 * 16, device=DEV).float().view(2, 2, 128, 16).to(torch.bfloat16).contiguous()
+        vc = (kc.float() + 0.5).to(torch.bfloat16).contiguous()
+        k0, v0 = kc.clone(), vc.clone()
+        acc.run(logits, d['ids'], mask, d['n'], seq, seq_len, 0, at, ac, an, prefix, fin)
+        ops.kv_compact(kc, vc, an, ac, prefix)
+        torch.cuda.synchronize()
+        c = int(ac)
+        assert at[:c].tolist() == toks, (trial, at[:c].tolist(), toks)
+        assert an[:c].tolist() == nodes
+        assert int(seq_len) == seq_len0 + c and int(prefix) == P0 + c
+        assert seq[seq_len0:seq_len0 + c].tolist() == toks
+        assert int(fin) == (1 if 2 in toks else 0)
+        # rows [0, P0] untouched, accepted draft rows moved next to the prefix (:894-907)
+        keep = list(range(P0 + 1)) + [P0 + j for j in nodes[1:]]
+        assert torch.equal(kc[:, :, :len(keep)], k0[:, :, keep]) and torch.equal(vc[:, :, :len(keep)], v0[:, :, keep])
