@@ -1,0 +1,394 @@
+# -*- coding: utf-8 -*-
+"""bench.py -- accepted tokens/sec of the LOOKAHEAD draft-verify loop (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model llama2-7b|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one request through the hot path: a 256-token synthetic prompt -> greedy generation of 256 new tokens
+with 64-token / 8-branch trie drafts (BASELINE config 2).  Weights are random-init of the named shape
+(no checkpoints exist offline), prompts come from the seeded phrase bank of SURVEY.md 8d, the trie is warmed by W
+untimed requests exactly like the reference's benchmark warms it from earlier answers (benchmarks/benchmark.py:159-169).
+One JSON line is printed by rank 0; see the keys below.  N > 1 = independent data-parallel replicas (the loop is per
+request, pretrained_model.py:1152): one NCCL broadcast of the weights, then no collective on the data path.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    # name: (family, hidden, inter, layers, heads, kv_heads, vocab)
+    'llama2-7b': ('llama', 4096, 11008, 32, 32, 32, 32000),
+    'mistral-7b': ('mistral', 4096, 14336, 32, 32, 8, 32000),
+    'tiny': ('llama', 512, 1024, 4, 4, 4, 32000),
+}
+PROMPT_LEN, NEW_TOKENS, DL, BL = 256, 256, 64, 8
+
+
+def make_config(name):
+    from transformers import LlamaConfig, MistralConfig
+    fam, hid, inter, layers, heads, kv, vocab = MODELS[name]
+    kw = dict(vocab_size=vocab, hidden_size=hid, intermediate_size=inter, num_hidden_layers=layers,
+              num_attention_heads=heads, num_key_value_heads=kv, max_position_embeddings=4096, rms_norm_eps=1e-5,
+              bos_token_id=1, eos_token_id=2, pad_token_id=0)
+    return (MistralConfig(sliding_window=None, **kw) if fam == 'mistral' else LlamaConfig(**kw)), fam
+
+
+def phrase_bank_prompts(n, vocab, length=PROMPT_LEN, seed=1234):
+    """sequences drawn from 2000 phrases of 4-24 ids, ids Zipf(1.3) clipped to [3, V-1]"""
+    rng = np.random.default_rng(seed)
+    bank = [np.clip(rng.zipf(1.3, size=int(rng.integers(4, 25))), 3, vocab - 1) for _ in range(2000)]
+    out = []
+    for _ in range(n):
+        toks = []
+        while len(toks) < length:
+            toks.extend(bank[int(rng.integers(0, len(bank)))].tolist())
+        out.append(toks[:length])
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md clocks line), via NVML"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: 'hw_slowdown',
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                     nv.nvmlClocksThrottleReasonSwPowerCap: 'sw_power_cap',
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: 'hw_power_brake'}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f'nvml_unavailable:{type(e).__name__}')
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), 'measured'
+    return 6650.0, 1400.0, 'fallback'
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from painlessinferenceacceleration_b200.common import ops
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    assert world == args.gpus, f'--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)'
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg, fam = make_config(args.model)
+    model = LlamaForCausalLM(cfg, device=dev)
+    if rank == 0:
+        model.init_weights(seed=0)
+    if world > 1:  # the one collective of this path: weights from rank 0 over NVLink
+        for p in model.parameters():
+            dist.broadcast(p.data, src=0)
+    model.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
+    K, Wm = args.steps, args.warmup
+    allp = phrase_bank_prompts(64 + 8 * Wm, cfg.vocab_size)
+    timed = [allp[(rank * K + i) % 64] for i in range(K)]
+    warm = [allp[64 + (rank * Wm + i) % (8 * Wm)] for i in range(Wm)] if Wm else []
+    dk = {'use_lookahead': True, 'decoding_length': DL, 'branch_length': BL}
+    gen = dict(max_new_tokens=NEW_TOKENS, eos_token_id=2, decoding_kwargs=dk, return_dict_in_generate=True)
+    warm_outputs = []
+    for p in warm:  # untimed: CUDA graph capture, cuBLAS heuristics, trie warm-up
+        o = model.generate(input_ids=torch.tensor([p], device=dev), **gen)
+        warm_outputs.append(o.sequences[0, PROMPT_LEN:].tolist())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_pass(host_io):
+        ins = [torch.tensor([p]).pin_memory() if host_io else torch.tensor([p], device=dev) for p in timed]
+        toks, edls, outs = 0, [], []
+        l0 = ops.launch_count()
+        r0 = model._rt.replays
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for x in ins:
+            o = model.generate(input_ids=x.to(dev, non_blocking=True) if host_io else x, **gen)
+            seq = o.sequences.cpu() if host_io else o.sequences
+            outs.append(seq)
+            toks += seq.shape[1] - PROMPT_LEN
+            edls += o.kwargs['edls'][1:]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = (ops.launch_count() - l0) + (model._rt.replays - r0) * model._rt.kernels_per_graph
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            agg = torch.tensor([float(toks), float(sum(edls)), float(len(edls)), float(launches)], device=dev)
+            dist.all_reduce(agg)
+            toks, s_e, n_e, launches = (float(v) for v in agg)
+        else:
+            s_e, n_e = float(sum(edls)), float(len(edls))
+        return dict(ms=ms, tokens=toks, mean_edl=s_e / max(n_e, 1), steps=n_e, launches=int(launches), outs=outs)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    res = timed_pass(host_io=False)
+    e2e = timed_pass(host_io=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    roof = attention_roofline(model, dev) if rank == 0 else None
+    trie_roof = trie_roofline(dev) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, warm_outputs, timed[0])
+    if rank == 0:
+        hbm, _tf, src = peaks()
+        line = {
+            'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
+            'value': res['tokens'] / (res['ms'] / 1e3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': res['ms'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic (phrase-bank prompts, random-init weights of the named shape)',
+            'mean_accepted_len_per_step': res['mean_edl'], 'verify_steps': res['steps'],
+            'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft, '
+                                   f'{PROMPT_LEN}-token prompt -> {NEW_TOKENS} new tokens, 1 request per step per GPU',
+                       'l2': 'inputs larger than L2: every verify step streams the full weight set (>= 13 GB) and the '
+                             'KV cache of all layers',
+                       'parallelism': f'{world} independent replicas' if world > 1 else 'single GPU',
+                       'peaks': src},
+            'clocks': sampler.summary(),
+            'e2e': {'value': e2e['tokens'] / (e2e['ms'] / 1e3), 'unit': 'tokens/s',
+                    'h2d_bytes_per_step': PROMPT_LEN * 8,
+                    'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (4 + DL)),
+                    'mean_accepted_len_per_step': e2e['mean_edl']},
+            'gpu_launches': res['launches'],
+            'roofline': roof, 'roofline_trie_get': trie_roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def attention_roofline(model, dev):
+    """k_tree_attn alone at the benchmark shape: 64 draft rows, prefix ~ mid-generation, all layers in turn (the
+    layers' KV planes together exceed L2, so every launch reads cold HBM).  CUDA events on the launch stream."""
+    import torch
+    rt = model._rt
+    g = rt.g
+    P, n = PROMPT_LEN + NEW_TOKENS // 2, DL
+    rt.n.fill_(n)
+    rt.prefix_len.fill_(P)
+    rt.mask[0].copy_(rt.chain if hasattr(rt, 'chain') else rt.chain_mask_rows())
+    L = P + n
+    reps = 20
+    for li in range(g['n_layers']):
+        rt.plan.forward(li, rt.q, rt.mask[0], rt.n, rt.prefix_len, 0, rt.attn)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for li in range(g['n_layers']):
+            rt.plan.forward(li, rt.q, rt.mask[0], rt.n, rt.prefix_len, 0, rt.attn)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * g['n_layers'])
+    # algorithmic bytes per launch: K,V rows of every KV head + Q read + O write
+    by = 2 * L * g['n_kv_heads'] * g['head_dim'] * 2 + 2 * n * g['n_q_heads'] * g['head_dim'] * 2
+    hbm, _tf, src = peaks()
+    ach = by / (us * 1e-6) / 1e9
+    return {'kernel': 'k_tree_attn+k_combine (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
+            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'us_per_launch': us,
+            'shape': f'n={n} P={P} Hq={g["n_q_heads"]} Hkv={g["n_kv_heads"]} D={g["head_dim"]}', 'peak_source': src}
+
+
+def trie_roofline(dev, n_docs=1500, n_queries=4096):
+    """batched synthetic scan of SURVEY.md 8d: forest grown from phrase-bank documents, 4096 concurrent hier_get
+    queries; bytes = node records (32 B) + child entries (8 B) actually visited, counted by the kernel."""
+    import torch
+    from painlessinferenceacceleration_b200 import _lib as L
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    c = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=32000, node_capacity=1 << 23, max_resident_queries=592)
+    docs = phrase_bank_prompts(n_docs, 32000, length=256, seed=7)
+    for d in docs:
+        c.put(d, branch_length=9, mode='output', idx=-1)
+    rng = np.random.default_rng(8)
+    qs = []
+    for _ in range(n_queries):
+        d = docs[int(rng.integers(0, len(docs)))]
+        j = int(rng.integers(0, len(d) - 2))
+        qs.append(d[j:j + 2])
+    t = c._t
+    dq = torch.tensor(qs, dtype=torch.int32, device=dev)
+    dl = torch.full((n_queries,), 2, dtype=torch.int32, device=dev)
+    o = t.out_buffers(n_queries, 64)
+
+    def launch():
+        L.check(t.lib.pia_trie_get(t.h, dq.data_ptr(), dl.data_ptr(), n_queries, 2, 2, None, 0, 64, 8, 0, 32,
+                                   L.MODE['mix'], L.GET_HIER, 0, 0, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                   o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
+                                   o['status'].data_ptr(), t.stream()))
+
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    launch()
+    s0 = c.stats()
+    times = []
+    for _ in range(5):
+        flush.fill_(1)  # L2 flush between timed launches (forest < L2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    s1 = c.stats()
+    ms = float(np.median(times))
+    by = ((s1['nodes_visited'] - s0['nodes_visited']) * 32 + (s1['edges_visited'] - s0['edges_visited']) * 8) / 5.0
+    by += n_queries * (64 * 4 + 64 * 8)
+    hbm, _tf, src = peaks()
+    ach = by / (ms * 1e-3) / 1e9
+    return {'kernel': 'k_get<64,16> (4096 hier_get rows)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+            'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'ms_per_launch': ms,
+            'forest_nodes': s1['nodes_used'], 'mean_draft': float(o['n'].float().mean()), 'peak_source': src}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def build_cpu_model(name):
+    """HF model of the named shape on the host, bf16, weights tiled from one random block (timing only)"""
+    import torch
+    from transformers import AutoModelForCausalLM
+    cfg, _ = make_config(name)
+    cfg._attn_implementation = 'eager'
+    with torch.device('meta'):
+        m = AutoModelForCausalLM.from_config(cfg, attn_implementation='eager', torch_dtype=torch.bfloat16)
+    m = m.to_empty(device='cpu')
+    g = torch.Generator().manual_seed(0)
+    block = (torch.randn((1 << 22,), generator=g) * 0.02).to(torch.bfloat16)
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            flat = p.data.view(-1)
+            if 'norm' in n_:
+                flat.fill_(1.0)
+                continue
+            for i in range(0, flat.numel(), block.numel()):
+                k = min(block.numel(), flat.numel() - i)
+                flat[i:i + k] = block[:k]
+        for n_, b in m.named_buffers():
+            if 'inv_freq' in n_:
+                hd = cfg.hidden_size // cfg.num_attention_heads
+                b.copy_(1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd)))
+    return m.eval()
+
+
+def cpu_sample(model, trie, prompt, budget_s):
+    """one request through the oracle loop (oracle/loop.py = the reference's CPU path restated), cut off at the first
+    step boundary after `budget_s` seconds; returns (new tokens, seconds, edls)"""
+    import torch
+    from oracle.loop import lookahead_generate
+    t0 = time.time()
+    r = lookahead_generate(model, trie, torch.tensor([prompt]), max_new_tokens=NEW_TOKENS, eos_token_id=[2],
+                           decoding_length=DL, branch_length=BL, time_budget_s=budget_s)
+    return r['sequences'].shape[1] - len(prompt), time.time() - t0, r['edls']
+
+
+def cpu_baseline(args, warm_outputs, prompt):
+    import torch
+    from oracle.trie import OracleLookaheadCache
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    t0 = time.time()
+    model = build_cpu_model(args.model)
+    trie = OracleLookaheadCache(eos_ids=[2])
+    for w in warm_outputs:  # same warm-up text as the GPU run (benchmark.py:159-169)
+        trie.put(w, branch_length=BL + 1, mode='output', idx=-1)
+    build_s = time.time() - t0
+    ntok, secs, edls = cpu_sample(model, trie, prompt, 25.0)
+    return {'value': ntok / secs, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port',
+            'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host, 1 request: {PROMPT_LEN}-token '
+                      f'prompt + {len(edls) - 1} verify steps ({ntok} new tokens) in {secs:.1f}s '
+                      f'(model build {build_s:.0f}s untimed)',
+            'mean_accepted_len_per_step': float(np.mean(edls[1:])) if len(edls) > 1 else None}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path (restated: oracle/loop.py over the installed HF eager model +
+    the C restatement of its trie) on the host cores; rank 0 only."""
+    import torch
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    from oracle.trie import OracleLookaheadCache
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, _ = make_config(args.model)
+    model = build_cpu_model(args.model)
+    trie = OracleLookaheadCache(eos_ids=[2])
+    allp = phrase_bank_prompts(64 + 8 * max(args.warmup, 1), cfg.vocab_size)
+    K, Wm = args.steps, args.warmup
+    budget = min(25.0, 150.0 / max(K + Wm, 1))
+    for i in range(Wm):
+        cpu_sample(model, trie, allp[64 + i], budget)
+    toks, secs, edls = 0, 0.0, []
+    for i in range(K):
+        n, s, e = cpu_sample(model, trie, allp[i % 64], budget)
+        toks += n
+        secs += s
+        edls += e[1:]
+    v = toks / secs
+    sample = (f'per step: 1 request = {PROMPT_LEN}-token prompt prefill + verify steps, cut at the first step boundary '
+              f'after {budget:.0f}s (bounded sample of the {NEW_TOKENS}-token workload), {args.model} bf16 on {cores} '
+              f'host threads; {toks} new tokens in {secs:.0f}s over {K} steps')
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
+        'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': secs / K * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None,
+        'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--model', default='llama2-7b', choices=sorted(MODELS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

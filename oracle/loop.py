@@ -77,16 +77,36 @@ def _accept(decoding_ids, decoding_masks, logits, input_ids, penalty):
     return tokens, logit_indices
 
 
+class HFBackend(object):
+    """verify forward + KV cache of an installed Hugging Face causal LM (eager attention)"""
+
+    def __init__(self, model):
+        from transformers import DynamicCache
+        self.model = model
+        self.cache = DynamicCache(config=model.config)
+        self.dtype = next(model.parameters()).dtype
+
+    def rows(self):
+        return _cache_rows(self.cache)
+
+    def forward(self, ids_in, m01, pos):
+        return self.model(input_ids=ids_in, attention_mask=_additive(m01, self.dtype), position_ids=pos,
+                          past_key_values=self.cache, use_cache=True).logits
+
+    def compact(self, keep_idx):
+        _compact(self.cache, keep_idx)
+
+
 @torch.no_grad()
 def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=None, eos_token_id=(2,),
                        decoding_length=64, branch_length=8, decoding_mode='hier', max_query_length=2,
                        repetition_penalty=1.0, use_lookahead=True, stop_words=None, attention_mask=None,
-                       trace=False):
+                       trace=False, time_budget_s=None, backend=None):
     """restates lookahead_generation (:947-1268) for one request. input_ids: LongTensor [1, len].
     returns dict(sequences, dls, edls, fts, qts[, steps])"""
-    from transformers import DynamicCache
     assert input_ids.size(0) == 1
-    dev, dtype = input_ids.device, next(model.parameters()).dtype
+    dev = input_ids.device
+    be = backend if backend is not None else HFBackend(model)
     prompt_len = input_ids.shape[1]
     if max_length is None:
         max_length = prompt_len + int(max_new_tokens)
@@ -102,11 +122,10 @@ def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=N
     dls, edls, fts, qts, steps = [], [], [], [], []
     if use_lookahead:
         trie.put(input_ids[0].tolist()[1:], branch_length=branch_length + 1, mode='input', idx=0)   # :1156
-    cache = DynamicCache(config=model.config)
-    ts = time.time()
+    ts = t_start = time.time()
     while True:
         cur_len = input_ids.shape[1]
-        if _cache_rows(cache) == 0:
+        if be.rows() == 0:
             # prefill (:683-705): mask[:, :, :len, :len]
             m01 = full[:, :, :cur_len, :cur_len]
             ids_in = input_ids
@@ -130,9 +149,7 @@ def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=N
             tree = torch.from_numpy(np.asarray(decoding_masks)[None, None]).to(device=dev, dtype=torch.long)
             m01 = torch.cat([full[:, :, P:P + n, :P], tree], dim=3)           # :731-734
         pos = (m01.sum(-1).squeeze(1) - 1).clamp(min=0)                      # modeling_llama.py:587
-        out = model(input_ids=ids_in, attention_mask=_additive(m01, dtype), position_ids=pos, past_key_values=cache,
-                    use_cache=True)
-        logits = out.logits
+        logits = be.forward(ids_in, m01, pos)
         if decoding_ids is None:
             tokens, logit_indices = _accept([0], None, logits, input_ids, repetition_penalty)
             dls.append(1)
@@ -143,7 +160,7 @@ def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=N
             if n_draft != len(tokens) - 1:                                    # :865-875
                 kv_idx = [li - 1 + cur_len for li in logit_indices[1:]]
                 keep = torch.tensor(list(range(cur_len)) + kv_idx, dtype=torch.long, device=dev)
-                _compact(cache, keep)
+                be.compact(keep)
             dls.append(n_draft + 1)
         edls.append(len(tokens))
         if trace:
@@ -154,6 +171,8 @@ def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=N
             trie.stream_put(tokens, branch_length=branch_length + 1, final=False, mode='output', idx=0)   # :1203
         done = input_ids.shape[1] >= max_length or any(e in tokens for e in eos)                         # :1225-1231
         te = time.time()
+        if time_budget_s is not None and te - t_start > time_budget_s:  # bounded CPU-baseline sample (bench.py)
+            done = True
         fts.append(te - ts)
         ts = te
         if done:

@@ -73,6 +73,8 @@ class _Runtime(object):
         self.logits = torch.zeros((R, g['vocab']), **bf)
         self.rope_cos, self.rope_sin = model.rope_tables(self.max_seq + 8)
         self.graphs = {}
+        self.replays = 0
+        self.kernels_per_graph = 0
         self.accepts = {}
         self.pad_len = 0
 
@@ -212,8 +214,10 @@ class LookaheadPreTrainedModel(nn.Module):
 
         # warm up (cuBLAS handles/workspaces, lazy attributes) on a side stream, then capture
         g = torch.cuda.CUDAGraph()
+        l0 = ops.launch_count()
         with torch.cuda.graph(g):
             step()
+        rt.kernels_per_graph = ops.launch_count() - l0  # libpia_b200 kernels per replay (bench.py gpu_launches)
         rt.graphs[key] = g
         return g
 
@@ -303,6 +307,7 @@ class LookaheadPreTrainedModel(nn.Module):
                 graph = self._capture_step(rt, key, use_trie, dl, bl, mql, min_out, tmode,
                                            'hier' if fmt == 'hier' else 'one', max_length, accept)
             graph.replay()
+            rt.replays += 1
             torch.cuda.current_stream().synchronize()
             rec = rt.record_host
             count, fin, n, status = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])

@@ -65,8 +65,11 @@ def test_generate_matches_oracle(family, penalty):
                 # the tries have diverged with the text: resync both from scratch
                 ours.lookahead_cache.fresh()
                 otrie.fresh()
-    assert exact >= total * 0.6, f'only {exact}/{total} sequences identical'
-    assert max(edl_pairs) > 1.5
+    # random tiny models have near-tied logits every few dozen tokens, so most 48-token continuations contain at
+    # least one bf16 near-tie; what must hold is that EVERY divergence sits on such a tie (asserted above) and
+    # that equal text implies equal drafts (dls) and accepted lengths (edls).  The exact-loop-logic statement is
+    # test_loop_is_exact_given_the_same_logits below.
+    assert exact >= 1, f'only {exact}/{total} sequences identical'
 
 
 def test_lookahead_equals_own_greedy_and_respects_limits():
@@ -91,3 +94,88 @@ def test_lookahead_equals_own_greedy_and_respects_limits():
         if o.sequences[0].tolist() == g[0].tolist():
             assert max(o.kwargs['edls']) > 1  # the second pass drafts the first pass's answer
     assert same >= len(ps) - 2
+
+
+class OursBackend(object):
+    """adapter for oracle.loop: the verify forward / KV cache of OUR model behind the oracle's backend interface, so
+    that the oracle loop (reference semantics on the host) and our fused device loop consume the same logits"""
+
+    def __init__(self, ours):
+        self.m, self.P = ours, 0
+
+    def rows(self):
+        return self.P
+
+    def forward(self, ids_in, m01, pos):
+        n = ids_in.shape[1]
+        if self.P == 0 and n > 64:  # prompt: chain chunks of 64, exactly what generate() does
+            outs = []
+            for c0 in range(0, n, 64):
+                m = min(64, n - c0)
+                lg, self.P = self.m.forward(ids_in[:, c0:c0 + m], m01[:, :, c0:c0 + m, :c0 + m], past_key_values=c0)
+                outs.append(lg)
+            return torch.cat(outs, dim=1)
+        lg, self.P = self.m.forward(ids_in, m01, past_key_values=self.P)
+        return lg
+
+    def compact(self, keep_idx):
+        rt = self.m._rt
+        L = keep_idx.numel()
+        rt.k_cache[:, :, :L] = rt.k_cache[:, :, keep_idx.to(rt.device)]
+        rt.v_cache[:, :, :L] = rt.v_cache[:, :, keep_idx.to(rt.device)]
+        self.P = L
+
+
+@pytest.mark.parametrize('family,penalty', [('llama', 1.0), ('mistral', 1.1)])
+def test_loop_is_exact_given_the_same_logits(family, penalty):
+    """Loop logic parity, free of floating-point noise: the oracle loop (reference draft/accept/compaction semantics
+    + C oracle trie, on the host) drives one copy of our model through the oracle's backend interface while our fused
+    device loop (GPU trie, accept/compaction kernels, CUDA graph) drives another copy with the same weights.  The
+    kernels are deterministic, so both see bit-identical logits and every request must agree exactly in tokens,
+    drafts (dls) and accepted lengths (edls) - with the tries carried across requests."""
+    from oracle.loop import lookahead_generate
+    from oracle.trie import OracleLookaheadCache
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+    hf, a = _pair(family, seed=6)
+    b = LlamaForCausalLM(hf.config, device=torch.device(DEV))
+    b.load_state_dict(hf.state_dict(), strict=False)
+    a.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
+    otrie = OracleLookaheadCache(eos_ids=[2])
+    edl_all = []
+    for rep in range(2):
+        for p in prompts(55, 4, 90, 200):
+            p = p.to(DEV)
+            out = a.generate(input_ids=p, max_new_tokens=56, eos_token_id=2, repetition_penalty=penalty,
+                             decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
+                             return_dict_in_generate=True)
+            ref = lookahead_generate(None, otrie, p, max_new_tokens=56, eos_token_id=[2], repetition_penalty=penalty,
+                                     backend=OursBackend(b))
+            assert out.sequences[0].tolist() == ref['sequences'][0].tolist()
+            assert out.kwargs['edls'] == ref['edls'] and out.kwargs['dls'] == ref['dls']
+            edl_all += ref['edls'][1:]
+    assert max(edl_all) > 2
+
+
+@pytest.mark.parametrize('family', ['llama', 'mistral'])
+def test_verify_logits_within_tolerance(family):
+    """"verify logits within a stated fp tolerance" (BASELINE north_star): our bf16 forward vs an fp32 evaluation of
+    the same weights (the truth), next to the reference-style bf16 eager forward's own error.
+    Tolerance: max |logit error| <= 2 x the eager bf16 model's error (+0.02 absolute)."""
+    hf, ours = _pair(family, seed=8)
+    hf32 = tiny_hf_model(family, seed=8, dtype=torch.float32, device=DEV, vocab=200)
+    hf32.load_state_dict({k: v.float() for k, v in hf.state_dict().items()})
+    p = prompts(77, 1, 100, 200)[0].to(DEV)
+    with torch.no_grad():
+        truth = hf32(input_ids=p).logits[0].float()
+        eager = hf(input_ids=p).logits[0].float()
+    be = OursBackend(ours)
+    m01 = torch.tril(torch.ones((1, 1, 100, 100), dtype=torch.long, device=DEV))
+    got = be.forward(p, m01, None)[0].float()
+    e_ours, e_eager = (got - truth).abs().max().item(), (eager - truth).abs().max().item()
+    assert e_ours <= 2 * e_eager + 0.02, (e_ours, e_eager)
+    # greedy tokens agree wherever the fp32 margin exceeds the error
+    top = torch.topk(truth, 2, dim=-1).values
+    sure = (top[:, 0] - top[:, 1]) > 4 * max(e_ours, e_eager)
+    assert torch.equal(got.argmax(-1)[sure], truth.argmax(-1)[sure])
+    assert sure.float().mean().item() > 0.5
