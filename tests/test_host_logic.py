@@ -1,0 +1,98 @@
+# -*- coding: utf-8 -*-
+"""Host-side logic that needs no GPU: generation-mode selection, kwargs validation, bench sharding over a
+world_size-2 gloo group (the N>1 path is independent replicas + one weight broadcast)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model():
+    from transformers import LlamaConfig
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=64, hidden_size=256, intermediate_size=256, num_hidden_layers=1,
+                      num_attention_heads=2, num_key_value_heads=2)
+    return LlamaForCausalLM(cfg, device='cpu')
+
+
+def test_generation_mode_selection():
+    from painlessinferenceacceleration_b200.common.lookahead_generation_utils import GenerationMode
+    m = _model()
+    g = m._get_generation_mode
+    assert g(False, True, {'use_lookahead': True}) == GenerationMode.LOOKAHEAD_GENERATION          # reference :72-77
+    assert g(False, True, {'use_lookahead': True, 'decoding_length': 1}) == GenerationMode.GREEDY_SEARCH
+    assert g(False, True, {'use_lookahead': True, 'branch_length': 0}) == GenerationMode.GREEDY_SEARCH
+    assert g(False, False, {'use_lookahead': True}) == GenerationMode.GREEDY_SEARCH
+    assert g(False, True, {}) == GenerationMode.GREEDY_SEARCH
+
+
+def test_unknown_generate_kwargs_raise_like_the_reference():
+    m = _model()
+    with pytest.raises(ValueError):
+        m.generate(input_ids=torch.zeros((1, 4), dtype=torch.long), not_a_real_kwarg=1)  # reference :1309-1317
+
+
+def test_hf_checkpoint_roundtrip(tmp_path):
+    """from_pretrained reads an HF checkpoint directory unchanged (module tree / parameter names are HF's)"""
+    from transformers import LlamaConfig, LlamaForCausalLM as HF
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=64, hidden_size=256, intermediate_size=256, num_hidden_layers=2,
+                      num_attention_heads=2, num_key_value_heads=2)
+    torch.manual_seed(0)
+    hf = HF(cfg).to(torch.bfloat16)
+    hf.save_pretrained(tmp_path)
+    ours = LlamaForCausalLM.from_pretrained(str(tmp_path), device='cpu')
+    sd = hf.state_dict()
+    for k, v in ours.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    ours.fuse()
+    w = ours.model.layers[1].self_attn.qkv_weight
+    assert torch.equal(w[:256], sd['model.layers.1.self_attn.q_proj.weight'])
+    assert ours.model.layers[1].self_attn.k_proj.weight.data_ptr() == w[256:].data_ptr()
+
+
+def test_phrase_bank_prompts_are_seeded():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.phrase_bank_prompts(3, 32000)
+    b = bench.phrase_bank_prompts(3, 32000)
+    assert a == b and all(len(p) == 256 and min(p) >= 3 and max(p) < 32000 for p in a)
+
+
+def test_replica_sharding_and_aggregation_gloo_world2(tmp_path):
+    """N>1 path on CPU: 2 ranks over gloo shard the timed prompts like bench.py, broadcast 'weights' from rank 0
+    and aggregate tokens with SUM / time with MAX - no data-path collective."""
+    script = tmp_path / 'w.py'
+    script.write_text(textwrap.dedent('''
+        import os, sys, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        import bench
+        dist.init_process_group('gloo')
+        rank, world = dist.get_rank(), dist.get_world_size()
+        K = 3
+        allp = bench.phrase_bank_prompts(64, 32000)
+        mine = [(rank * K + i) %% 64 for i in range(K)]
+        w = torch.full((8,), float(rank + 1))
+        dist.broadcast(w, src=0)
+        assert float(w.sum()) == 8.0
+        t = torch.tensor([10.0 + rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        agg = torch.tensor([float(len(mine) * 256)]); dist.all_reduce(agg)
+        idx = torch.tensor(mine); gathered = [torch.zeros_like(idx) for _ in range(world)]
+        dist.all_gather(gathered, idx)
+        flat = sorted(int(v) for g in gathered for v in g)
+        assert flat == list(range(world * K)), flat
+        if rank == 0:
+            print('OK', float(t), float(agg))
+        dist.destroy_process_group()
+    ''' % ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29571')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29571', str(script)], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'OK 11.0 1536.0' in out.stdout
