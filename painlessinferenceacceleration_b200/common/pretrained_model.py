@@ -197,7 +197,7 @@ class LookaheadPreTrainedModel(nn.Module):
             else:  # plain greedy: the draft is the last token alone
                 rt.ids[0, 0:1] = rt.seq.gather(0, (rt.seq_len - 1).long())
                 rt.n.fill_(1)
-                rt.mask[0, 0, 0] = 1
+                rt.mask[0, 0, 0:1].fill_(1)
             self._verify_layers(rt)
             accept.run(rt.logits, rt.ids, rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens,
                        rt.acc_count, rt.acc_nodes, rt.prefix_len, rt.finished)

@@ -1,0 +1,31 @@
+# -*- coding: utf-8 -*-
+"""A short, profiler-friendly run of the hot path: Llama-2-7B shape, one prompt, a handful of decode steps.
+Used under `ncu` (launch list / --set full); numbers printed here are never bench values."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--model', default='llama2-7b')
+ap.add_argument('--new', type=int, default=12)
+ap.add_argument('--prompt', type=int, default=256)
+ap.add_argument('--requests', type=int, default=2)
+a = ap.parse_args()
+from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache  # noqa: E402
+from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM  # noqa: E402
+
+dev = torch.device('cuda:0')
+cfg, _ = bench.make_config(a.model)
+model = LlamaForCausalLM(cfg, device=dev).init_weights(seed=0)
+model.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
+ps = bench.phrase_bank_prompts(4, cfg.vocab_size, length=a.prompt)
+for r in range(a.requests):  # same prompt twice: the second request drafts from the first one's answer
+    o = model.generate(input_ids=torch.tensor([ps[0]], device=dev), max_new_tokens=a.new, eos_token_id=2,
+                       decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
+                       return_dict_in_generate=True)
+    print('request', r, 'edls', o.kwargs['edls'], 'dls', o.kwargs['dls'])

