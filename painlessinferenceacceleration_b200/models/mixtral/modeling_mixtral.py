@@ -1,0 +1,77 @@
+# -*- coding: utf-8 -*-
+"""Mixtral with the lookahead patch (reference: models/mixtral/modeling_mixtral.py, patch :1032-1036, attention
+:302-381, MixtralSparseMoeBlock :692-759, expert MLP :668-683).
+
+Attention / norms / RoPE are the Llama-family kernels (GQA packed into the UMMA tile).  The MoE block: at n = 64
+draft nodes with top-2 of 8 routing practically every expert is hit, so the verify step reads all expert weights
+either way (>= 90 GB per step); the block therefore evaluates every expert on all n rows with
+static-shape GEMMs (CUDA-graph friendly, no host-side routing) and combines with the routing weights, zero for
+unselected experts.  Rounding follows the reference: fp32 softmax -> top-k -> renormalise -> cast to bf16 (:723-727);
+per token the two selected expert outputs are scaled in bf16 and accumulated in expert-index order, exactly what
+`index_add_` into a zero tensor produces (:729-757); adding an unselected expert's 0 is exact."""
+import torch
+from torch import nn
+
+from ...common import ops
+from ..llama.modeling_llama import LlamaDecoderLayer, LlamaForCausalLM, LlamaModel
+
+
+class MixtralRouter(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty((cfg.num_local_experts, cfg.hidden_size), device=device, dtype=dtype))
+
+
+class MixtralExperts(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        E, H, I = cfg.num_local_experts, cfg.hidden_size, cfg.intermediate_size
+        self.gate_up_proj = nn.Parameter(torch.empty((E, 2 * I, H), device=device, dtype=dtype))
+        self.down_proj = nn.Parameter(torch.empty((E, H, I), device=device, dtype=dtype))
+
+
+class MixtralSparseMoeBlock(nn.Module):
+    def __init__(self, cfg, device, dtype):
+        super().__init__()
+        self.top_k = cfg.num_experts_per_tok
+        self.num_experts = cfg.num_local_experts
+        self.gate = MixtralRouter(cfg, device, dtype)
+        self.experts = MixtralExperts(cfg, device, dtype)
+
+
+class MixtralDecoderLayer(LlamaDecoderLayer):
+    def _make_mlp(self, cfg, device, dtype):
+        return MixtralSparseMoeBlock(cfg, device, dtype)
+
+
+class MixtralModel(LlamaModel):
+    layer_cls = MixtralDecoderLayer
+
+
+class MixtralForCausalLM(LlamaForCausalLM):
+    model_cls = MixtralModel
+
+    def _fuse_mlp(self, layer):
+        pass  # experts are stored fused ([E, 2I, H]) already
+
+    def geometry(self):
+        g = super().geometry()
+        g['n_experts'] = self.config.num_local_experts
+        return g
+
+    def _mlp(self, rt, layer, y):
+        moe = layer.mlp
+        logits = torch.mm(y, moe.gate.weight.t())                                   # :721
+        probs = torch.softmax(logits.float(), dim=1)                                # :723
+        w, sel = torch.topk(probs, moe.top_k, dim=-1)                               # :724
+        w = (w / w.sum(dim=-1, keepdim=True)).to(y.dtype)                           # :725-727
+        dense = torch.zeros((y.shape[0], moe.num_experts), dtype=y.dtype, device=y.device).scatter_(1, sel, w)
+        out = torch.zeros_like(y)
+        inter = moe.experts.down_proj.shape[2]
+        act = torch.empty((y.shape[0], inter), dtype=y.dtype, device=y.device)
+        for e in range(moe.num_experts):                                            # expert-index order (:734)
+            gu = torch.mm(y, moe.experts.gate_up_proj[e].t())
+            ops.silu_mul(gu, act)
+            ye = torch.mm(act, moe.experts.down_proj[e].t())
+            out += ye * dense[:, e:e + 1]                                           # bf16 scale, bf16 accumulate
+        return out
