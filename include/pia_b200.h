@@ -144,6 +144,10 @@ typedef struct {
  * plan's lifetime (TMA descriptors are encoded over them). Synchronous; not capturable. */
 int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cache, void *d_v_cache, pia_attn_plan_t **out);
 int pia_attn_plan_destroy(pia_attn_plan_t *p);
+/* diagnostics: per-CTA phase timestamps (16 x uint64 globaltimer values per CTA of the last launch), or NULL to
+ * disable; grid geometry of the plan (n_split x n_groups CTAs). */
+int pia_attn_plan_set_debug(pia_attn_plan_t *p, void *d_timestamps);
+int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n_groups);
 /* bytes of fp32 workspace the forward needs (split-KV partials) */
 int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p);
 

@@ -16,7 +16,9 @@
 //                    -> P (bf16) to shared memory in the UMMA K-major SWIZZLE_128B layout
 //                    -> O_tile = P V (8 x UMMA, V consumed MN-major straight from the TMA tile)
 //                    -> acc = acc * alpha + O_tile in registers.
-// Split partials (acc, m, l) go to a workspace; k_combine merges the splits and writes bf16.
+// The KV range is split across CTAs only when it is long (>= 4 tiles per CTA, decided on the device from the
+// live length): a single-split CTA normalises and writes bf16 directly; otherwise partials (acc, m, l) go to a
+// workspace and the last split CTA of the head group to arrive merges them (no separate combine launch).
 // HBM-bound by design (arithmetic intensity = rows per KV byte: 64 FLOP/B for MHA, 256 for GQA-4;
 // DESIGN.md gives the roofline).
 #include <cuda.h>
@@ -41,6 +43,7 @@ constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr int TILES_PER_CTA = 4;        // target tiles per CTA before the KV range is split across CTAs
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,7 +126,17 @@ struct Params {
   float *ws_m, *ws_l;      // [n_split, Hq, np]
   int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split;
   float scale_log2;
+  __nv_bfloat16 *out;            // [max_nodes, Hq, HD]
+  int *counters;                 // [n_groups] arrival counters of the split CTAs (self-resetting)
+  unsigned long long *dbg;       // optional per-CTA phase timestamps (pia_attn_plan_set_debug)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, Params p) {
@@ -134,8 +147,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
 
   const uint32_t bar0 = base + SMEM_BAR;
   const uint32_t bar_kv_full = bar0, bar_kv_empty = bar0 + 8 * NSTAGE, bar_s_full = bar0 + 16 * NSTAGE,
-                 bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 32);
+                 bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 8, bar_q_full = bar_o_full + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 48);
 
   const int split = blockIdx.x, group = blockIdx.y;
   const int n = *p.d_n, P = *p.d_prefix;
@@ -143,56 +156,48 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const int hq0 = group * p.heads_per_cta;
   const int hkv = hq0 / (p.n_q_heads / p.n_kv_heads);
   const int tiles_total = (L + BN - 1) / BN;
-  const int tps = (tiles_total + p.n_split - 1) / p.n_split;
+  // Work split decided on the device from the live length: aim at >= TILES_PER_CTA tiles per CTA so that short
+  // contexts run as ONE CTA per head group and write the final output directly (no partials, no merge).
+  int ns = (tiles_total + TILES_PER_CTA - 1) / TILES_PER_CTA;
+  if (ns > p.n_split) ns = p.n_split;
+  if (ns < 1) ns = 1;
+  if (split >= ns) return;
+  const int tps = (tiles_total + ns - 1) / ns;
   const int t0 = split * tps;
   int t1 = t0 + tps;
   if (t1 > tiles_total) t1 = tiles_total;
-  const int ntile = t1 - t0;
+  const int ntile = t1 - t0;  // >= 1 for split < ns except possibly the last one
 
-  const bool is_sm_thread = warp >= 2;
-  const int row = ((warp & 3) << 5) | lane;  // TMEM lane this softmax thread owns
+  const int rows_used = p.heads_per_cta * p.np;          // 64 (MHA, 64 nodes) or 128
+  const bool is_sm_warp = warp >= 2;
+  const int row = ((warp & 3) << 5) | lane;              // TMEM lane this softmax thread owns
+  const bool warp_active = is_sm_warp && (((warp & 3) << 5) < rows_used);
   const int hs = row / p.np, node = row % p.np;
-  const bool row_live = is_sm_thread && hs < p.heads_per_cta && node < n;
-
-  if (ntile <= 0) {  // nothing for this split: leave an empty partial
-    if (row_live) {
-      const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
-      p.ws_m[o] = -INFINITY;
-      p.ws_l[o] = 0.f;
-    }
-    return;
-  }
+  const bool row_live = warp_active && node < n;
+  if (tid == 0) DBG(0);
 
   // ---- setup
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1); mbar_init(bar_s_full + 8, 1);
-    mbar_init(bar_p_full, 128);
+    mbar_init(bar_p_full, rows_used);
     mbar_init(bar_o_full, 1);
+    mbar_init(bar_q_full, rows_used);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // Q tile -> shared memory, UMMA K-major SWIZZLE_128B ([128 rows x 64] sub-tiles per d-half); idle rows = 0
-  for (int c = tid; c < BM * (HD / 8); c += NTHREADS) {
-    const int r = c >> 4, ch = c & 15;
-    const int rhs = r / p.np, rnode = r % p.np;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (rhs < p.heads_per_cta && rnode < n)
-      v = *reinterpret_cast<const uint4 *>(p.q + ((long long)rnode * p.n_q_heads + hq0 + rhs) * HD + ch * 8);
-    *reinterpret_cast<uint4 *>(sm + SMEM_Q + (ch >> 3) * SUB + r * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v;
-  }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tid == 0) DBG(1);
 
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && ntile > 0) {
       const int plane = p.layer * p.n_kv_heads + hkv;
       for (int i = 0; i < ntile; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
@@ -204,12 +209,14 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         tma_load_3d(kd + SUB, &map_k, bar_kv_full + 8 * s, 64, key0, plane);
         tma_load_3d(vd, &map_v, bar_kv_full + 8 * s, 0, key0, plane);
         tma_load_3d(vd + SUB, &map_v, bar_kv_full + 8 * s, 64, key0, plane);
+        if (i == 0) DBG(2);
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
-    if (lane == 0) {
+    if (lane == 0 && ntile > 0) {
       constexpr uint32_t IDESC_QK = make_idesc(0), IDESC_PV = make_idesc(1);
+      mbar_wait(bar_q_full, 0);
       auto issue_qk = [&](int i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         mbar_wait(bar_kv_full + 8 * s, ph);
@@ -224,6 +231,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         umma_commit(bar_s_full + 8 * (i & 1));
       };
       issue_qk(0);
+      DBG(3);
       for (int i = 0; i < ntile; ++i) {
         if (i + 1 < ntile) issue_qk(i + 1);  // S is double buffered: next QK^T overlaps this tile's softmax
         const int s = i % NSTAGE;
@@ -239,9 +247,24 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         umma_commit(bar_o_full);
         umma_commit(bar_kv_empty + 8 * s);
       }
+      DBG(4);
     }
-  } else {
+  } else if (warp_active) {
     // ================================================================ softmax + accumulate (one row per thread)
+    // Q rows -> shared memory (UMMA K-major SWIZZLE_128B, [rows x 64] sub-tiles per d-half); all loads first
+    {
+      uint4 qv[16];
+      const bool have = hs < p.heads_per_cta && node < n;
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((long long)node * p.n_q_heads + hq0 + hs) * HD);
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) qv[ch] = have ? src[ch] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch)
+        *reinterpret_cast<uint4 *>(sm + SMEM_Q + (ch >> 3) * SUB + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = qv[ch];
+      fence_async_smem();
+      mbar_arrive(bar_q_full);
+    }
+    if (row == 0) DBG(5);
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     unsigned long long mrow[2] = {0ull, 0ull};
     if (row_live) for (int w = 0; w < p.mask_words; ++w) mrow[w] = p.mask[(long long)node * p.mask_words + w];
@@ -255,6 +278,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       const uint32_t s_addr = tmem + lane_addr + ((i & 1) ? TM_S1 : TM_S0);
       mbar_wait(bar_s_full + 8 * (i & 1), (i >> 1) & 1);
       tc_fence_after();
+      if (row == 0 && i == 0) DBG(6);
       const bool all_visible = (key0 >= p.pad_len) && (key0 + BN <= P);
       auto visible = [&](int kk) -> bool {
         if (kk < P) return kk >= p.pad_len;
@@ -305,9 +329,11 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       fence_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       tc_fence_before();    // order our tcgen05.ld of S before the issuer's next MMA into this S buffer
       mbar_arrive(bar_p_full);
+      if (row == 0 && i == 0) DBG(7);
       // accumulate this tile's PV
       mbar_wait(bar_o_full, i & 1);
       tc_fence_after();
+      if (row == 0 && i == 0) DBG(8);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(tmem + lane_addr + TM_O + c * 32, v);
@@ -317,7 +343,23 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       }
       tc_fence_before();
     }
-    if (row_live) {
+    if (row == 0) DBG(9);
+    if (ns == 1) {
+      // single split: normalise and write the final bf16 row
+      if (row_live) {
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)node * p.n_q_heads + hq0 + hs) * HD);
+#pragma unroll
+        for (int j = 0; j < HD / 8; ++j) {
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv);
+          dst[j] = make_uint4(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1),
+                              *reinterpret_cast<uint32_t *>(&b2), *reinterpret_cast<uint32_t *>(&b3));
+        }
+      }
+    } else if (row_live) {
       const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
       p.ws_m[o] = m_run;
       p.ws_l[o] = l_run;
@@ -325,38 +367,56 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
 #pragma unroll
       for (int j = 0; j < HD / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
+    if (row == 0) DBG(10);
   }
   tc_fence_before();
+  __threadfence();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
-}
-
-// merge the KV splits: out[node, head, :] = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)
-__global__ void __launch_bounds__(128) k_combine(const float *ws_acc, const float *ws_m, const float *ws_l,
-                                                 const int *d_n, int n_split, int n_q_heads, int np,
-                                                 __nv_bfloat16 *out) {
-  const int head = blockIdx.x, node = blockIdx.y * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (node >= *d_n) return;
-  float M = -INFINITY;
-  for (int s = 0; s < n_split; ++s) M = fmaxf(M, ws_m[((long long)s * n_q_heads + head) * np + node]);
-  float den = 0.f;
-  float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < n_split; ++s) {
-    const long long o = ((long long)s * n_q_heads + head) * np + node;
-    const float m = ws_m[o];
-    if (m == -INFINITY) continue;
-    const float w = exp2f(m - M);
-    den += ws_l[o] * w;
-    const float4 a = reinterpret_cast<const float4 *>(ws_acc + o * HD)[lane];
-    num.x += a.x * w; num.y += a.y * w; num.z += a.z * w; num.w += a.w * w;
+  if (ns > 1) {
+    // the last split CTA of this head group to arrive merges the partials (no separate combine launch)
+    __shared__ int s_last;
+    if (tid == 0) {
+      const int prev = atomicAdd(&p.counters[group], 1);
+      s_last = (prev == ns - 1);
+      if (s_last) p.counters[group] = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      // thread = (row, 8-wide d chunk): out = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)
+      const int items = rows_used * (HD / 8);
+      for (int it = tid; it < items; it += NTHREADS) {
+        const int r = it / (HD / 8), ch = it % (HD / 8);
+        const int rh = r / p.np, rn = r % p.np;
+        if (rn >= n) continue;
+        float M = -INFINITY;
+        for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, p.ws_m[((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn]);
+        float den = 0.f, num[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int s2 = 0; s2 < ns; ++s2) {
+          const long long o = ((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn;
+          const float m = p.ws_m[o];
+          if (m == -INFINITY) continue;
+          const float w = exp2f(m - M);
+          den += p.ws_l[o] * w;
+          const float4 a0 = reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[2 * ch];
+          const float4 a1 = reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[2 * ch + 1];
+          num[0] += a0.x * w; num[1] += a0.y * w; num[2] += a0.z * w; num[3] += a0.w * w;
+          num[4] += a1.x * w; num[5] += a1.y * w; num[6] += a1.z * w; num[7] += a1.w * w;
+        }
+        const float inv = den > 0.f ? 1.f / den : 0.f;
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(num[0] * inv, num[1] * inv), b1 = __floats2bfloat162_rn(num[2] * inv, num[3] * inv);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(num[4] * inv, num[5] * inv), b3 = __floats2bfloat162_rn(num[6] * inv, num[7] * inv);
+        reinterpret_cast<uint4 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[ch] =
+            make_uint4(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1),
+                       *reinterpret_cast<uint32_t *>(&b2), *reinterpret_cast<uint32_t *>(&b3));
+      }
+    }
   }
-  const float inv = den > 0.f ? 1.f / den : 0.f;
-  __nv_bfloat162 lo = __floats2bfloat162_rn(num.x * inv, num.y * inv), hi = __floats2bfloat162_rn(num.z * inv, num.w * inv);
-  uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
-  reinterpret_cast<uint2 *>(out + ((long long)node * n_q_heads + head) * HD)[lane] = pk;
+  if (tid == 0) DBG(11);
 }
 
 }  // namespace attn
@@ -370,6 +430,8 @@ struct pia_attn_plan {
   pia_attn_config_t cfg;
   CUtensorMap map_k, map_v;
   int heads_per_cta, n_groups, n_split, mask_words;
+  int *counters;
+  unsigned long long *dbg;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -415,7 +477,7 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int max_tiles = (cfg->max_seq + BN - 1) / BN;
-  int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : (n_sm + p->n_groups - 1) / p->n_groups;
+  int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : (2 * n_sm + p->n_groups - 1) / p->n_groups;
   if (ns > max_tiles) ns = max_tiles;
   if (ns < 1) ns = 1;
   if (ns > 64) ns = 64;
@@ -426,12 +488,34 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
     cudaError_t e = cudaFuncSetAttribute(k_tree_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
-  if (rc != PIA_OK) { delete p; return rc; }
+  p->counters = nullptr;
+  p->dbg = nullptr;
+  if (rc == PIA_OK) {
+    cudaError_t e = cudaMalloc((void **)&p->counters, sizeof(int) * p->n_groups);
+    if (e == cudaSuccess) e = cudaMemset(p->counters, 0, sizeof(int) * p->n_groups);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("attn plan: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
+  }
+  if (rc != PIA_OK) { if (p->counters) cudaFree(p->counters); delete p; return rc; }
   *out = p;
   return PIA_OK;
 }
 
-extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) { delete p; return PIA_OK; }
+extern "C" int pia_attn_plan_set_debug(pia_attn_plan_t *p, void *d_timestamps) {
+  PIA_REQUIRE(p, "null plan");
+  p->dbg = (unsigned long long *)d_timestamps;
+  return PIA_OK;
+}
+extern "C" int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n_groups) {
+  PIA_REQUIRE(p && n_split && n_groups, "null argument");
+  *n_split = p->n_split; *n_groups = p->n_groups;
+  return PIA_OK;
+}
+
+extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) {
+  if (p) { if (p->counters) cudaFree(p->counters); delete p; }
+  return PIA_OK;
+}
 
 extern "C" int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p) {
   if (!p) return 0;
@@ -455,13 +539,10 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
   a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.pad_len = pad_len; a.max_seq = p->cfg.max_seq;
   a.n_split = p->n_split;
+  a.out = (__nv_bfloat16 *)d_out; a.counters = p->counters; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
   k_tree_attn<<<dim3(p->n_split, p->n_groups), NTHREADS, SMEM_TOTAL, s>>>(p->map_k, p->map_v, a);
-  PIA_LAUNCH_CHECK();
-  k_combine<<<dim3(p->cfg.n_q_heads, (p->cfg.max_nodes + 3) / 4), 128, 0, s>>>(a.ws_acc, a.ws_m, a.ws_l, d_n, p->n_split,
-                                                                              p->cfg.n_q_heads, p->cfg.max_nodes,
-                                                                              (__nv_bfloat16 *)d_out);
   PIA_LAUNCH_CHECK();
   return PIA_OK;
 }

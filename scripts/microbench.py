@@ -22,7 +22,7 @@ from painlessinferenceacceleration_b200.models.llama.modeling_llama import Llama
 
 dev = torch.device('cuda:0')
 cfg, _ = bench.make_config(a.model)
-model = LlamaForCausalLM(cfg, device=dev).init_weights(seed=0)
+model = LlamaForCausalLM(cfg, device=dev).init_weights(seed=0).requires_grad_(False)
 model.fuse()
 rt = model._runtime(a.max_seq, 64)
 rt.mask[0].copy_(rt.chain_mask_rows())
@@ -68,7 +68,7 @@ timeit('gemm qkv', lambda: [torch.mm(rt.y, w.t(), out=rt.qkv) for w in qkv_w], N
 timeit('gemm o', lambda: [torch.mm(rt.attn, l.self_attn.o_proj.weight.t()) for l in layers], NL, bytes_per=hid * hid * 2)
 timeit('gemm gate_up', lambda: [torch.mm(rt.y, l.mlp.gate_up_weight.t(), out=gu) for l in layers], NL, bytes_per=2 * g['inter'] * hid * 2)
 timeit('gemm down', lambda: [torch.mm(act, l.mlp.down_proj.weight.t()) for l in layers], NL, bytes_per=g['inter'] * hid * 2)
-timeit('gemm lm_head', lambda: torch.mm(rt.y, model.lm_head.weight.t(), out=rt.logits), 1, bytes_per=g['vocab'] * hid * 2)
+timeit('gemm lm_head', lambda: torch.mm(rt.y, model.lm_head.weight.t()), 1, bytes_per=g['vocab'] * hid * 2)
 timeit('verify layers (whole forward)', lambda: model._verify_layers(rt), 1, bytes_per=sum(p.numel() for p in model.parameters()) * 2)
 # single-request trie get on a warmed trie
 trie = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
