@@ -100,6 +100,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t *v) {
       : "r"(addr)
       : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
@@ -267,7 +272,10 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     if (row == 0) DBG(5);
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     unsigned long long mrow[2] = {0ull, 0ull};
-    if (row_live) for (int w = 0; w < p.mask_words; ++w) mrow[w] = p.mask[(long long)node * p.mask_words + w];
+    if (row_live) {
+      mrow[0] = p.mask[(long long)node * p.mask_words];
+      if (p.mask_words > 1) mrow[1] = p.mask[(long long)node * p.mask_words + 1];
+    }
     float acc[HD];
 #pragma unroll
     for (int j = 0; j < HD; ++j) acc[j] = 0.f;
@@ -280,38 +288,57 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       tc_fence_after();
       if (row == 0 && i == 0) DBG(6);
       const bool all_visible = (key0 >= p.pad_len) && (key0 + BN <= P);
-      auto visible = [&](int kk) -> bool {
-        if (kk < P) return kk >= p.pad_len;
-        const int j = kk - P;
-        return j < n && ((mrow[j >> 6] >> (j & 63)) & 1ull);
+      // 32-bit visibility word of keys [kb, kb+32): prefix keys [pad_len, P) are visible to every row, the n draft
+      // keys follow the row's ancestor bits.  (Kept out of the unrolled element loops: the code must stay small
+      // enough for the instruction cache - the first version spent 16 us per tile fetching instructions.)
+      auto vis32 = [&](int kb) -> uint32_t {
+        if (all_visible) return 0xffffffffu;
+        uint32_t m = 0;
+        const int lo = kb < p.pad_len ? p.pad_len : kb;       // prefix part: [max(kb,pad), min(kb+32,P))
+        const int hi = kb + 32 < P ? kb + 32 : P;
+        if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << (lo - kb);
+        const int j0 = kb - P;                                 // draft index of bit 0 (may be negative)
+        if (j0 + 32 > 0 && j0 < n) {
+          uint32_t d;
+          if (j0 < 0) d = (uint32_t)(mrow[0] << (-j0));
+          else if (j0 < 64) {
+            unsigned long long x = mrow[0] >> j0;
+            if (j0 > 32) x |= mrow[1] << (64 - j0);
+            d = (uint32_t)x;
+          } else d = (uint32_t)(mrow[1] >> (j0 - 64));
+          // bits beyond the n live nodes are never set in mrow (rows of the trie mask only name nodes < n)
+          m |= d;
+        }
+        return m;
       };
       // pass 1: row max
       float m_tile = -INFINITY;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(s_addr + c * 32, v);
         tmem_ld_wait();
+        const uint32_t vm = vis32(key0 + c * 32);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]);
-          if (all_visible || visible(key0 + c * 32 + j)) m_tile = fmaxf(m_tile, s);
+          const float s = (vm >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY;
+          m_tile = fmaxf(m_tile, s);
         }
       }
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_use);
+      const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_use);
       // pass 2: p = exp2(s*scale - m), P -> smem (bf16, swizzled), row sum
       float l_tile = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(s_addr + c * 32, v);
         tmem_ld_wait();
+        const uint32_t vm = vis32(key0 + c * 32);
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (all_visible || visible(key0 + c * 32 + j)) p0 = exp2f(__uint_as_float(v[j]) * p.scale_log2 - m_use);
-          if (all_visible || visible(key0 + c * 32 + j + 1)) p1 = exp2f(__uint_as_float(v[j + 1]) * p.scale_log2 - m_use);
+          const float p0 = (vm >> j) & 1u ? ex2(__uint_as_float(v[j]) * p.scale_log2 - m_use) : 0.f;
+          const float p1 = (vm >> (j + 1)) & 1u ? ex2(__uint_as_float(v[j + 1]) * p.scale_log2 - m_use) : 0.f;
           const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
           l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);

@@ -80,6 +80,8 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         self.model = self.model_cls(config, device, dtype)
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False, device=device, dtype=dtype)
         self._fused = False
+        for p_ in self.parameters():  # inference only: no autograd state on the hot path
+            p_.requires_grad_(False)
 
     # ------------------------------------------------------------------ weights
     @torch.no_grad()
