@@ -1,0 +1,84 @@
+# -*- coding: utf-8 -*-
+"""Turns the raw ncu outputs brought back in gpurun_out/ into the small tracked summaries under profiles/.
+    python scripts/summarize_profiles.py <tag>        e.g. r01a"""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, 'profiles')
+GO = os.path.join(ROOT, 'gpurun_out')
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+os.makedirs(OUT, exist_ok=True)
+
+
+def short(n):
+    n = re.sub(r'\(.*', '', n)
+    n = n.replace('pia::', '').replace('void ', '')
+    return n[:64]
+
+
+def launch_list(path, name):
+    lines = [l for l in open(path) if not l.startswith('==')]
+    rows = [(int(r['ID']), r['Kernel Name'], float(r['Metric Value'].replace(',', '')))
+            for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
+    gets = [i for i, r in enumerate(rows) if 'k_get' in r[1]]
+    out = [f'# ncu launch list ({name}): `ncu --metrics gpu__time_duration.sum --clock-control none` on '
+           f'scripts/profile_step.py (Llama-2-7B shape)', '',
+           'Per-launch times are cold-cache and serialised: read the SHARES, not the absolutes.', '',
+           f'{len(rows)} launches captured; one decode step = the launches between two consecutive `k_get`.', '']
+    if len(gets) >= 2:
+        seg = rows[gets[-2]:gets[-1]]
+        tot = sum(r[2] for r in seg)
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for r in seg:
+            agg[short(r[1])][0] += 1
+            agg[short(r[1])][1] += r[2]
+        out += [f'## one decode step: {len(seg)} launches, sum of kernel durations {tot / 1e3:.0f} us', '',
+                '| kernel | launches | total us | share |', '|---|---:|---:|---:|']
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            out.append(f'| `{k}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% |')
+        own = sum(v[1] for k, v in agg.items() if 'nvjet' not in k and 'cutlass' not in k and 'at::' not in k)
+        out += ['', f'own kernels (libpia_b200): {100 * own / tot:.1f}% of the step; cuBLAS GEMMs (`nvjet_*`): '
+                    f'{100 * (tot - own) / tot:.1f}%']
+    open(os.path.join(OUT, f'{tag}_launches.md'), 'w').write('\n'.join(out) + '\n')
+
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size',
+        'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__cycles_active.avg', 'sm__cycles_elapsed.max',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
+        'lts__t_sector_hit_rate.pct', 'smsp__inst_executed.sum']
+
+
+def full(rep, name):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(raw)))
+    if len(rd) < 3:
+        return
+    hdr, units = rd[0], rd[1]
+    out = [f'# ncu --set full summary: {name}', '', f'source: `{os.path.basename(rep)}` (kept in gpurun_out/, not tracked)', '']
+    for row in rd[2:]:
+        d = dict(zip(hdr, row))
+        out += [f"## launch {d.get('ID')}: `{short(d.get('Kernel Name', ''))}`", '', '| metric | value | unit |', '|---|---:|---|']
+        for w in WANT:
+            if w in d:
+                out.append(f'| {w} | {d[w]} | {units[hdr.index(w)]} |')
+        rd_b = float(d.get('dram__bytes_read.sum', '0').replace(',', '') or 0)
+        out.append('')
+    open(os.path.join(OUT, f'{tag}_{name}.md'), 'w').write('\n'.join(out) + '\n')
+
+
+for f in sorted(os.listdir(GO)):
+    p = os.path.join(GO, f)
+    if f.startswith('launches') and f.endswith('.csv'):
+        launch_list(p, f[:-4])
+    elif f.endswith('.ncu-rep'):
+        full(p, f[:-8])
+print(sorted(os.listdir(OUT)))

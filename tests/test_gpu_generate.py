@@ -35,7 +35,7 @@ def _pair(family, seed):
     return hf, ours
 
 
-def _legit_divergence(family, hf, prefix, tok_a, tok_b):
+def _legit_divergence(family, hf, prefix, tok_a, tok_b, penalty=1.0):
     """a bf16 flip is legitimate iff, under an fp32 evaluation of the same weights on the common prefix, BOTH
     candidate tokens lie within the bf16 noise of the optimum; noise = the reference-style eager bf16 forward's own
     max logit error on that prefix (x4, +0.05)."""
@@ -47,6 +47,9 @@ def _legit_divergence(family, hf, prefix, tok_a, tok_b):
         truth = hf.fp32_twin(input_ids=prefix).logits[0, -1].float()
         noisy = hf(input_ids=prefix).logits[0, -1].float()
     noise = (noisy - truth).abs().max().item()
+    if penalty != 1.0:  # the arg-max is taken over the penalised scores (pretrained_model.py:834)
+        from transformers import RepetitionPenaltyLogitsProcessor
+        truth = RepetitionPenaltyLogitsProcessor(penalty)(prefix, truth[None])[0]
     gap = max((truth.max() - truth[tok_a]).item(), (truth.max() - truth[tok_b]).item())
     return gap <= 4 * noise + 0.05, gap, noise
 
@@ -77,7 +80,7 @@ def test_generate_matches_oracle(family, penalty):
                 edl_pairs.append(sum(ref['edls'][1:]) / max(len(ref['edls']) - 1, 1))
             else:
                 k = next(i for i in range(min(len(a), len(b))) if a[i] != b[i])
-                ok, gap, noise = _legit_divergence(family, hf, ref['sequences'][:, :k], a[k], b[k])
+                ok, gap, noise = _legit_divergence(family, hf, ref['sequences'][:, :k], a[k], b[k], penalty)
                 _diag('generate_matches_oracle', family=family, pos=k, gap=gap, noise=noise)
                 assert ok, f'diverged at {k}: fp32 gap {gap:.3f} vs bf16 noise {noise:.3f}'
                 # the tries have diverged with the text: resync both from scratch
