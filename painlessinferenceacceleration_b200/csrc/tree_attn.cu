@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -43,7 +45,6 @@ constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
-constexpr int TILES_PER_CTA = 4;        // target tiles per CTA before the KV range is split across CTAs
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,7 +130,7 @@ struct Params {
   const int *d_n, *d_prefix;
   float *ws_acc;           // [n_split, Hq, np, HD]
   float *ws_m, *ws_l;      // [n_split, Hq, np]
-  int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split;
+  int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split, tiles_per_cta;
   float scale_log2;
   __nv_bfloat16 *out;            // [max_nodes, Hq, HD]
   int *counters;                 // [n_groups] arrival counters of the split CTAs (self-resetting)
@@ -161,9 +162,9 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const int hq0 = group * p.heads_per_cta;
   const int hkv = hq0 / (p.n_q_heads / p.n_kv_heads);
   const int tiles_total = (L + BN - 1) / BN;
-  // Work split decided on the device from the live length: aim at >= TILES_PER_CTA tiles per CTA so that short
-  // contexts run as ONE CTA per head group and write the final output directly (no partials, no merge).
-  int ns = (tiles_total + TILES_PER_CTA - 1) / TILES_PER_CTA;
+  // Work split decided on the device from the live length: tiles_per_cta tiles per CTA (more only when the
+  // plan's split limit is reached); a single split writes the final output directly (no partials, no merge).
+  int ns = (tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   if (ns > p.n_split) ns = p.n_split;
   if (ns < 1) ns = 1;
   if (split >= ns) return;
@@ -456,7 +457,7 @@ using namespace pia::attn;
 struct pia_attn_plan {
   pia_attn_config_t cfg;
   CUtensorMap map_k, map_v;
-  int heads_per_cta, n_groups, n_split, mask_words;
+  int heads_per_cta, n_groups, n_split, mask_words, tiles_per_cta;
   int *counters;
   unsigned long long *dbg;
 };
@@ -509,6 +510,8 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
   if (ns < 1) ns = 1;
   if (ns > 64) ns = 64;
   p->n_split = ns;
+  p->tiles_per_cta = 1;
+  if (const char *e = getenv("PIA_ATTN_TILES_PER_CTA")) { int v = atoi(e); if (v >= 1 && v <= 64) p->tiles_per_cta = v; }
   int rc = encode_kv_map(&p->map_k, d_k_cache, *cfg);
   if (rc == PIA_OK) rc = encode_kv_map(&p->map_v, d_v_cache, *cfg);
   if (rc == PIA_OK) {
@@ -565,7 +568,7 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   a.ws_l = a.ws_m + rows;
   a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
   a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.pad_len = pad_len; a.max_seq = p->cfg.max_seq;
-  a.n_split = p->n_split;
+  a.n_split = p->n_split; a.tiles_per_cta = p->tiles_per_cta;
   a.out = (__nv_bfloat16 *)d_out; a.counters = p->counters; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
