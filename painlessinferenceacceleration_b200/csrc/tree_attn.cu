@@ -8,9 +8,10 @@
 //
 // One CTA = (KV split, head group).  A head group is one KV head's worth of rows packed into a single
 // UMMA M=128 tile: 2 query heads x 64 draft rows under GQA, 1 head otherwise (rows 64..127 idle for MHA/64).
-// Warp roles (192 threads):  warp 0 = TMA producer (K/V tiles of 128 keys, 2-stage ring),
+// Warp roles (320 threads):  warp 0 = TMA producer (K/V tiles of 128 keys, 2-stage ring),
 //                            warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
-//                            warps 2-5 = softmax / accumulate, one thread per row (TMEM lane == row).
+//                            warps 2-9 = softmax / accumulate, two threads per row (TMEM lane == row; each
+//                            takes 64 S columns and 64 O columns, row max / sum exchanged through smem).
 // Per 128-key tile:  S = Q K^T (8 x UMMA 128x128x16, fp32 in TMEM, double buffered)
 //                    -> thread-local online softmax in fp32 (no shuffles: a thread owns its row)
 //                    -> P (bf16) to shared memory in the UMMA K-major SWIZZLE_128B layout
@@ -37,14 +38,16 @@ constexpr int BM = 128;      // rows per CTA (UMMA M)
 constexpr int BN = 128;      // keys per tile (UMMA N of QK^T, K extent of PV)
 constexpr int HD = 128;      // head dim
 constexpr int NSTAGE = 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two warps per TMEM lane quadrant)
 constexpr int SUB = 128 * 128;             // bytes of one [128 rows x 64 bf16] swizzle-128B sub-tile
 constexpr int TILE_BYTES = 2 * SUB;        // one 128 x 128 bf16 operand tile
 constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_K = 2 * TILE_BYTES, SMEM_V = SMEM_K + NSTAGE * TILE_BYTES;
 constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;  // + alignment slack
+constexpr int SMEM_XCH = SMEM_BAR + 256;           // row max / row sum exchange between the two column halves
+constexpr int SMEM_TOTAL = SMEM_XCH + 3 * 1024 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr int MAX_SPLIT = 8;            // KV splits per head group (merge keeps all partial rows in flight)
 
 // ------------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -176,7 +179,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
 
   const int rows_used = p.heads_per_cta * p.np;          // 64 (MHA, 64 nodes) or 128
   const bool is_sm_warp = warp >= 2;
-  const int row = ((warp & 3) << 5) | lane;              // TMEM lane this softmax thread owns
+  const int half = is_sm_warp ? (warp - 2) >> 2 : 0;     // which 64 columns of S / O this softmax warp owns
+  const int row = ((warp & 3) << 5) | lane;              // TMEM lane == row (a warp may only touch its quadrant)
   const bool warp_active = is_sm_warp && (((warp & 3) << 5) < rows_used);
   const int hs = row / p.np, node = row % p.np;
   const bool row_live = warp_active && node < n;
@@ -186,9 +190,9 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1); mbar_init(bar_s_full + 8, 1);
-    mbar_init(bar_p_full, rows_used);
+    mbar_init(bar_p_full, 2 * rows_used);
     mbar_init(bar_o_full, 1);
-    mbar_init(bar_q_full, rows_used);
+    mbar_init(bar_q_full, 2 * rows_used);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -256,49 +260,52 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       DBG(4);
     }
   } else if (warp_active) {
-    // ================================================================ softmax + accumulate (one row per thread)
-    // Q rows -> shared memory (UMMA K-major SWIZZLE_128B, [rows x 64] sub-tiles per d-half); all loads first
+    // ================================================================ softmax + accumulate
+    // two threads per row: `half` selects 64 of the 128 S columns (keys) and 64 of the 128 O columns (head dim)
     {
-      uint4 qv[16];
+      uint4 qv[8];  // Q row -> shared memory (UMMA K-major SWIZZLE_128B); each half loads one 64-wide d sub-tile
       const bool have = hs < p.heads_per_cta && node < n;
-      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((long long)node * p.n_q_heads + hq0 + hs) * HD);
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((long long)node * p.n_q_heads + hq0 + hs) * HD) + half * 8;
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) qv[ch] = have ? src[ch] : make_uint4(0, 0, 0, 0);
+      for (int ch = 0; ch < 8; ++ch) qv[ch] = have ? src[ch] : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch)
-        *reinterpret_cast<uint4 *>(sm + SMEM_Q + (ch >> 3) * SUB + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = qv[ch];
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4 *>(sm + SMEM_Q + half * SUB + row * 128 + ((ch ^ (row & 7)) << 4)) = qv[ch];
       fence_async_smem();
       mbar_arrive(bar_q_full);
     }
-    if (row == 0) DBG(5);
+    if (row == 0 && half == 0) DBG(5);
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const int pair_bar = 1 + (warp & 3);  // named barrier shared by the two warps of this lane quadrant
     unsigned long long mrow[2] = {0ull, 0ull};
     if (row_live) {
       mrow[0] = p.mask[(long long)node * p.mask_words];
       if (p.mask_words > 1) mrow[1] = p.mask[(long long)node * p.mask_words + 1];
     }
-    float acc[HD];
+    float acc[64];
 #pragma unroll
-    for (int j = 0; j < HD; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    uint32_t v[32];
+    uint32_t sv[64];
     for (int i = 0; i < ntile; ++i) {
-      const int key0 = (t0 + i) * BN;
-      const uint32_t s_addr = tmem + lane_addr + ((i & 1) ? TM_S1 : TM_S0);
+      const int key0 = (t0 + i) * BN + half * 64;
+      const uint32_t s_addr = tmem + lane_addr + ((i & 1) ? TM_S1 : TM_S0) + half * 64;
       mbar_wait(bar_s_full + 8 * (i & 1), (i >> 1) & 1);
       tc_fence_after();
-      if (row == 0 && i == 0) DBG(6);
-      const bool all_visible = (key0 >= p.pad_len) && (key0 + BN <= P);
+      if (row == 0 && half == 0 && i == 0) DBG(6);
+      tmem_ld32(s_addr, sv);
+      tmem_ld32(s_addr + 32, sv + 32);
+      tmem_ld_wait();
       // 32-bit visibility word of keys [kb, kb+32): prefix keys [pad_len, P) are visible to every row, the n draft
-      // keys follow the row's ancestor bits.  (Kept out of the unrolled element loops: the code must stay small
-      // enough for the instruction cache - the first version spent 16 us per tile fetching instructions.)
+      // keys follow the row's ancestor bits (bits beyond the live nodes are never set in the trie's mask rows)
+      const bool all_visible = ((t0 + i) * BN >= p.pad_len) && ((t0 + i) * BN + BN <= P);
       auto vis32 = [&](int kb) -> uint32_t {
         if (all_visible) return 0xffffffffu;
         uint32_t m = 0;
-        const int lo = kb < p.pad_len ? p.pad_len : kb;       // prefix part: [max(kb,pad), min(kb+32,P))
+        const int lo = kb < p.pad_len ? p.pad_len : kb;
         const int hi = kb + 32 < P ? kb + 32 : P;
         if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << (lo - kb);
-        const int j0 = kb - P;                                 // draft index of bit 0 (may be negative)
+        const int j0 = kb - P;
         if (j0 + 32 > 0 && j0 < n) {
           uint32_t d;
           if (j0 < 0) d = (uint32_t)(mrow[0] << (-j0));
@@ -307,78 +314,76 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
             if (j0 > 32) x |= mrow[1] << (64 - j0);
             d = (uint32_t)x;
           } else d = (uint32_t)(mrow[1] >> (j0 - 64));
-          // bits beyond the n live nodes are never set in mrow (rows of the trie mask only name nodes < n)
           m |= d;
         }
         return m;
       };
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        const uint32_t vm = vis32(key0 + c * 32);
+      const uint32_t vm0 = vis32(key0), vm1 = vis32(key0 + 32);
+      float m_half = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = (vm >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY;
-          m_tile = fmaxf(m_tile, s);
-        }
+      for (int j = 0; j < 32; ++j) {
+        if ((vm0 >> j) & 1u) m_half = fmaxf(m_half, __uint_as_float(sv[j]));
+        if ((vm1 >> j) & 1u) m_half = fmaxf(m_half, __uint_as_float(sv[32 + j]));
       }
+      // row max across the two halves (double-buffered exchange slot, one named barrier per quadrant pair)
+      float *xm = reinterpret_cast<float *>(sm + SMEM_XCH) + (i & 1) * 256;
+      xm[half * 128 + row] = m_half;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float m_tile = fmaxf(m_half, xm[(half ^ 1) * 128 + row]);
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_use);
-      // pass 2: p = exp2(s*scale - m), P -> smem (bf16, swizzled), row sum
+      // p = exp2(s*scale - m) -> bf16 -> shared memory (this half = one 64-key sub-tile of P), row sum
       float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(s_addr + c * 32, v);
-        tmem_ld_wait();
-        const uint32_t vm = vis32(key0 + c * 32);
-        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = (vm >> j) & 1u ? ex2(__uint_as_float(v[j]) * p.scale_log2 - m_use) : 0.f;
-          const float p1 = (vm >> (j + 1)) & 1u ? ex2(__uint_as_float(v[j + 1]) * p.scale_log2 - m_use) : 0.f;
+      for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks = 64 keys
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = c * 8 + e * 2;
+          const uint32_t vm = j < 32 ? vm0 : vm1;
+          const float p0 = (vm >> (j & 31)) & 1u ? ex2(__uint_as_float(sv[j]) * p.scale_log2 - m_use) : 0.f;
+          const float p1 = (vm >> ((j + 1) & 31)) & 1u ? ex2(__uint_as_float(sv[j + 1]) * p.scale_log2 - m_use) : 0.f;
           const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
           // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
           l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
-          pk[j >> 1] = *reinterpret_cast<const uint32_t *>(&b);
+          pk[e] = *reinterpret_cast<const uint32_t *>(&b);
         }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {  // 4 x 16 B chunks = 32 keys
-          const int ch = c * 4 + q4;      // 16 B chunk index along the 128-key row
-          uint8_t *dst = sm + SMEM_P + (ch >> 3) * SUB + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[q4 * 4], pk[q4 * 4 + 1], pk[q4 * 4 + 2], pk[q4 * 4 + 3]);
-        }
+        *reinterpret_cast<uint4 *>(sm + SMEM_P + half * SUB + row * 128 + ((c ^ (row & 7)) << 4)) =
+            make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
       fence_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       tc_fence_before();    // order our tcgen05.ld of S before the issuer's next MMA into this S buffer
       mbar_arrive(bar_p_full);
-      if (row == 0 && i == 0) DBG(7);
-      // accumulate this tile's PV
+      if (row == 0 && half == 0 && i == 0) DBG(7);
+      // accumulate this tile's PV (this half's 64 head-dim columns)
       mbar_wait(bar_o_full, i & 1);
       tc_fence_after();
-      if (row == 0 && i == 0) DBG(8);
+      if (row == 0 && half == 0 && i == 0) DBG(8);
+      tmem_ld32(tmem + lane_addr + TM_O + half * 64, sv);
+      tmem_ld32(tmem + lane_addr + TM_O + half * 64 + 32, sv + 32);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(tmem + lane_addr + TM_O + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[c * 32 + j] = acc[c * 32 + j] * alpha + __uint_as_float(v[j]);
-      }
+      for (int j = 0; j < 64; ++j) acc[j] = acc[j] * alpha + __uint_as_float(sv[j]);
       tc_fence_before();
     }
-    if (row == 0) DBG(9);
+    if (row == 0 && half == 0) DBG(9);
+    // total row sum = both halves (same running max, so the partial sums just add)
+    {
+      float *xl = reinterpret_cast<float *>(sm + SMEM_XCH) + 512;
+      xl[half * 128 + row] = l_run;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      l_run += xl[(half ^ 1) * 128 + row];
+    }
     if (ns == 1) {
-      // single split: normalise and write the final bf16 row
+      // single split: normalise and write this half of the final bf16 row
       if (row_live) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)node * p.n_q_heads + hq0 + hs) * HD);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)node * p.n_q_heads + hq0 + hs) * HD + half * 64);
 #pragma unroll
-        for (int j = 0; j < HD / 8; ++j) {
+        for (int j = 0; j < 8; ++j) {
           __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
           __nv_bfloat162 b1 = __floats2bfloat162_rn(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv);
           __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv);
@@ -389,13 +394,12 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       }
     } else if (row_live) {
       const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
-      p.ws_m[o] = m_run;
-      p.ws_l[o] = l_run;
-      float4 *dst = reinterpret_cast<float4 *>(p.ws_acc + o * HD);
+      if (half == 0) { p.ws_m[o] = m_run; p.ws_l[o] = l_run; }
+      float4 *dst = reinterpret_cast<float4 *>(p.ws_acc + o * HD + half * 64);
 #pragma unroll
-      for (int j = 0; j < HD / 4; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      for (int j = 0; j < 16; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
     }
-    if (row == 0) DBG(10);
+    if (row == 0 && half == 0) DBG(10);
   }
   tc_fence_before();
   __threadfence();
@@ -415,32 +419,49 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     __syncthreads();
     if (s_last) {
       __threadfence();
-      // thread = (row, 8-wide d chunk): out = sum_s acc_s 2^(m_s - M) / sum_s l_s 2^(m_s - M)
-      const int items = rows_used * (HD / 8);
+      // (1) per-row split weights  wn[r][s] = 2^(m_s - M) / sum_s l_s 2^(m_s - M)  into shared memory (P tile is free)
+      float *wn = reinterpret_cast<float *>(sm + SMEM_P);  // [rows_used][MAX_SPLIT]
+      for (int r = tid; r < rows_used; r += NTHREADS) {
+        const int rh = r / p.np, rn = r % p.np;
+        float ms[MAX_SPLIT], ls[MAX_SPLIT];
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
+          const long long o = ((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn;
+          const bool on = s2 < ns && rn < n;
+          ms[s2] = on ? p.ws_m[o] : -INFINITY;
+          ls[s2] = on ? p.ws_l[o] : 0.f;
+        }
+        float M = -INFINITY, den = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) M = fmaxf(M, ms[s2]);
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) { ms[s2] = ms[s2] == -INFINITY ? 0.f : ex2(ms[s2] - M); den += ls[s2] * ms[s2]; }
+        const float inv = den > 0.f ? 1.f / den : 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) wn[r * MAX_SPLIT + s2] = ms[s2] * inv;
+      }
+      __syncthreads();
+      // (2) out[r][:] = sum_s wn[r][s] * acc_s[r][:], thread = (row, 4 floats), loads of all splits in flight together
+      const int items = rows_used * (HD / 4);
       for (int it = tid; it < items; it += NTHREADS) {
-        const int r = it / (HD / 8), ch = it % (HD / 8);
+        const int r = it / (HD / 4), c4 = it % (HD / 4);
         const int rh = r / p.np, rn = r % p.np;
         if (rn >= n) continue;
-        float M = -INFINITY;
-        for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, p.ws_m[((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn]);
-        float den = 0.f, num[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int s2 = 0; s2 < ns; ++s2) {
+        float4 a[MAX_SPLIT];
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
           const long long o = ((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn;
-          const float m = p.ws_m[o];
-          if (m == -INFINITY) continue;
-          const float w = exp2f(m - M);
-          den += p.ws_l[o] * w;
-          const float4 a0 = reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[2 * ch];
-          const float4 a1 = reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[2 * ch + 1];
-          num[0] += a0.x * w; num[1] += a0.y * w; num[2] += a0.z * w; num[3] += a0.w * w;
-          num[4] += a1.x * w; num[5] += a1.y * w; num[6] += a1.z * w; num[7] += a1.w * w;
+          a[s2] = s2 < ns ? reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const float inv = den > 0.f ? 1.f / den : 0.f;
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(num[0] * inv, num[1] * inv), b1 = __floats2bfloat162_rn(num[2] * inv, num[3] * inv);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(num[4] * inv, num[5] * inv), b3 = __floats2bfloat162_rn(num[6] * inv, num[7] * inv);
-        reinterpret_cast<uint4 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[ch] =
-            make_uint4(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1),
-                       *reinterpret_cast<uint32_t *>(&b2), *reinterpret_cast<uint32_t *>(&b3));
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
+          const float w = wn[r * MAX_SPLIT + s2];
+          acc4.x += a[s2].x * w; acc4.y += a[s2].y * w; acc4.z += a[s2].z * w; acc4.w += a[s2].w * w;
+        }
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(acc4.x, acc4.y), b1 = __floats2bfloat162_rn(acc4.z, acc4.w);
+        reinterpret_cast<uint2 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[c4] =
+            make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
       }
     }
   }
@@ -508,7 +529,7 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
   int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : (2 * n_sm + p->n_groups - 1) / p->n_groups;
   if (ns > max_tiles) ns = max_tiles;
   if (ns < 1) ns = 1;
-  if (ns > 64) ns = 64;
+  if (ns > MAX_SPLIT) ns = MAX_SPLIT;
   p->n_split = ns;
   p->tiles_per_cta = 1;
   if (const char *e = getenv("PIA_ATTN_TILES_PER_CTA")) { int v = atoi(e); if (v >= 1 && v <= 64) p->tiles_per_cta = v; }

@@ -378,15 +378,26 @@ constexpr unsigned long long HEMPTY = ~0ull;
 
 struct Hist { unsigned long long key[HCAP]; unsigned cnt[HCAP]; };
 
-__device__ __forceinline__ void hist_add(Hist *h, unsigned long long bits, int *ovf) {
+__device__ __forceinline__ void hist_add(Hist *h, unsigned long long bits, unsigned count, int *ovf) {
   unsigned s = (unsigned)((bits * 0x9E3779B97F4A7C15ull) >> 54) & (HCAP - 1);
   for (int probe = 0; probe < HCAP; ++probe) {
     unsigned long long old = atomicCAS(&h->key[s], HEMPTY, bits);
-    if (old == HEMPTY || old == bits) { atomicAdd(&h->cnt[s], 1u); return; }
+    if (old == HEMPTY || old == bits) { atomicAdd(&h->cnt[s], count); return; }
     s = (s + 1) & (HCAP - 1);
   }
   *ovf = 1;
 }
+// per-thread run-length front end: n-gram counts are overwhelmingly 1.0, so consecutive equal values are
+// accumulated in registers and reach the shared histogram (one contended address otherwise) only on a change
+struct HistRun {
+  unsigned long long key; unsigned cnt;
+  __device__ __forceinline__ void add(Hist *h, unsigned long long bits, int *ovf) {
+    if (cnt && bits == key) { ++cnt; return; }
+    if (cnt) hist_add(h, key, cnt, ovf);
+    key = bits; cnt = 1;
+  }
+  __device__ __forceinline__ void flush(Hist *h, int *ovf) { if (cnt) hist_add(h, key, cnt, ovf); cnt = 0; }
+};
 
 // sorted(values, reverse=True)[rank-1] from the histogram; `found` stays 0 if rank is out of range
 __device__ void hist_kth(const Hist *h, long long rank, unsigned long long *result, int *found) {
@@ -546,16 +557,20 @@ __device__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree
   const bool need_out = (mode == PIA_MODE_OUTPUT) || (mode == PIA_MODE_MIX && min_out_sz > 0);
   {
     long long my_live = 0, my_in = 0, my_out = 0;
+    HistRun run_in, run_out;
+    run_in.cnt = 0; run_in.key = 0; run_out.cnt = 0; run_out.key = 0;
     auto visit = [&](int id, const Node &nd) -> bool {
       const float fi = load_fi(D, nd, id, idx);
       const double fo = nd.fo;
       if (!(fo > 0.0 || fi > 0.f)) return false;
       ++my_live; my_in += fi > 0.f; my_out += fo > 0.0;
-      if (need_in) hist_add(&S->hin, dbits((double)fi), &S->hist_ovf);
-      if (need_out) hist_add(&S->hout, dbits(fo), &S->hist_ovf);
+      if (need_in) run_in.add(&S->hin, dbits((double)fi), &S->hist_ovf);
+      if (need_out) run_out.add(&S->hout, dbits(fo), &S->hist_ovf);
       return true;
     };
     bfs_below(D, start, fr0, fr1, &S->bfs, visit, nv, ne);
+    run_in.flush(&S->hin, &S->hist_ovf);
+    run_out.flush(&S->hout, &S->hist_ovf);
     if (my_live) { atomicAdd((unsigned long long *)&S->n_live, (unsigned long long)my_live);
                    atomicAdd((unsigned long long *)&S->n_in, (unsigned long long)my_in);
                    atomicAdd((unsigned long long *)&S->n_out, (unsigned long long)my_out); }
