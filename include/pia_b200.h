@@ -163,12 +163,33 @@ int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint
                       void *stream);
 
 /* ============================================================================================
+ * Weight-streaming GEMM of the verify forward: Y[t, n] = sum_k X[t, k] W[n, k]  (X: <= 64 draft rows, W = an
+ * nn.Linear weight [N, K] bf16), i.e. the projections of modeling_llama.py:254-256, :303, :185-186, :769.
+ * TMA + tcgen05, weights read once; see csrc/gemm_ws.cu.
+ * ============================================================================================ */
+typedef struct pia_gemm_plan pia_gemm_plan_t;
+/* d_x : [x_rows >= 64, K] bf16 activation buffer the plan's TMA descriptor is bound to; K % 64 == 0.
+ * split_k > 1 splits the K range over CTAs (for projections with few 128-row weight tiles). Synchronous. */
+int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d_x, int x_rows, int split_k,
+                         pia_gemm_plan_t **out);
+int pia_gemm_plan_destroy(pia_gemm_plan_t *g);
+int pia_gemm_plan_splits(const pia_gemm_plan_t *g);
+/* splits == 1: d_out is bf16 [rows_cap, N]; splits > 1: d_out is fp32 [splits][64][N] partial slices (sum them in
+ * slice order, e.g. with pia_rmsnorm_partials).  rows <= 64 rows are written. */
+int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream);
+
+/* ============================================================================================
  * Fused elementwise pieces of the verify forward (all bf16 I/O, fp32 math)
  * ============================================================================================ */
 /* RMSNorm (modeling_llama.py:76-90): y = (w * (x * rsqrt(mean(x^2)+eps)).to(bf16)) ; rows x hidden.
  * If d_residual_in != NULL: x <- x + residual_in first and the sum is written to d_residual_out. */
 int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows, int hidden,
                 void *d_residual_out, void *d_y, void *stream);
+/* same, with x given as `n_parts` fp32 split-K slices of pia_gemm_run ([n_parts][part_stride] floats, row-major
+ * [rows, hidden] inside a slice): x = bf16(sum of slices), i.e. what a bf16 GEMM output would have held */
+int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t part_stride, const void *d_residual_in,
+                         const void *d_weight, float eps, int rows, int hidden, void *d_residual_out, void *d_y,
+                         void *stream);
 /* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; position of node i =
  * P - pad_len + depth_i = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection
  * output).  d_cos / d_sin : [max_pos, D/2] bf16 tables (cos/sin already rounded to the model dtype exactly as

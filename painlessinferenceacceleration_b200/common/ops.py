@@ -22,6 +22,47 @@ def rmsnorm(x, residual_in, weight, eps, residual_out, y):
                                  _p(y), _s()))
 
 
+def rmsnorm_partials(parts, residual_in, weight, eps, residual_out, y):
+    """parts: fp32 [n_parts, 64, hidden] split-K slices of a Gemm"""
+    n_parts, prow, hidden = parts.shape
+    rows = y.shape[0]
+    L.check(L.load().pia_rmsnorm_partials(_p(parts), n_parts, prow * hidden, _p(residual_in), _p(weight), float(eps),
+                                          rows, hidden, _p(residual_out), _p(y), _s()))
+
+
+class Gemm(object):
+    """pia_gemm_plan_t: Y = X @ W^T for one (weight, activation buffer) pair; `out` is bf16 [rows, N] when the plan
+    has one K split, else fp32 [splits, 64, N]"""
+
+    def __init__(self, weight, x, split_k=1):
+        N, K = weight.shape
+        assert x.shape[1] == K and x.is_contiguous() and weight.is_contiguous()
+        self.lib = L.load()
+        self.h = L.vp()
+        with torch.cuda.device(weight.device):
+            L.check(self.lib.pia_gemm_plan_create(_p(weight), N, K, _p(x), x.shape[0], split_k, C.byref(self.h)))
+        self.splits = self.lib.pia_gemm_plan_splits(self.h)
+        self.N = N
+        self._keep = (weight, x)
+        if self.splits == 1:
+            self.out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=weight.device)
+        else:
+            self.out = torch.empty((self.splits, 64, N), dtype=torch.float32, device=weight.device)
+
+    def run(self, rows=64, out=None):
+        o = out if out is not None else self.out
+        L.check(self.lib.pia_gemm_run(self.h, rows, _p(o), _s()))
+        return o
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.pia_gemm_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 def rope_kv_append(qkv, mask, n, prefix_len, pad_len, n_q_heads, n_kv_heads, head_dim, cos, sin, q_out, k_layer,
                    v_layer, max_seq):
     rows = qkv.shape[0]

@@ -18,13 +18,32 @@ __device__ __forceinline__ float bf(float x) { return __bfloat162float(__float2b
 union Pack8 { uint4 u; __nv_bfloat16 h[8]; };
 
 // one CTA per row; hidden % 8 == 0
-__global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const __nv_bfloat16 *res_in,
+// x comes either as bf16 [rows, hidden] or as `n_parts` fp32 split-K slices [n_parts][part_rows][hidden] of the
+// producing GEMM (summed in slice order and rounded to bf16 first, i.e. what a bf16 GEMM output would hold)
+__device__ __forceinline__ Pack8 load_x8(const __nv_bfloat16 *x, const float *parts, int n_parts, long long part_stride,
+                                         long long off) {
+  Pack8 a;
+  if (parts == nullptr) { a.u = *reinterpret_cast<const uint4 *>(x + off); return a; }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < n_parts; ++s) {
+    const float4 lo = *reinterpret_cast<const float4 *>(parts + s * part_stride + off);
+    const float4 hi = *reinterpret_cast<const float4 *>(parts + s * part_stride + off + 4);
+    acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
+    acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a.h[j] = __float2bfloat16_rn(acc[j]);
+  return a;
+}
+
+__global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const float *parts, int n_parts,
+                                                 long long part_stride, const __nv_bfloat16 *res_in,
                                                  const __nv_bfloat16 *w, float eps, int hidden,
                                                  __nv_bfloat16 *res_out, __nv_bfloat16 *y) {
   __shared__ float red[16];
   const int row = blockIdx.x, tid = threadIdx.x;
   const int nvec = hidden >> 3;
-  const uint4 *xv = reinterpret_cast<const uint4 *>(x + (long long)row * hidden);
+  const long long row_off = (long long)row * hidden;
   const uint4 *rv = res_in ? reinterpret_cast<const uint4 *>(res_in + (long long)row * hidden) : nullptr;
   uint4 *rov = res_out ? reinterpret_cast<uint4 *>(res_out + (long long)row * hidden) : nullptr;
   float ss = 0.f;
@@ -32,7 +51,7 @@ __global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const _
   Pack8 keep[2];
   int cnt = 0;
   for (int v = tid; v < nvec; v += 512) {
-    Pack8 a; a.u = xv[v];
+    Pack8 a = load_x8(x, parts, n_parts, part_stride, row_off + v * 8);
     if (rv) {
       Pack8 r; r.u = rv[v];
 #pragma unroll
@@ -59,7 +78,7 @@ __global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const _
     Pack8 a;
     if (cnt < 2) a = keep[cnt];
     else {  // (only for hidden > 8192) recompute the residual sum
-      a.u = xv[v];
+      a = load_x8(x, parts, n_parts, part_stride, row_off + v * 8);
       if (rv) { Pack8 r; r.u = rv[v];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a.h[j] = __float2bfloat16_rn(__bfloat162float(a.h[j]) + __bfloat162float(r.h[j])); }
@@ -154,7 +173,20 @@ using namespace pia::fused;
 extern "C" int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows,
                            int hidden, void *d_residual_out, void *d_y, void *stream) {
   PIA_REQUIRE(d_x && d_weight && d_y && rows > 0 && hidden > 0 && hidden % 8 == 0, "bad rmsnorm arguments");
-  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, (const __nv_bfloat16 *)d_residual_in,
+  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, nullptr, 0, 0,
+                                                   (const __nv_bfloat16 *)d_residual_in,
+                                                   (const __nv_bfloat16 *)d_weight, eps, hidden,
+                                                   (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+extern "C" int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t part_stride, const void *d_residual_in,
+                                    const void *d_weight, float eps, int rows, int hidden, void *d_residual_out,
+                                    void *d_y, void *stream) {
+  PIA_REQUIRE(d_x_parts && n_parts >= 1 && d_weight && d_y && rows > 0 && hidden > 0 && hidden % 8 == 0, "bad rmsnorm arguments");
+  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>(nullptr, d_x_parts, n_parts, (long long)part_stride,
+                                                   (const __nv_bfloat16 *)d_residual_in,
                                                    (const __nv_bfloat16 *)d_weight, eps, hidden,
                                                    (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y);
   PIA_LAUNCH_CHECK();

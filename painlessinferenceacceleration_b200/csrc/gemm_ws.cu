@@ -1,0 +1,271 @@
+// Weight-streaming GEMM for the verify forward (sm_100a: TMA + tcgen05 + TMEM).
+//
+//   Y[t, n] = sum_k X[t, k] * W[n, k]        X: [TOK <= 64 draft rows, K] bf16,  W: [N, K] bf16 (nn.Linear weight)
+//
+// i.e. the q/k/v/o/gate/up/down/lm_head projections of the reference's patched forward
+// (models/llama/modeling_llama.py:254-256, :303, :185-186, :769) at the draft's row count.  With <= 64 rows the
+// GEMM is a pure weight stream (arithmetic intensity = rows FLOP/B << ridge), so the kernel is built around HBM:
+//   * swap-AB: 128 weight rows are the UMMA M dimension, the 64 tokens the UMMA N dimension; D[128 x 64] fp32 lives in
+//     64 TMEM columns, so the big operand (W) is read exactly once and only the small one (X, <= 1.4 MB, L2 resident)
+//     is re-read per tile;
+//   * one CTA per (128-row weight tile, K split): warp 0 = TMA producer over a 4-stage mbarrier ring of
+//     {W tile 128x64 (16 KB), X tile 64x64 (8 KB)} SWIZZLE_128B boxes, warp 1 = single-thread tcgen05.mma issuer
+//     (4 x UMMA 128x64x16 per stage), warps 2-5 = epilogue (tcgen05.ld -> bf16 / fp32 store).  ~100 KB of shared
+//     memory per CTA so that two CTAs share an SM and one CTA's prologue/epilogue hides behind the other's stream;
+//   * projections with few weight tiles (o_proj, down_proj: N = 4096 -> 32 tiles) split K across CTAs and write fp32
+//     partial slices that the consumer (k_rmsnorm_partials) sums in a fixed order - deterministic, no atomics.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <new>
+
+#include "common.cuh"
+
+namespace pia {
+namespace gemm {
+
+constexpr int BMW = 128;   // weight rows per tile (UMMA M)
+constexpr int BK = 64;     // k elements per stage (one 128-byte swizzle row)
+constexpr int TOK = 64;    // token rows (UMMA N)
+constexpr int NSTAGE = 4;
+constexpr int NTHREADS = 192;
+constexpr int W_BYTES = BMW * BK * 2, X_BYTES = TOK * BK * 2, STAGE_BYTES = W_BYTES + X_BYTES;
+constexpr int SMEM_BAR = NSTAGE * STAGE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 128 + 1024;
+constexpr int TMEM_COLS = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(addr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;           // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32; // SBO
+  d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+// bf16 x bf16 -> fp32, M = 128, N = TOK, both operands K-major
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOK >> 3) << 17) | ((uint32_t)(BMW >> 4) << 24);
+
+struct Params {
+  int N, K, n_split, chunks_per_split, n_chunks, rows;
+  __nv_bfloat16 *out_bf16;  // [rows_cap, N]            (n_split == 1)
+  float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_full = base + SMEM_BAR, bar_empty = bar_full + 8 * NSTAGE, bar_acc = bar_empty + 8 * NSTAGE;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 16);
+  const int n0 = blockIdx.x * BMW, split = blockIdx.y;
+  const int c0 = split * p.chunks_per_split;
+  int c1 = c0 + p.chunks_per_split;
+  if (c1 > p.n_chunks) c1 = p.n_chunks;
+  const int nch = c1 - c0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nch; ++i) {
+        const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        const uint32_t wd = base + s * STAGE_BYTES, xd = wd + W_BYTES;
+        tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
+        tma_load_2d(xd, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nch; ++i) {
+        const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t wa = base + s * STAGE_BYTES, xa = wa + W_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / 16; ++j)
+          umma_bf16(tmem, kmajor_desc(wa + j * 32), kmajor_desc(xa + j * 32), IDESC, (i | j) != 0);
+        umma_commit(bar_empty + 8 * s);
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // epilogue: thread = one weight row n (TMEM lane), 64 token values in registers
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    uint32_t v[64];
+    if (nch > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      const uint32_t a = tmem + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(a, v);
+      tmem_ld32(a + 32, v + 32);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int t = 0; t < 64; ++t) v[t] = 0u;
+    }
+    if (n < p.N) {
+      if (p.n_split == 1) {
+#pragma unroll
+        for (int t = 0; t < TOK; ++t)
+          if (t < p.rows) p.out_bf16[(long long)t * p.N + n] = __float2bfloat16_rn(__uint_as_float(v[t]));
+      } else {
+        float *o = p.out_f32 + (long long)split * TOK * p.N;
+#pragma unroll
+        for (int t = 0; t < TOK; ++t)
+          if (t < p.rows) o[(long long)t * p.N + n] = __uint_as_float(v[t]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+  }
+}
+
+}  // namespace gemm
+}  // namespace pia
+
+using namespace pia;
+using namespace pia::gemm;
+
+struct pia_gemm_plan {
+  CUtensorMap map_w, map_x;
+  Params p;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                     uint32_t box_outer, CUtensorMapL2promotion promo) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void *ptr = nullptr;
+    PIA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    PIA_REQUIRE(ptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    fn = (EncodeTiledFn)ptr;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PIA_ERR_CUDA; }
+  return PIA_OK;
+}
+
+extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d_x, int x_rows, int split_k,
+                                    pia_gemm_plan_t **out) {
+  PIA_REQUIRE(d_w && d_x && out, "null argument");
+  PIA_REQUIRE(N > 0 && K > 0 && K % BK == 0, "K must be a multiple of %d", BK);
+  PIA_REQUIRE(x_rows >= TOK, "the activation buffer must hold at least %d rows", TOK);
+  PIA_REQUIRE((reinterpret_cast<uintptr_t>(d_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, "operands must be 16-byte aligned");
+  pia_gemm_plan *g = new (std::nothrow) pia_gemm_plan();
+  PIA_REQUIRE(g, "out of host memory");
+  const int n_chunks = K / BK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > n_chunks) split_k = n_chunks;
+  g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks;
+  g->p.chunks_per_split = (n_chunks + split_k - 1) / split_k;
+  g->p.n_split = (n_chunks + g->p.chunks_per_split - 1) / g->p.chunks_per_split;
+  g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr;
+  int rc = encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc == PIA_OK) rc = encode_2d(&g->map_x, d_x, (uint64_t)K, (uint64_t)x_rows, BK, TOK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc == PIA_OK) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
+  }
+  if (rc != PIA_OK) { delete g; return rc; }
+  *out = g;
+  return PIA_OK;
+}
+
+extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) { delete g; return PIA_OK; }
+extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? g->p.n_split : 0; }
+
+extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream) {
+  PIA_REQUIRE(g && d_out, "null argument");
+  PIA_REQUIRE(rows >= 1 && rows <= TOK, "rows %d outside [1,%d]", rows, TOK);
+  Params p = g->p;
+  p.rows = rows;
+  if (p.n_split == 1) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
+  dim3 grid((p.N + BMW - 1) / BMW, p.n_split);
+  k_gemm_ws<<<grid, NTHREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}

@@ -1,0 +1,46 @@
+# -*- coding: utf-8 -*-
+"""pia weight-streaming GEMM vs cuBLAS (torch.mm) at the Llama-2-7B decode shapes, 32 distinct weights per shape
+(so no weight is L2 resident), CUDA-graph replay, CUDA events."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from painlessinferenceacceleration_b200.common import ops  # noqa: E402
+
+dev = 'cuda:0'
+NL = 32
+
+
+def timeit(fn, per, reps=20):
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * per)
+
+
+for name, N, K, splits in [('qkv', 12288, 4096, (1, 2)), ('o', 4096, 4096, (1, 2, 4, 8)), ('gate_up', 22016, 4096, (1, 2)),
+                           ('down', 4096, 11008, (2, 4, 8)), ('lm_head', 32000, 4096, (1,))]:
+    nl = NL if N * K < 1.5e8 else 8
+    ws = [(torch.randn((N, K), device=dev) * 0.02).to(torch.bfloat16) for _ in range(nl)]
+    x = torch.randn((64, K), device=dev).to(torch.bfloat16)
+    by = N * K * 2
+    t = timeit(lambda: [torch.mm(x, w.t()) for w in ws], nl)
+    print(f'{name:8s} cuBLAS           {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
+    for s in splits:
+        gs = [ops.Gemm(w, x, split_k=s) for w in ws]
+        t = timeit(lambda: [g.run(64) for g in gs], nl)
+        print(f'{name:8s} pia split_k={s:<2d}   {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
+        del gs
+    del ws

@@ -233,3 +233,49 @@ def test_accept_walk_and_kv_compact(penalty):
         # rows [0, P0] untouched, accepted draft rows moved next to the prefix (:894-907)
         keep = list(range(P0 + 1)) + [P0 + j for j in nodes[1:]]
         assert torch.equal(kc[:, :, :len(keep)], k0[:, :, keep]) and torch.equal(vc[:, :, :len(keep)], v0[:, :, keep])
+
+
+@pytest.mark.parametrize('N,K,split', [(256, 128, 1), (12288, 4096, 1), (4096, 4096, 4), (22016, 4096, 1),
+                                       (4096, 11008, 4), (32000, 4096, 1), (4096, 4096, 1), (1024, 14336, 7)])
+def test_gemm_weight_streaming(N, K, split):
+    """tcgen05 weight-streaming GEMM vs an fp32 matmul of the same bf16 operands (nn.Linear semantics,
+    modeling_llama.py:254-256/:303/:185-186/:769).  Tolerance: one bf16 rounding of the fp32 result."""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(N + K)
+    w = (torch.randn((N, K), device=DEV) * 0.05).to(torch.bfloat16)
+    x = torch.randn((64, K), device=DEV).to(torch.bfloat16)
+    g = ops.Gemm(w, x, split_k=split)
+    out = g.run(64)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    if g.splits == 1:
+        got = out.float()
+    else:
+        assert out.shape == (g.splits, 64, N)
+        got = out.sum(0)
+    err = (got - ref).abs().max().item()
+    assert torch.allclose(got, ref, atol=2e-2, rtol=1.6e-2), f'max abs err {err}'
+    # fewer live rows: rows beyond `rows` are left untouched
+    if g.splits == 1:
+        out.fill_(7.0)
+        g.run(5)
+        torch.cuda.synchronize()
+        assert torch.allclose(out[:5].float(), ref[:5], atol=2e-2, rtol=1.6e-2) and float(out[5:].float().min()) == 7.0
+
+
+def test_rmsnorm_partials_matches_bf16_input():
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(3)
+    hidden = 4096
+    parts = torch.randn((4, 64, hidden), device=DEV)
+    r = torch.randn((64, hidden), device=DEV).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn((hidden,), device=DEV)).to(torch.bfloat16)
+    x = parts.sum(0).to(torch.bfloat16)
+    y0, r0 = torch.empty_like(r), torch.empty_like(r)
+    y1, r1 = torch.empty_like(r), torch.empty_like(r)
+    ops.rmsnorm(x, r, w, 1e-6, r0, y0)
+    ops.rmsnorm_partials(parts, r, w, 1e-6, r1, y1)
+    torch.cuda.synchronize()
+    # the slice sum is taken in slice order in fp32, like torch's sum over dim 0 of 4 slices up to association
+    assert (r0 != r1).float().mean().item() < 0.02 and (y0 != y1).float().mean().item() < 0.02
+    assert torch.allclose(y0.float(), y1.float(), atol=2e-2, rtol=2e-2)
