@@ -26,6 +26,28 @@ from .lookahead_cache import LookaheadCache
 from .lookahead_generation_utils import GenerationMode, LookaheadDecoderOnlyOutput
 
 
+class _Bufs(object):
+    """activation buffers of one forward pass over `rows` token rows split into 64|128-row attention chunks"""
+
+    def __init__(self, g, rows, dev, with_logits):
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        hid, qkv_dim = g['hidden'], (g['n_q_heads'] + 2 * g['n_kv_heads']) * g['head_dim']
+        self.rows = rows
+        self.ids = torch.zeros((rows,), dtype=torch.int32, device=dev)
+        self.n_total = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.h = torch.zeros((rows, hid), **bf)
+        self.resid = torch.zeros((rows, hid), **bf)
+        self.y = torch.zeros((rows, hid), **bf)
+        self.qkv = torch.zeros((rows, qkv_dim), **bf)
+        self.q = torch.zeros((rows, g['n_q_heads'], g['head_dim']), **bf)
+        self.attn = torch.zeros((rows, g['n_q_heads'] * g['head_dim']), **bf)
+        self.logits = torch.zeros((rows, g['vocab']), **bf) if with_logits else None
+        self.chunks = []
+
+    def set_chunk_rows(self, n):
+        pass
+
+
 class _Runtime(object):
     """device-resident state of one model's draft-verify loop (built once per (max_seq, max_nodes))"""
 
@@ -62,15 +84,20 @@ class _Runtime(object):
         # host-visible step record: [count, finished, n, status, tokens...]
         self.record = torch.zeros((4 + R,), **i32)
         self.record_host = torch.zeros((4 + R,), dtype=torch.int32).pin_memory()
-        # activations
-        hid, qkv_dim = g['hidden'], (g['n_q_heads'] + 2 * g['n_kv_heads']) * g['head_dim']
-        self.h = torch.zeros((R, hid), **bf)
-        self.resid = torch.zeros((R, hid), **bf)
-        self.y = torch.zeros((R, hid), **bf)
-        self.qkv = torch.zeros((R, qkv_dim), **bf)
-        self.q = torch.zeros((R, g['n_q_heads'], g['head_dim']), **bf)
-        self.attn = torch.zeros((R, g['n_q_heads'] * g['head_dim']), **bf)
-        self.logits = torch.zeros((R, g['vocab']), **bf)
+        # activations of a decode step: one chunk = the draft
+        db = _Bufs(g, R, dev, with_logits=True)
+        db.ids = self.ids[0]
+        db.n_total = self.n
+        db.chunks = [(0, R, self.mask[0], self.n, self.prefix_len)]
+        self.decode_bufs = db
+        self.h, self.resid, self.y, self.qkv, self.q, self.attn, self.logits = db.h, db.resid, db.y, db.qkv, db.q, \
+            db.attn, db.logits
+        # activations of a prefill pass: up to PF_CHUNKS chain chunks of R rows through one set of GEMMs
+        self.pf_chunks = max(1, 256 // R)
+        pb = _Bufs(g, R * self.pf_chunks, dev, with_logits=False)
+        self.pf_n = torch.zeros((self.pf_chunks,), **i32)
+        self.pf_P = torch.zeros((self.pf_chunks,), **i32)
+        self.prefill_bufs = pb
         self.rope_cos, self.rope_sin = model.rope_tables(self.max_seq + 8)
         self.graphs = {}
         self.replays = 0
@@ -199,7 +226,7 @@ class LookaheadPreTrainedModel(nn.Module):
                 rt.n.fill_(1)
                 rt.mask[0, 0, 0:1].fill_(1)
             self._verify_layers(rt)
-            accept.run(rt.logits, rt.ids, rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens,
+            accept.run(rt.logits, rt.ids[0], rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens,
                        rt.acc_count, rt.acc_nodes, rt.prefix_len, rt.finished)
             ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len)
             if use_trie:  # :1203
@@ -341,30 +368,34 @@ class LookaheadPreTrainedModel(nn.Module):
 
     def _prefill(self, rt, prompt_len, accept):
         """prompt -> KV rows [0, prompt_len) and the first generated token (argmax of the last prompt row).
-        The prompt goes through the verify kernels as chain drafts of <= max_nodes tokens."""
-        R = rt.max_nodes
+        The prompt goes through the verify kernels as chain drafts (row i attends rows <= i): per pass the GEMMs see
+        up to 256 rows at once, RoPE/KV-append and tree attention run per 64-row chunk."""
+        R, C = rt.max_nodes, rt.pf_chunks
         if not hasattr(rt, 'chain'):
             rt.chain = rt.chain_mask_rows()
-        rt.mask[0].copy_(rt.chain)
+        pb = rt.prefill_bufs
         pos = 0
         while pos < prompt_len:
-            m = min(R, prompt_len - pos)
-            rt.ids[0, :m] = rt.seq[pos:pos + m]
-            rt.n.fill_(m)
-            rt.prefix_len.fill_(pos)
-            self._verify_layers(rt, last_only=(pos + m < prompt_len))
+            m = min(R * C, prompt_len - pos)
+            pb.ids[:m] = rt.seq[pos:pos + m]
+            pb.n_total.fill_(m)
+            ns = [max(0, min(R, m - R * c)) for c in range(C)]
+            meta = torch.tensor([ns, [pos + R * c for c in range(C)]], dtype=torch.int32).to(rt.device)
+            rt.pf_n.copy_(meta[0])
+            rt.pf_P.copy_(meta[1])
+            pb.chunks = [(R * c, R * (c + 1), rt.chain, rt.pf_n[c:c + 1], rt.pf_P[c:c + 1]) for c in range(C) if ns[c] > 0]
+            last = pos + m >= prompt_len
+            self._verify_layers(rt, bufs=pb, last_only=not last)
             pos += m
-        # first token: (penalised) arg-max of the last row
+        # first token: (penalised) arg-max of the last prompt row's logits
+        last_row = (prompt_len - 1) % (R * C)
+        torch.mm(pb.y[last_row:last_row + 1], self.lm_head.weight.t(), out=rt.logits[0:1])
+        rt.ids[0, 0:1] = rt.seq[prompt_len - 1:prompt_len]
+        rt.mask[0].copy_(rt.chain)
+        rt.n.fill_(1)
         rt.seq_len.fill_(prompt_len)
-        last = m - 1
-        from .. import _lib as L
-        import ctypes as C
-        L.check(L.load().pia_accept(C.byref(accept.cfg), rt.logits[last:].data_ptr(), rt.ids[0, last:].data_ptr(),
-                                    rt.chain[0:].data_ptr(), rt.mask.shape[2], rt.n.fill_(1).data_ptr(),
-                                    rt.seq.data_ptr(), rt.seq_len.data_ptr(), rt.seq.numel(), rt.pad_len,
-                                    rt.acc_tokens.data_ptr(), rt.acc_count.data_ptr(), rt.acc_nodes.data_ptr(),
-                                    rt.prefix_len.data_ptr(), rt.finished.data_ptr(), accept.workspace.data_ptr(),
-                                    torch.cuda.current_stream().cuda_stream))
+        accept.run(rt.logits, rt.ids[0], rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens, rt.acc_count,
+                   rt.acc_nodes, rt.prefix_len, rt.finished)
         rt.prefix_len.fill_(prompt_len)
         return int(rt.acc_tokens[0].item())
 

@@ -173,31 +173,36 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         ops.silu_mul(gu, act)
         return torch.mm(act, m.down_proj.weight.t())
 
-    def _verify_layers(self, rt, last_only=False):
-        """embed -> decoder layers -> final norm -> lm_head over the draft in rt.ids / rt.mask / rt.n with
-        rt.prefix_len tokens already cached.  Writes rt.logits [max_nodes, vocab] (skipped when last_only)."""
+    def _verify_layers(self, rt, bufs=None, last_only=False):
+        """embed -> decoder layers -> final norm -> lm_head over the rows described by `bufs` (default: the decode
+        buffers = one draft of <= max_nodes tree nodes in rt.ids / rt.mask / rt.n on top of rt.prefix_len cached
+        tokens).  A prefill pass uses wider buffers holding several 64-row chain chunks: the GEMMs run once over all
+        rows, RoPE/KV-append and tree attention run per chunk.  Writes bufs.logits (skipped when last_only)."""
         self.fuse()
+        b = bufs if bufs is not None else rt.decode_bufs
         g = rt.g
-        mask = rt.mask[0]
         eps = self.config.rms_norm_eps
-        ops.embed_gather(self.model.embed_tokens.weight, rt.ids, rt.n, rt.h)
-        x, resid_in = rt.h, None  # rmsnorm(x, resid_in) -> (resid = x + resid_in, y = norm(resid))
+        ops.embed_gather(self.model.embed_tokens.weight, b.ids, b.n_total, b.h)
+        x, resid_in = b.h, None  # rmsnorm(x, resid_in) -> (resid = x + resid_in, y = norm(resid))
         for li, layer in enumerate(self.model.layers):
-            ops.rmsnorm(x, resid_in, layer.input_layernorm.weight, eps, rt.resid, rt.y)
+            ops.rmsnorm(x, resid_in, layer.input_layernorm.weight, eps, b.resid, b.y)
             a = layer.self_attn
-            torch.mm(rt.y, a.qkv_weight.t(), out=rt.qkv)
-            ops.rope_kv_append(rt.qkv, mask, rt.n, rt.prefix_len, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
-                               g['head_dim'], rt.rope_cos, rt.rope_sin, rt.q, rt.k_cache[li], rt.v_cache[li],
-                               rt.max_seq)
-            rt.plan.forward(li, rt.q, mask, rt.n, rt.prefix_len, rt.pad_len, rt.attn)
-            o = torch.mm(rt.attn, a.o_proj.weight.t())
-            ops.rmsnorm(o, rt.resid, layer.post_attention_layernorm.weight, eps, rt.resid, rt.y)
-            x = self._mlp(rt, layer, rt.y)
-            resid_in = rt.resid
+            torch.mm(b.y, a.qkv_weight.t(), out=b.qkv)
+            for (r0, r1, mask, n, P) in b.chunks:
+                ops.rope_kv_append(b.qkv[r0:r1], mask, n, P, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
+                                   g['head_dim'], rt.rope_cos, rt.rope_sin, b.q[r0:r1], rt.k_cache[li], rt.v_cache[li],
+                                   rt.max_seq)
+            for (r0, r1, mask, n, P) in b.chunks:
+                rt.plan.forward(li, b.q[r0:r1], mask, n, P, rt.pad_len, b.attn[r0:r1])
+            o = torch.mm(b.attn, a.o_proj.weight.t())
+            ops.rmsnorm(o, b.resid, layer.post_attention_layernorm.weight, eps, b.resid, b.y)
+            x = self._mlp(rt, layer, b.y)
+            resid_in = b.resid
         if last_only:
             return
-        ops.rmsnorm(x, resid_in, self.model.norm.weight, eps, rt.resid, rt.y)
-        torch.mm(rt.y, self.lm_head.weight.t(), out=rt.logits)
+        ops.rmsnorm(x, resid_in, self.model.norm.weight, eps, b.resid, b.y)
+        if b.logits is not None:
+            torch.mm(b.y, self.lm_head.weight.t(), out=b.logits)
 
     # ------------------------------------------------------------------ reference-shaped forward (API parity)
     @torch.no_grad()
@@ -229,6 +234,7 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         rows = torch.from_numpy(bits.view(np.int64))
         rt.mask[0].copy_(rows.to(rt.device))
         rt.ids[0, :n] = input_ids[0].to(device=rt.device, dtype=torch.int32)
+        rt.decode_bufs.set_chunk_rows(n)
         rt.n.fill_(n)
         rt.prefix_len.fill_(P)
         rt.pad_len = pad_len
