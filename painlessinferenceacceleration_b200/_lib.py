@@ -69,7 +69,7 @@ SYMBOLS = {
     'pia_tree_attn_fwd': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp, vp]),
     'pia_rmsnorm': (C.c_int, [vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     'pia_rmsnorm_partials': (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
-    'pia_gemm_plan_create': (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    'pia_gemm_plan_create': (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
     'pia_gemm_plan_destroy': (C.c_int, [vp]),
     'pia_gemm_plan_splits': (C.c_int, [vp]),
     'pia_gemm_run': (C.c_int, [vp, C.c_int, vp, vp]),

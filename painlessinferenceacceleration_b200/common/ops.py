@@ -30,17 +30,29 @@ def rmsnorm_partials(parts, residual_in, weight, eps, residual_out, y):
                                           rows, hidden, _p(residual_out), _p(y), _s()))
 
 
+def tile_weight(w):
+    """[N, K] -> [N/128, K/64, 128, 64] contiguous: one 16 KB block per (128-row tile, 64-wide k chunk), the unit the
+    GEMM kernel's TMA box moves, so each CTA reads one contiguous slab of HBM"""
+    N, K = w.shape
+    assert N % 128 == 0 and K % 64 == 0
+    t = w.view(N // 128, 128, K // 64, 64).permute(0, 2, 1, 3).contiguous()
+    t.pia_shape = (N, K)
+    return t
+
+
 class Gemm(object):
     """pia_gemm_plan_t: Y = X @ W^T for one (weight, activation buffer) pair; `out` is bf16 [rows, N] when the plan
     has one K split, else fp32 [splits, 64, N]"""
 
-    def __init__(self, weight, x, split_k=1):
-        N, K = weight.shape
+    def __init__(self, weight, x, split_k=1, tiled=False):
+        """weight: [N, K] row-major, or (tiled=True) the output of tile_weight() with its logical shape in .pia_shape"""
+        N, K = weight.pia_shape if tiled else weight.shape
         assert x.shape[1] == K and x.is_contiguous() and weight.is_contiguous()
         self.lib = L.load()
         self.h = L.vp()
         with torch.cuda.device(weight.device):
-            L.check(self.lib.pia_gemm_plan_create(_p(weight), N, K, _p(x), x.shape[0], split_k, C.byref(self.h)))
+            L.check(self.lib.pia_gemm_plan_create(_p(weight), N, K, _p(x), x.shape[0], split_k, int(tiled),
+                                                  C.byref(self.h)))
         self.splits = self.lib.pia_gemm_plan_splits(self.h)
         self.N = N
         self._keep = (weight, x)

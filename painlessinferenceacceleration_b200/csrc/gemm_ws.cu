@@ -59,6 +59,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -99,7 +105,7 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t saddr) {
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOK >> 3) << 17) | ((uint32_t)(BMW >> 4) << 24);
 
 struct Params {
-  int N, K, n_split, chunks_per_split, n_chunks, rows;
+  int N, K, n_split, chunks_per_split, n_chunks, rows, tiled;
   __nv_bfloat16 *out_bf16;  // [rows_cap, N]            (n_split == 1)
   float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
 };
@@ -139,7 +145,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         const uint32_t wd = base + s * STAGE_BYTES, xd = wd + W_BYTES;
-        tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
+        if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, blockIdx.x * p.n_chunks + c0 + i);
+        else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
         tma_load_2d(xd, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
       }
     }
@@ -209,6 +216,33 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void *ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// weights pre-tiled in HBM: [N/128 * K/64] contiguous 16 KB blocks of 128 rows x 64 k (one TMA box each), so a CTA
+// streams one contiguous slab instead of 128 strided 128-byte pieces per stage
+static int encode_tiled_w(CUtensorMap *m, const void *base, uint64_t n_blocks) {
+  EncodeTiledFn fn = get_encode();
+  PIA_REQUIRE(fn, "cuTensorMapEncodeTiled not available in this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)BK, (cuuint64_t)BMW, n_blocks};
+  cuuint64_t strides[2] = {(cuuint64_t)BK * 2, (cuuint64_t)BK * BMW * 2};
+  cuuint32_t box[3] = {BK, BMW, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return PIA_ERR_CUDA; }
+  return PIA_OK;
+}
+
 static int encode_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint32_t box_inner,
                      uint32_t box_outer, CUtensorMapL2promotion promo) {
   static EncodeTiledFn fn = nullptr;
@@ -230,7 +264,7 @@ static int encode_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_t 
 }
 
 extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d_x, int x_rows, int split_k,
-                                    pia_gemm_plan_t **out) {
+                                    int w_tiled, pia_gemm_plan_t **out) {
   PIA_REQUIRE(d_w && d_x && out, "null argument");
   PIA_REQUIRE(N > 0 && K > 0 && K % BK == 0, "K must be a multiple of %d", BK);
   PIA_REQUIRE(x_rows >= TOK, "the activation buffer must hold at least %d rows", TOK);
@@ -244,7 +278,10 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   g->p.chunks_per_split = (n_chunks + split_k - 1) / split_k;
   g->p.n_split = (n_chunks + g->p.chunks_per_split - 1) / g->p.chunks_per_split;
   g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr;
-  int rc = encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  g->p.tiled = w_tiled ? 1 : 0;
+  if (w_tiled && N % BMW != 0) { delete g; set_error("a tiled weight needs N %% %d == 0", BMW); return PIA_ERR_INVALID; }
+  int rc = w_tiled ? encode_tiled_w(&g->map_w, d_w, (uint64_t)(N / BMW) * n_chunks)
+                   : encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) rc = encode_2d(&g->map_x, d_x, (uint64_t)K, (uint64_t)x_rows, BK, TOK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);

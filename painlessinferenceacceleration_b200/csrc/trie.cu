@@ -629,16 +629,18 @@ __device__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree
     if (tid == 0) { S->fcnt[0] = cnt0; S->fcur[0] = 0; S->fpid[0] = -1; S->depth = 0; }
     __syncthreads();
     while (true) {
-      // thread 0 advances the DFS until a new frame must be built (state 1) or the walk ends (state 0)
+      // thread 0 advances the DFS until a sorted frame must be built (state 1) or the walk ends (state 0).
+      // Single-child nodes (n-gram chains, the common case below the first levels) are followed inline by thread 0:
+      // one dependent record load per node instead of a CTA-wide frame construction.
       if (tid == 0) {
         int st = 0;
-        while (S->depth >= 0 && S->n < max_size) {
+        while (S->depth >= 0 && S->n < max_size && st == 0) {
           const int d = S->depth;
           if (S->fcur[d] >= S->fcnt[d]) { S->depth = d - 1; continue; }
           const int e = S->fcur[d]++;
-          const int rid = S->n;
+          int rid = S->n;
           S->ids[rid] = S->ftok[d][e];
-          const int fl = S->fflag[d][e];
+          int fl = S->fflag[d][e];
           S->sizes0 += (fl & CF_FI) ? 1 : 0;
           S->sizes1 += (fl & CF_FO) ? 1 : 0;
           const int pid = S->fpid[d];
@@ -646,11 +648,41 @@ __device__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree
           S->mask[rid][rid >> 6] |= 1ull << (rid & 63);
           S->n = rid + 1;
           // recurse (:283-293): children exist, depth budget max_length-1-d > 0, room left
-          if ((fl & CF_KIDS) && (max_length - 1 - d) > 0 && S->n < max_size && d + 1 < MAXD) {
-            S->best_node = S->fnode[d][e];
-            S->fpid[d + 1] = rid;
-            st = 1;
-            break;
+          int cur_node = S->fnode[d][e], cur_d = d;
+          while ((fl & CF_KIDS) && (max_length - 1 - cur_d) > 0 && S->n < max_size && cur_d + 1 < MAXD) {
+            const Node x = D.nodes[cur_node];
+            ++nv;
+            if (x.n_child != 1) {  // several children: they must be ranked by fm -> build a frame
+              S->best_node = cur_node;
+              S->fpid[cur_d + 1] = rid;
+              S->depth = cur_d;
+              st = 1;
+              break;
+            }
+            int cid;
+            if (x.cap == 0) cid = x.child; else { cid = D.edges[x.child].y; ++ne; }
+            const Node c = D.nodes[cid];
+            ++nv;
+            const double fi = (double)load_fi(D, c, cid, idx), fo = c.fo;
+            const double fm = mix_freq(omw, w, fi, fo);
+            bool skip;
+            if (mode == PIA_MODE_MIX) skip = (fi < min_in && fo < min_out && fm < min_mix);
+            else if (mode == PIA_MODE_INPUT) skip = fi < min_in;
+            else skip = fo < min_out;
+            // an (already exhausted) frame at this depth keeps the unwinding uniform
+            S->fcnt[cur_d + 1] = 0; S->fcur[cur_d + 1] = 0; S->fpid[cur_d + 1] = rid; S->depth = cur_d + 1;
+            if (skip) break;
+            const int prid = rid;
+            rid = S->n;
+            S->ids[rid] = c.token;
+            S->sizes0 += fi > 0.0 ? 1 : 0;
+            S->sizes1 += fo > 0.0 ? 1 : 0;
+            for (int w2 = 0; w2 < W; ++w2) S->mask[rid][w2] = S->mask[prid][w2];
+            S->mask[rid][rid >> 6] |= 1ull << (rid & 63);
+            S->n = rid + 1;
+            fl = c.n_child > 0 ? CF_KIDS : 0;
+            cur_node = cid;
+            cur_d = cur_d + 1;
           }
         }
         S->state = st;

@@ -38,9 +38,12 @@ for name, N, K, splits in [('qkv', 12288, 4096, (1, 2)), ('o', 4096, 4096, (1, 2
     by = N * K * 2
     t = timeit(lambda: [torch.mm(x, w.t()) for w in ws], nl)
     print(f'{name:8s} cuBLAS           {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
-    for s in splits:
-        gs = [ops.Gemm(w, x, split_k=s) for w in ws]
-        t = timeit(lambda: [g.run(64) for g in gs], nl)
-        print(f'{name:8s} pia split_k={s:<2d}   {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
-        del gs
+    for tiled in (False, True):
+        wt = [ops.tile_weight(w) for w in ws] if tiled else ws
+        for s in splits:
+            gs = [ops.Gemm(w, x, split_k=s, tiled=tiled) for w in wt]
+            t = timeit(lambda: [g.run(64) for g in gs], nl)
+            print(f'{name:8s} pia split_k={s:<2d} {"tiled" if tiled else "rowmj"} {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
+            del gs
+        del wt
     del ws
