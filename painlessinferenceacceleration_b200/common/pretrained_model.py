@@ -366,10 +366,10 @@ class LookaheadPreTrainedModel(nn.Module):
             return LookaheadDecoderOnlyOutput(sequences=out_ids, scores=() if output_scores else None, kwargs=kw)
         return out_ids
 
-    def _prefill(self, rt, prompt_len, accept):
-        """prompt -> KV rows [0, prompt_len) and the first generated token (argmax of the last prompt row).
-        The prompt goes through the verify kernels as chain drafts (row i attends rows <= i): per pass the GEMMs see
-        up to 256 rows at once, RoPE/KV-append and tree attention run per 64-row chunk."""
+    def _prefill_kv(self, rt, prompt_len):
+        """prompt tokens rt.seq[:prompt_len] -> KV rows [0, prompt_len); leaves the last prompt row's logits in
+        rt.logits[0].  The prompt goes through the verify kernels as chain drafts (row i attends rows <= i): per pass
+        the GEMMs see up to 256 rows at once, RoPE/KV-append and tree attention run per 64-row chunk."""
         R, C = rt.max_nodes, rt.pf_chunks
         if not hasattr(rt, 'chain'):
             rt.chain = rt.chain_mask_rows()
@@ -387,9 +387,13 @@ class LookaheadPreTrainedModel(nn.Module):
             last = pos + m >= prompt_len
             self._verify_layers(rt, bufs=pb, last_only=not last)
             pos += m
-        # first token: (penalised) arg-max of the last prompt row's logits
         last_row = (prompt_len - 1) % (R * C)
         torch.mm(pb.y[last_row:last_row + 1], self.lm_head.weight.t(), out=rt.logits[0:1])
+        rt.prefix_len.fill_(prompt_len)
+
+    def _prefill(self, rt, prompt_len, accept):
+        """prefill + the first generated token: (penalised) arg-max of the last prompt row's logits (:783-798)"""
+        self._prefill_kv(rt, prompt_len)
         rt.ids[0, 0:1] = rt.seq[prompt_len - 1:prompt_len]
         rt.mask[0].copy_(rt.chain)
         rt.n.fill_(1)

@@ -27,11 +27,9 @@ namespace gemm {
 constexpr int BMW = 128;   // weight rows per tile (UMMA M)
 constexpr int BK = 64;     // k elements per stage (one 128-byte swizzle row)
 constexpr int TOK = 64;    // token rows (UMMA N)
-constexpr int NSTAGE = 4;
 constexpr int NTHREADS = 192;
 constexpr int W_BYTES = BMW * BK * 2, X_BYTES = TOK * BK * 2, STAGE_BYTES = W_BYTES + X_BYTES;
-constexpr int SMEM_BAR = NSTAGE * STAGE_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BAR + 128 + 1024;
+constexpr int smem_total(int nstage) { return nstage * STAGE_BYTES + 256 + 1024; }
 constexpr int TMEM_COLS = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,8 +108,13 @@ struct Params {
   float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
 };
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+// NSTAGE = 4: ~100 KB of shared memory, two CTAs per SM (grids with more CTAs than SMs);
+// NSTAGE = 8: ~200 KB, one CTA per SM with twice the bytes in flight (grids that do not fill the SMs twice) -
+// HBM only saturates with >= ~10 MB of loads in flight chip-wide.
+template <int NSTAGE>
+__global__ void __launch_bounds__(NTHREADS, NSTAGE <= 4 ? 2 : 1)
 k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, Params p) {
+  constexpr int SMEM_BAR = NSTAGE * STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -210,6 +213,7 @@ using namespace pia::gemm;
 struct pia_gemm_plan {
   CUtensorMap map_w, map_x;
   Params p;
+  int nstage;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -284,7 +288,13 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
                    : encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) rc = encode_2d(&g->map_x, d_x, (uint64_t)K, (uint64_t)x_rows, BK, TOK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) {
-    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int ctas = ((N + BMW - 1) / BMW) * g->p.n_split;
+    g->nstage = ctas <= n_sm + n_sm / 4 ? 8 : 4;
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(8));
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
   if (rc != PIA_OK) { delete g; return rc; }
@@ -302,7 +312,8 @@ extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *str
   p.rows = rows;
   if (p.n_split == 1) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
   dim3 grid((p.N + BMW - 1) / BMW, p.n_split);
-  k_gemm_ws<<<grid, NTHREADS, SMEM_TOTAL, (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
+  if (g->nstage == 8) k_gemm_ws<8><<<grid, NTHREADS, smem_total(8), (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
+  else k_gemm_ws<4><<<grid, NTHREADS, smem_total(4), (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
   PIA_LAUNCH_CHECK();
   return PIA_OK;
 }

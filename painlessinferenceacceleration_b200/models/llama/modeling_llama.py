@@ -165,13 +165,54 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         freqs = pos[:, None] * inv_freq[None, :]
         return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
 
+    # ------------------------------------------------------------------ weight-streaming GEMM plans (decode rows)
+    def _gemm_plans(self, rt):
+        """tcgen05 weight-streaming GEMMs (csrc/gemm_ws.cu) for the 64-row decode buffers: HBM-tiled copies of the
+        fused weights, one plan per (weight, activation buffer).  Prefill passes (256 rows) stay on cuBLAS."""
+        plans = getattr(rt, 'gemm_plans', None)
+        if plans is not None:
+            return plans
+        import os
+        if os.environ.get('PIA_GEMM', '1') == '0' or rt.max_nodes != 64:
+            rt.gemm_plans = False
+            return False
+        b = rt.decode_bufs
+        g = rt.g
+        dev = b.y.device
+        b.gu = torch.zeros((b.rows, 2 * g['inter']), dtype=torch.bfloat16, device=dev)
+        b.act = torch.zeros((b.rows, g['inter']), dtype=torch.bfloat16, device=dev)
+        plans = {'layers': []}
+        for layer in self.model.layers:
+            plans['layers'].append(self._layer_gemm_plans(layer, b))
+        plans['lm_head'] = self._mk_gemm(self.lm_head.weight.data, b.y)
+        rt.gemm_plans = plans
+        return plans
+
+    def _layer_gemm_plans(self, layer, b):
+        a, m = layer.self_attn, layer.mlp
+        return {'qkv': self._mk_gemm(a.qkv_weight, b.y), 'gate_up': self._mk_gemm(m.gate_up_weight, b.y),
+                'down': self._mk_gemm(m.down_proj.weight.data, b.act, split_k=8)}
+
+    @staticmethod
+    def _mk_gemm(w, x, split_k=1):
+        """HBM-tiled copy of the weight when its row count allows it (N % 128 == 0), else the row-major tensor"""
+        if w.shape[0] % 128 == 0:
+            return ops.Gemm(ops.tile_weight(w), x, split_k=split_k, tiled=True)
+        return ops.Gemm(w.contiguous(), x, split_k=split_k)
+
     # ------------------------------------------------------------------ the verify forward on static buffers
-    def _mlp(self, rt, layer, y):
+    def _mlp(self, rt, layer, y, plans=None):
+        """returns (x, parts): the MLP output as a bf16 tensor or as fp32 split-K slices for the next rmsnorm"""
         m = layer.mlp
+        if plans:
+            b = rt.decode_bufs
+            plans['gate_up'].run(64, out=b.gu)
+            ops.silu_mul(b.gu, b.act)
+            return None, plans['down'].run(64)
         gu = torch.mm(y, m.gate_up_weight.t())
         act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=gu.dtype, device=gu.device)
         ops.silu_mul(gu, act)
-        return torch.mm(act, m.down_proj.weight.t())
+        return torch.mm(act, m.down_proj.weight.t()), None
 
     def _verify_layers(self, rt, bufs=None, last_only=False):
         """embed -> decoder layers -> final norm -> lm_head over the rows described by `bufs` (default: the decode
@@ -183,26 +224,40 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         g = rt.g
         eps = self.config.rms_norm_eps
         ops.embed_gather(self.model.embed_tokens.weight, b.ids, b.n_total, b.h)
-        x, resid_in = b.h, None  # rmsnorm(x, resid_in) -> (resid = x + resid_in, y = norm(resid))
+        plans = self._gemm_plans(rt) if b is rt.decode_bufs else False
+        x, parts, resid_in = b.h, None, None  # norm(x | parts, resid_in) -> (resid = x + resid_in, y = norm(resid))
+
+        def norm(w):
+            if parts is not None:
+                ops.rmsnorm_partials(parts, resid_in, w, eps, b.resid, b.y)
+            else:
+                ops.rmsnorm(x, resid_in, w, eps, b.resid, b.y)
+
         for li, layer in enumerate(self.model.layers):
-            ops.rmsnorm(x, resid_in, layer.input_layernorm.weight, eps, b.resid, b.y)
+            lp = plans['layers'][li] if plans else None
+            norm(layer.input_layernorm.weight)
             a = layer.self_attn
-            torch.mm(b.y, a.qkv_weight.t(), out=b.qkv)
+            if lp:
+                lp['qkv'].run(64, out=b.qkv)
+            else:
+                torch.mm(b.y, a.qkv_weight.t(), out=b.qkv)
             for (r0, r1, mask, n, P) in b.chunks:
                 ops.rope_kv_append(b.qkv[r0:r1], mask, n, P, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
                                    g['head_dim'], rt.rope_cos, rt.rope_sin, b.q[r0:r1], rt.k_cache[li], rt.v_cache[li],
                                    rt.max_seq)
             for (r0, r1, mask, n, P) in b.chunks:
                 rt.plan.forward(li, b.q[r0:r1], mask, n, P, rt.pad_len, b.attn[r0:r1])
-            o = torch.mm(b.attn, a.o_proj.weight.t())
-            ops.rmsnorm(o, b.resid, layer.post_attention_layernorm.weight, eps, b.resid, b.y)
-            x = self._mlp(rt, layer, b.y)
-            resid_in = b.resid
+            x, parts, resid_in = torch.mm(b.attn, a.o_proj.weight.t()), None, b.resid
+            norm(layer.post_attention_layernorm.weight)
+            x, parts = self._mlp(rt, layer, b.y, lp)
         if last_only:
             return
-        ops.rmsnorm(x, resid_in, self.model.norm.weight, eps, b.resid, b.y)
+        norm(self.model.norm.weight)
         if b.logits is not None:
-            torch.mm(b.y, self.lm_head.weight.t(), out=b.logits)
+            if plans:
+                plans['lm_head'].run(64, out=b.logits)
+            else:
+                torch.mm(b.y, self.lm_head.weight.t(), out=b.logits)
 
     # ------------------------------------------------------------------ reference-shaped forward (API parity)
     @torch.no_grad()

@@ -59,7 +59,11 @@ class MixtralForCausalLM(LlamaForCausalLM):
         g['n_experts'] = self.config.num_local_experts
         return g
 
-    def _mlp(self, rt, layer, y):
+    def _layer_gemm_plans(self, layer, b):
+        a = layer.self_attn
+        return {'qkv': self._mk_gemm(a.qkv_weight, b.y)}
+
+    def _mlp(self, rt, layer, y, plans=None):
         moe = layer.mlp
         logits = torch.mm(y, moe.gate.weight.t())                                   # :721
         probs = torch.softmax(logits.float(), dim=1)                                # :723
@@ -74,4 +78,4 @@ class MixtralForCausalLM(LlamaForCausalLM):
             ops.silu_mul(gu, act)
             ye = torch.mm(act, moe.experts.down_proj[e].t())
             out += ye * dense[:, e:e + 1]                                           # bf16 scale, bf16 accumulate
-        return out
+        return out, None

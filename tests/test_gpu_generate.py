@@ -121,15 +121,23 @@ class OursBackend(object):
     """adapter for oracle.loop: the verify forward / KV cache of OUR model behind the oracle's backend interface, so
     that the oracle loop (reference semantics on the host) and our fused device loop consume the same logits"""
 
-    def __init__(self, ours):
+    def __init__(self, ours, prefill_like_generate=False, max_seq=512):
         self.m, self.P = ours, 0
+        self.prefill_like_generate, self.max_seq = prefill_like_generate, max_seq
 
     def rows(self):
         return self.P
 
     def forward(self, ids_in, m01, pos):
         n = ids_in.shape[1]
-        if self.P == 0 and n > 64:  # prompt: chain chunks of 64, exactly what generate() does
+        if self.P == 0 and self.prefill_like_generate:  # prompt: exactly the prefill generate() runs (last row only)
+            rt = self.m._runtime(self.max_seq, 64)
+            rt.pad_len = 0
+            rt.seq[:n] = ids_in[0].to(device=rt.device, dtype=torch.int32)
+            self.m._prefill_kv(rt, n)
+            self.P = n
+            return rt.logits[0:1].clone()[None]
+        if self.P == 0 and n > 64:  # prompt: chain chunks of 64 through forward()
             outs = []
             for c0 in range(0, n, 64):
                 m = min(64, n - c0)
@@ -171,7 +179,7 @@ def test_loop_is_exact_given_the_same_logits(family, penalty):
                              decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
                              return_dict_in_generate=True)
             ref = lookahead_generate(None, otrie, p, max_new_tokens=56, eos_token_id=[2], repetition_penalty=penalty,
-                                     backend=OursBackend(b))
+                                     backend=OursBackend(b, prefill_like_generate=True, max_seq=90 + 56 + 65))
             assert out.sequences[0].tolist() == ref['sequences'][0].tolist()
             assert out.kwargs['edls'] == ref['edls'] and out.kwargs['dls'] == ref['dls']
             edl_all += ref['edls'][1:]
