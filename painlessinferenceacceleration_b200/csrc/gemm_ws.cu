@@ -292,7 +292,7 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int ctas = ((N + BMW - 1) / BMW) * g->p.n_split;
-    g->nstage = ctas <= n_sm + n_sm / 4 ? 8 : 4;
+    g->nstage = ctas <= n_sm ? 8 : 4;
     cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(4));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(8));
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }

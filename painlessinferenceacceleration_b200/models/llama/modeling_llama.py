@@ -278,7 +278,9 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             nz = am[0, :P].nonzero()[0]
             pad_len = int(nz[0]) if len(nz) else P
         tree = am[:, P:]
-        rt = self._runtime(max(P + n + 1, 256), 64 if n <= 64 else 128)
+        need = P + n + 1
+        rt = self._runtime(need if self._rt is not None and self._rt.max_seq >= need else max(need, 256),
+                           64 if n <= 64 else 128)
         assert n <= rt.max_nodes, 'at most 128 tree nodes per forward; prefill goes through generate()'
         rows = torch.zeros((rt.max_nodes, rt.max_nodes // 64), dtype=torch.int64)
         import numpy as np
