@@ -141,6 +141,11 @@ class LookaheadPreTrainedModel(nn.Module):
             self._rt = None
             rt = _Runtime(self, max(max_seq, 128), max_nodes)
             self._rt = rt
+            # one-time weight preparation must never end up inside a captured step graph
+            if hasattr(self, 'fuse'):
+                self.fuse()
+            if hasattr(self, '_gemm_plans'):
+                self._gemm_plans(rt)
         return rt
 
     def _decoding_args(self):
