@@ -1,12 +1,19 @@
 // Error reporting, ABI version and launch accounting of libpia_b200.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace pia {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("PIA_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 
 void set_error(const char *fmt, ...) {
   va_list ap;

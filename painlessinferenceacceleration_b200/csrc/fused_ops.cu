@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const f
                                                  const __nv_bfloat16 *w, float eps, int hidden,
                                                  __nv_bfloat16 *res_out, __nv_bfloat16 *y) {
   __shared__ float red[16];
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const int nvec = hidden >> 3;
   const long long row_off = (long long)row * hidden;
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv
                                                         int hq, int hkv, int hd, const __nv_bfloat16 *cos_t,
                                                         const __nv_bfloat16 *sin_t, int max_pos, __nv_bfloat16 *q_out,
                                                         __nv_bfloat16 *kc, __nv_bfloat16 *vc, int max_seq) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x;
   const int n = *d_n, P = *d_prefix;
   if (i >= n) return;
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv
 }
 
 __global__ void __launch_bounds__(256) k_silu_mul(const __nv_bfloat16 *gu, int inter, __nv_bfloat16 *out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.y;
   const int v = blockIdx.x * 256 + threadIdx.x;
   if (v * 8 >= inter) return;
@@ -155,6 +161,8 @@ __global__ void __launch_bounds__(256) k_silu_mul(const __nv_bfloat16 *gu, int i
 
 __global__ void __launch_bounds__(256) k_embed_gather(const __nv_bfloat16 *table, const int *ids, const int *d_n,
                                                       int hidden, __nv_bfloat16 *out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int n = *d_n;
   const int nvec = hidden >> 3;
@@ -173,11 +181,11 @@ using namespace pia::fused;
 extern "C" int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight, float eps, int rows,
                            int hidden, void *d_residual_out, void *d_y, void *stream) {
   PIA_REQUIRE(d_x && d_weight && d_y && rows > 0 && hidden > 0 && hidden % 8 == 0, "bad rmsnorm arguments");
-  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_x, nullptr, 0, 0,
-                                                   (const __nv_bfloat16 *)d_residual_in,
-                                                   (const __nv_bfloat16 *)d_weight, eps, hidden,
-                                                   (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_rmsnorm, dim3(rows), dim3(512), 0, (cudaStream_t)stream, (const __nv_bfloat16 *)d_x,
+                              (const float *)nullptr, 0, 0ll, (const __nv_bfloat16 *)d_residual_in,
+                              (const __nv_bfloat16 *)d_weight, eps, hidden, (__nv_bfloat16 *)d_residual_out,
+                              (__nv_bfloat16 *)d_y));
+  count_launch();
   return PIA_OK;
 }
 
@@ -185,11 +193,11 @@ extern "C" int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t
                                     const void *d_weight, float eps, int rows, int hidden, void *d_residual_out,
                                     void *d_y, void *stream) {
   PIA_REQUIRE(d_x_parts && n_parts >= 1 && d_weight && d_y && rows > 0 && hidden > 0 && hidden % 8 == 0, "bad rmsnorm arguments");
-  k_rmsnorm<<<rows, 512, 0, (cudaStream_t)stream>>>(nullptr, d_x_parts, n_parts, (long long)part_stride,
-                                                   (const __nv_bfloat16 *)d_residual_in,
-                                                   (const __nv_bfloat16 *)d_weight, eps, hidden,
-                                                   (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_rmsnorm, dim3(rows), dim3(512), 0, (cudaStream_t)stream,
+                              (const __nv_bfloat16 *)nullptr, d_x_parts, n_parts, (long long)part_stride,
+                              (const __nv_bfloat16 *)d_residual_in, (const __nv_bfloat16 *)d_weight, eps, hidden,
+                              (__nv_bfloat16 *)d_residual_out, (__nv_bfloat16 *)d_y));
+  count_launch();
   return PIA_OK;
 }
 
@@ -200,27 +208,31 @@ extern "C" int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int
   PIA_REQUIRE(d_qkv && d_mask && d_n && d_prefix_len && d_cos && d_sin && d_q_out && d_k_cache_layer && d_v_cache_layer,
               "null argument");
   PIA_REQUIRE(head_dim % 16 == 0 && rows > 0 && mask_words >= 1 && mask_words <= 2, "bad rope arguments");
-  k_rope_kv_append<<<rows, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16 *)d_qkv, (const unsigned long long *)d_mask, mask_words, d_n, d_prefix_len, pad_len,
-      n_q_heads, n_kv_heads, head_dim, (const __nv_bfloat16 *)d_cos, (const __nv_bfloat16 *)d_sin, max_pos,
-      (__nv_bfloat16 *)d_q_out, (__nv_bfloat16 *)d_k_cache_layer, (__nv_bfloat16 *)d_v_cache_layer, max_seq);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_rope_kv_append, dim3(rows), dim3(256), 0, (cudaStream_t)stream,
+                              (const __nv_bfloat16 *)d_qkv, (const unsigned long long *)d_mask, mask_words,
+                              (const int *)d_n, (const int *)d_prefix_len, pad_len, n_q_heads, n_kv_heads, head_dim,
+                              (const __nv_bfloat16 *)d_cos, (const __nv_bfloat16 *)d_sin, max_pos,
+                              (__nv_bfloat16 *)d_q_out, (__nv_bfloat16 *)d_k_cache_layer,
+                              (__nv_bfloat16 *)d_v_cache_layer, max_seq));
+  count_launch();
   return PIA_OK;
 }
 
 extern "C" int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *stream) {
   PIA_REQUIRE(d_gate_up && d_out && rows > 0 && inter > 0 && inter % 8 == 0, "bad silu_mul arguments");
   dim3 grid((inter / 8 + 255) / 256, rows);
-  k_silu_mul<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_gate_up, inter, (__nv_bfloat16 *)d_out);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_silu_mul, grid, dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16 *)d_gate_up,
+                              inter, (__nv_bfloat16 *)d_out));
+  count_launch();
   return PIA_OK;
 }
 
 extern "C" int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden,
                                 void *d_out, void *stream) {
   PIA_REQUIRE(d_table && d_ids && d_n && d_out && rows > 0 && hidden % 8 == 0, "bad embed arguments");
-  k_embed_gather<<<rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)d_table, d_ids, d_n, hidden,
-                                                        (__nv_bfloat16 *)d_out);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_embed_gather, dim3(rows), dim3(256), 0, (cudaStream_t)stream,
+                              (const __nv_bfloat16 *)d_table, (const int *)d_ids, (const int *)d_n, hidden,
+                              (__nv_bfloat16 *)d_out));
+  count_launch();
   return PIA_OK;
 }

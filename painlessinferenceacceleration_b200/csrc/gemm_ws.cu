@@ -136,10 +136,12 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();  // barriers + TMEM are set up while the previous kernel drains; global memory only from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -312,8 +314,8 @@ extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *str
   p.rows = rows;
   if (p.n_split == 1) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
   dim3 grid((p.N + BMW - 1) / BMW, p.n_split);
-  if (g->nstage == 8) k_gemm_ws<8><<<grid, NTHREADS, smem_total(8), (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
-  else k_gemm_ws<4><<<grid, NTHREADS, smem_total(4), (cudaStream_t)stream>>>(g->map_w, g->map_x, p);
-  PIA_LAUNCH_CHECK();
+  if (g->nstage == 8) PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<8>, grid, dim3(NTHREADS), smem_total(8), (cudaStream_t)stream, g->map_w, g->map_x, p));
+  else PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<4>, grid, dim3(NTHREADS), smem_total(4), (cudaStream_t)stream, g->map_w, g->map_x, p));
+  count_launch();
   return PIA_OK;
 }

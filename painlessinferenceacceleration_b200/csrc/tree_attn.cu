@@ -159,6 +159,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
                  bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 8, bar_q_full = bar_o_full + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 48);
 
+  pdl_launch_dependents();
+  pdl_wait();  // the split decision below already reads device state written by the step's earlier kernels
   const int split = blockIdx.x, group = blockIdx.y;
   const int n = *p.d_n, P = *p.d_prefix;
   const int L = P + n;
@@ -593,7 +595,7 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   a.out = (__nv_bfloat16 *)d_out; a.counters = p->counters; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
-  k_tree_attn<<<dim3(p->n_split, p->n_groups), NTHREADS, SMEM_TOTAL, s>>>(p->map_k, p->map_v, a);
-  PIA_LAUNCH_CHECK();
+  PIA_CUDA_CHECK(launch_kernel(k_tree_attn, dim3(p->n_split, p->n_groups), dim3(NTHREADS), SMEM_TOTAL, s, p->map_k, p->map_v, a));
+  count_launch();
   return PIA_OK;
 }
