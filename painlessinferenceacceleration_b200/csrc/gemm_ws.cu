@@ -206,6 +206,182 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ stream-K
+// Work = n_tiles x n_chunks (tile, k-chunk) units, cut into gridDim.x equal contiguous ranges: every SM streams
+// the same number of bytes whatever N is (qkv: 96 tiles, o/down: 32 tiles on 148 SMs).  A tile whose chunks span
+// several CTAs is finished by the CTA that holds its FIRST chunk (it reaches that tile last in its own range, so the
+// other contributors - which meet the tile first in theirs - are normally done already): contributors store their
+// fp32 partial to a workspace slot and bump the tile's flag, the owner adds the slots in slot order (deterministic)
+// and writes bf16.  All CTAs are co-resident (grid <= #SMs, one CTA per SM), so the owner's wait cannot deadlock.
+struct SkParams {
+  int N, n_tiles, n_chunks, rows, max_contrib;
+  long long units;
+  __nv_bfloat16 *out;   // [rows_cap, N]
+  float *ws;            // [n_tiles][max_contrib][128][64]
+  int *flags;           // [n_tiles], zero between launches
+};
+
+__device__ __forceinline__ long long sk_begin(long long b, long long U, int G) { return b * U / G; }
+__device__ __forceinline__ int sk_cta_of(long long x, long long U, int G) {
+  int b = (int)(x * G / U);
+  while (b + 1 < G && sk_begin(b + 1, U, G) <= x) ++b;
+  while (b > 0 && sk_begin(b, U, G) > x) --b;
+  return b;
+}
+
+constexpr int SK_STAGES = 8;
+constexpr int SK_SMEM_BAR = SK_STAGES * STAGE_BYTES;
+constexpr int SK_SMEM_TOTAL = SK_SMEM_BAR + 256 + 1024;
+constexpr int SK_TMEM_COLS = 128;  // two 64-column accumulators
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_sk(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, SkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bar_full = base + SK_SMEM_BAR, bar_empty = bar_full + 8 * SK_STAGES, bar_acc_full = bar_empty + 8 * SK_STAGES,
+                 bar_acc_empty = bar_acc_full + 16;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SK_SMEM_BAR + 16 * SK_STAGES + 48);
+  const int G = gridDim.x, b = blockIdx.x;
+  const long long u0 = sk_begin(b, p.units, G), u1 = sk_begin(b + 1, p.units, G);
+
+  if (tid == 0) {
+    for (int s = 0; s < SK_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc_full, 1); mbar_init(bar_acc_full + 8, 1);
+    mbar_init(bar_acc_empty, 128); mbar_init(bar_acc_empty + 8, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(SK_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (long long u = u0; u < u1; ++u, ++i) {
+        const int tile = (int)(u / p.n_chunks), ch = (int)(u % p.n_chunks);
+        const int s = i % SK_STAGES, ph = (i / SK_STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
+        const uint32_t wd = base + s * STAGE_BYTES, xd = wd + W_BYTES;
+        tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, tile * p.n_chunks + ch);
+        tma_load_2d(xd, &map_x, bar_full + 8 * s, ch * BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int i = 0, seg = 0;
+      long long u = u0;
+      while (u < u1) {
+        const int tile = (int)(u / p.n_chunks);
+        long long ue = (long long)(tile + 1) * p.n_chunks;
+        if (ue > u1) ue = u1;
+        const int buf = seg & 1;
+        mbar_wait(bar_acc_empty + 8 * buf, ((seg >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + buf * 64;
+        bool first = true;
+        for (; u < ue; ++u, ++i) {
+          const int s = i % SK_STAGES, ph = (i / SK_STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t wa = base + s * STAGE_BYTES, xa = wa + W_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / 16; ++j) {
+            umma_bf16(d, kmajor_desc(wa + j * 32), kmajor_desc(xa + j * 32), IDESC, !(first && j == 0));
+          }
+          first = false;
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_acc_full + 8 * buf);
+        ++seg;
+      }
+    }
+  } else {
+    // epilogue warps: thread = one weight row of the tile (TMEM lane), 64 token values
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int seg = 0;
+    long long u = u0;
+    uint32_t v[64];
+    while (u < u1) {
+      const int tile = (int)(u / p.n_chunks);
+      const long long ts = (long long)tile * p.n_chunks;
+      long long ue = ts + p.n_chunks;
+      if (ue > u1) ue = u1;
+      const int buf = seg & 1;
+      mbar_wait(bar_acc_full + 8 * buf, (seg >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a = tmem + buf * 64 + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(a, v);
+      tmem_ld32(a + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_acc_empty + 8 * buf) : "memory");
+      const bool head = (u == ts), whole = head && (ue == ts + p.n_chunks);
+      const int n = tile * BMW + r;
+      if (!head) {
+        // contributor: slot = how many CTA ranges after the owner's this one is
+        const int owner = sk_cta_of(ts, p.units, G);
+        const int slot = b - owner - 1;
+        float4 *dst = reinterpret_cast<float4 *>(p.ws + (((long long)tile * p.max_contrib + slot) * BMW + r) * TOK);
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          dst[t] = make_float4(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1]), __uint_as_float(v[4 * t + 2]),
+                               __uint_as_float(v[4 * t + 3]));
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (r == 0) atomicAdd(&p.flags[tile], 1);
+      } else {
+        if (!whole) {
+          // owner: wait for the other contributors of this tile, then add their slots in order
+          const int last = sk_cta_of(ts + p.n_chunks - 1, p.units, G);
+          const int contributors = last - b;
+          if (r == 0) {
+            while (atomicAdd(&p.flags[tile], 0) < contributors) __nanosleep(64);
+            p.flags[tile] = 0;  // self-reset for the next launch
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          __threadfence();
+          for (int c = 0; c < contributors; ++c) {
+            const float4 *src = reinterpret_cast<const float4 *>(p.ws + (((long long)tile * p.max_contrib + c) * BMW + r) * TOK);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float4 x = __ldcg(src + t);
+              v[4 * t] = __float_as_uint(__uint_as_float(v[4 * t]) + x.x);
+              v[4 * t + 1] = __float_as_uint(__uint_as_float(v[4 * t + 1]) + x.y);
+              v[4 * t + 2] = __float_as_uint(__uint_as_float(v[4 * t + 2]) + x.z);
+              v[4 * t + 3] = __float_as_uint(__uint_as_float(v[4 * t + 3]) + x.w);
+            }
+          }
+        }
+        if (n < p.N) {
+#pragma unroll
+          for (int t = 0; t < TOK; ++t)
+            if (t < p.rows) p.out[(long long)t * p.N + n] = __float2bfloat16_rn(__uint_as_float(v[t]));
+        }
+      }
+      u = ue;
+      ++seg;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(SK_TMEM_COLS));
+  }
+}
+
 }  // namespace gemm
 }  // namespace pia
 
@@ -216,6 +392,9 @@ struct pia_gemm_plan {
   CUtensorMap map_w, map_x;
   Params p;
   int nstage;
+  // stream-K mode
+  int stream_k, sk_grid;
+  SkParams sk;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -278,6 +457,7 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   pia_gemm_plan *g = new (std::nothrow) pia_gemm_plan();
   PIA_REQUIRE(g, "out of host memory");
   const int n_chunks = K / BK;
+  const int want_stream_k = (split_k == -1);
   if (split_k < 1) split_k = 1;
   if (split_k > n_chunks) split_k = n_chunks;
   g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks;
@@ -299,17 +479,54 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(8));
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
+  g->stream_k = 0;
+  if (rc == PIA_OK && want_stream_k) {
+    // stream-K over the HBM-tiled weight: grid = min(#SMs, units), fix-up workspace owned by the plan
+    if (!w_tiled) { delete g; set_error("stream-K needs the tiled weight layout"); return PIA_ERR_INVALID; }
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    SkParams &k = g->sk;
+    k.N = N; k.n_tiles = N / BMW; k.n_chunks = n_chunks; k.rows = TOK;
+    k.units = (long long)k.n_tiles * n_chunks;
+    g->sk_grid = (int)(k.units < n_sm ? k.units : n_sm);
+    const long long per = (k.units + g->sk_grid - 1) / g->sk_grid;
+    k.max_contrib = (int)((n_chunks + per - 1) / per) + 1;
+    k.out = nullptr;
+    cudaError_t e = cudaMalloc((void **)&k.ws, sizeof(float) * (size_t)k.n_tiles * k.max_contrib * BMW * TOK);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&k.flags, sizeof(int) * k.n_tiles);
+    if (e == cudaSuccess) e = cudaMemset(k.flags, 0, sizeof(int) * k.n_tiles);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_TOTAL);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("stream-K plan: %s", cudaGetErrorString(e)); delete g; return PIA_ERR_CUDA; }
+    g->stream_k = 1;
+    g->p.n_split = 1;
+  }
   if (rc != PIA_OK) { delete g; return rc; }
   *out = g;
   return PIA_OK;
 }
 
-extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) { delete g; return PIA_OK; }
+extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) {
+  if (g) {
+    if (g->stream_k) { cudaFree(g->sk.ws); cudaFree(g->sk.flags); }
+    delete g;
+  }
+  return PIA_OK;
+}
 extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? g->p.n_split : 0; }
 
 extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream) {
   PIA_REQUIRE(g && d_out, "null argument");
   PIA_REQUIRE(rows >= 1 && rows <= TOK, "rows %d outside [1,%d]", rows, TOK);
+  if (g->stream_k) {
+    SkParams k = g->sk;
+    k.rows = rows;
+    k.out = (__nv_bfloat16 *)d_out;
+    PIA_CUDA_CHECK(launch_kernel(k_gemm_sk, dim3(g->sk_grid), dim3(NTHREADS), SK_SMEM_TOTAL, (cudaStream_t)stream, g->map_w, g->map_x, k));
+    count_launch();
+    return PIA_OK;
+  }
   Params p = g->p;
   p.rows = rows;
   if (p.n_split == 1) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;

@@ -45,5 +45,10 @@ for name, N, K, splits in [('qkv', 12288, 4096, (1, 2)), ('o', 4096, 4096, (1, 2
             t = timeit(lambda: [g.run(64) for g in gs], nl)
             print(f'{name:8s} pia split_k={s:<2d} {"tiled" if tiled else "rowmj"} {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
             del gs
+        if tiled:
+            gs = [ops.Gemm(w, x, split_k=-1, tiled=True) for w in wt]
+            t = timeit(lambda: [g.run(64) for g in gs], nl)
+            print(f'{name:8s} pia stream-K   tiled {t:8.2f} us  {by / t / 1e3:7.0f} GB/s', flush=True)
+            del gs
         del wt
     del ws

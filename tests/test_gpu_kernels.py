@@ -251,6 +251,13 @@ def test_gemm_weight_streaming(N, K, split):
     if N % 128 == 0:  # the HBM-tiled weight layout gives bit-identical results (same MMA order)
         gt = ops.Gemm(ops.tile_weight(w), x, split_k=split, tiled=True)
         assert torch.equal(gt.run(64), out)
+        # stream-K: equal unit ranges per SM + in-kernel fix-up; deterministic from launch to launch
+        gs = ops.Gemm(ops.tile_weight(w), x, split_k=-1, tiled=True)
+        o1 = gs.run(64).clone()
+        o2 = gs.run(64).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(o1, o2)
+        assert torch.allclose(o1.float(), ref, atol=2e-2, rtol=1.6e-2), (o1.float() - ref).abs().max().item()
     if g.splits == 1:
         got = out.float()
     else:
