@@ -178,6 +178,9 @@ int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d_x, int x_r
                          pia_gemm_plan_t **out);
 int pia_gemm_plan_destroy(pia_gemm_plan_t *g);
 int pia_gemm_plan_splits(const pia_gemm_plan_t *g);
+/* fused SiLU(gate) * up epilogue (modeling_llama.py:185-186): the weight must be laid out so that every 128-row tile
+ * holds 64 gate rows followed by the 64 up rows of the same columns; d_out of pia_gemm_run is then [rows, N/2]. */
+int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on);
 /* splits == 1: d_out is bf16 [rows_cap, N]; splits > 1: d_out is fp32 [splits][64][N] partial slices (sum them in
  * slice order, e.g. with pia_rmsnorm_partials).  rows <= 64 rows are written. */
 int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream);

@@ -40,6 +40,17 @@ def tile_weight(w):
     return t
 
 
+def interleave_gate_up(w_gate_up):
+    """[gate (I rows); up (I rows)] -> per 128-row tile: 64 gate rows then the 64 up rows of the same columns, the
+    layout the fused SiLU*up epilogue of the GEMM expects"""
+    two_i, K = w_gate_up.shape
+    inter = two_i // 2
+    assert inter % 64 == 0
+    g = w_gate_up[:inter].view(inter // 64, 64, K)
+    u = w_gate_up[inter:].view(inter // 64, 64, K)
+    return torch.cat([g, u], dim=1).reshape(two_i, K).contiguous()
+
+
 class Gemm(object):
     """pia_gemm_plan_t: Y = X @ W^T for one (weight, activation buffer) pair; `out` is bf16 [rows, N] when the plan
     has one K split, else fp32 [splits, 64, N]"""
@@ -60,6 +71,10 @@ class Gemm(object):
             self.out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=weight.device)
         else:
             self.out = torch.empty((self.splits, 64, N), dtype=torch.float32, device=weight.device)
+
+    def set_silu(self, on=True):
+        L.check(self.lib.pia_gemm_plan_set_silu(self.h, int(on)))
+        return self
 
     def run(self, rows=64, out=None):
         o = out if out is not None else self.out

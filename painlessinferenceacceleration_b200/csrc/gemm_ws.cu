@@ -29,7 +29,8 @@ constexpr int BK = 64;     // k elements per stage (one 128-byte swizzle row)
 constexpr int TOK = 64;    // token rows (UMMA N)
 constexpr int NTHREADS = 192;
 constexpr int W_BYTES = BMW * BK * 2, X_BYTES = TOK * BK * 2, STAGE_BYTES = W_BYTES + X_BYTES;
-constexpr int smem_total(int nstage) { return nstage * STAGE_BYTES + 256 + 1024; }
+constexpr int XCH_BYTES = TOK * 64 * 2;  // bf16 [64 tokens][64 rows] exchange tile of the SiLU*up epilogue
+constexpr int smem_total(int nstage) { return nstage * STAGE_BYTES + 256 + XCH_BYTES + 1024; }
 constexpr int TMEM_COLS = 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,7 +105,8 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOK 
 
 struct Params {
   int N, K, n_split, chunks_per_split, n_chunks, rows, tiled;
-  __nv_bfloat16 *out_bf16;  // [rows_cap, N]            (n_split == 1)
+  int silu;                 // 1: tile rows are 64 gate rows + 64 up rows of the same columns -> out = silu(g) * u
+  __nv_bfloat16 *out_bf16;  // [rows_cap, N]  (or [rows_cap, N/2] with silu)   (n_split == 1)
   float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
 };
 
@@ -185,6 +187,31 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
 #pragma unroll
       for (int t = 0; t < 64; ++t) v[t] = 0u;
     }
+    if (p.silu) {
+      // act(gate) * up (modeling_llama.py:185-186) in the epilogue: lanes 0-63 hold gate rows, lanes 64-127 the up
+      // rows of the same 64 output columns.  Rounding points as in eager bf16: GEMM out -> bf16, silu -> bf16, * -> bf16
+      __nv_bfloat16 *xb = reinterpret_cast<__nv_bfloat16 *>(sm + SMEM_BAR + 256);  // [64 tokens][64 rows]
+      const int rr = (q & 1) * 32 + lane;
+      if (q >= 2) {
+#pragma unroll
+        for (int t = 0; t < TOK; ++t) xb[t * 64 + rr] = __float2bfloat16_rn(__uint_as_float(v[t]));
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q < 2) {
+        const int col = blockIdx.x * 64 + rr;
+        const int inter = p.N >> 1;
+        if (col < inter) {
+#pragma unroll
+          for (int t = 0; t < TOK; ++t) {
+            if (t < p.rows) {
+              const float g = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[t])));
+              const float sg = __bfloat162float(__float2bfloat16_rn(g / (1.f + expf(-g))));
+              p.out_bf16[(long long)t * inter + col] = __float2bfloat16_rn(sg * __bfloat162float(xb[t * 64 + rr]));
+            }
+          }
+        }
+      }
+    } else
     if (n < p.N) {
       if (p.n_split == 1) {
 #pragma unroll
@@ -463,7 +490,7 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks;
   g->p.chunks_per_split = (n_chunks + split_k - 1) / split_k;
   g->p.n_split = (n_chunks + g->p.chunks_per_split - 1) / g->p.chunks_per_split;
-  g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr;
+  g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr; g->p.silu = 0;
   g->p.tiled = w_tiled ? 1 : 0;
   if (w_tiled && N % BMW != 0) { delete g; set_error("a tiled weight needs N %% %d == 0", BMW); return PIA_ERR_INVALID; }
   int rc = w_tiled ? encode_tiled_w(&g->map_w, d_w, (uint64_t)(N / BMW) * n_chunks)
@@ -515,6 +542,11 @@ extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) {
   return PIA_OK;
 }
 extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? g->p.n_split : 0; }
+extern "C" int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on) {
+  PIA_REQUIRE(g && g->p.n_split == 1 && !g->stream_k && g->p.N % BMW == 0, "the SiLU*up epilogue needs split_k == 1 and N %% 128 == 0");
+  g->p.silu = on ? 1 : 0;
+  return PIA_OK;
+}
 
 extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream) {
   PIA_REQUIRE(g && d_out, "null argument");

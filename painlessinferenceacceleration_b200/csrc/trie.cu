@@ -346,18 +346,31 @@ __device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared
         ++nv;
         if (visit(id, nd) && nd.n_child > 0) push = nd.n_child;
       }
-      int incl = push;
+      // frontier reservation: single-child (inline) nodes - the bulk of an n-gram trie - are placed with one ballot;
+      // the shuffle scan only runs when some lane of the warp has a child block to expand
+      const bool one = push == 1 && nd.cap == 0;
+      const int many = one ? 0 : push;
+      const unsigned m1 = __ballot_sync(FULL, one);
+      const unsigned mm = __ballot_sync(FULL, many > 0);
+      int incl = many;
+      if (mm) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      const int total = __shfl_sync(FULL, incl, 31);
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      }
+      const int tot_many = mm ? __shfl_sync(FULL, incl, 31) : 0;
+      const int total = __popc(m1) + tot_many;
       int wbase = 0;
-      if (lane == 31 && total > 0) wbase = atomicAdd(&sh->next_cnt, total);
-      wbase = __shfl_sync(FULL, wbase, 31);
-      if (push) {
-        const int pos = wbase + incl - push;
-        if (pos + push > D.fr_cap) atomicOr(&sh->err, ERR_FRONTIER);
-        else if (nd.cap == 0) nxt[pos] = nd.child;
-        else { for (int k = 0; k < push; ++k) nxt[pos + k] = D.edges[nd.child + k].y; ne += push; }
+      if (lane == 0 && total > 0) wbase = atomicAdd(&sh->next_cnt, total);
+      wbase = __shfl_sync(FULL, wbase, 0);
+      if (total > 0 && wbase + total > D.fr_cap) {
+        if (lane == 0) atomicOr(&sh->err, ERR_FRONTIER);
+      } else {
+        if (one) nxt[wbase + __popc(m1 & ((1u << lane) - 1u))] = nd.child;
+        if (many > 0) {
+          const int pos = wbase + __popc(m1) + incl - many;
+          for (int k = 0; k < many; ++k) nxt[pos + k] = D.edges[nd.child + k].y;
+          ne += many;
+        }
       }
     }
     __syncthreads();

@@ -60,8 +60,7 @@ class MixtralForCausalLM(LlamaForCausalLM):
         return g
 
     def _layer_gemm_plans(self, layer, b):
-        a = layer.self_attn
-        return {'qkv': self._mk_gemm(a.qkv_weight, b.y)}
+        return {}
 
     def _mlp(self, rt, layer, y, plans=None):
         moe = layer.mlp

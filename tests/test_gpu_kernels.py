@@ -289,3 +289,19 @@ def test_rmsnorm_partials_matches_bf16_input():
     # the slice sum is taken in slice order in fp32, like torch's sum over dim 0 of 4 slices up to association
     assert (r0 != r1).float().mean().item() < 0.02 and (y0 != y1).float().mean().item() < 0.02
     assert torch.allclose(y0.float(), y1.float(), atol=2e-2, rtol=2e-2)
+
+
+def test_gemm_fused_silu_epilogue_matches_unfused():
+    """gate_up GEMM with the SiLU(gate)*up epilogue == plain GEMM followed by k_silu_mul, bit for bit"""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(5)
+    inter, K = 1024, 512
+    w = (torch.randn((2 * inter, K), device=DEV) * 0.05).to(torch.bfloat16)
+    x = torch.randn((64, K), device=DEV).to(torch.bfloat16)
+    gu = ops.Gemm(ops.tile_weight(w), x, tiled=True).run(64)
+    ref = torch.empty((64, inter), dtype=torch.bfloat16, device=DEV)
+    ops.silu_mul(gu, ref)
+    got = torch.zeros_like(ref)
+    ops.Gemm(ops.tile_weight(ops.interleave_gate_up(w)), x, tiled=True).set_silu().run(64, out=got)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref)
