@@ -179,6 +179,7 @@ def run_ours(args):
     sampler.join(timeout=2)
     roof = attention_roofline(model, dev) if rank == 0 else None
     trie_roof = trie_roofline(dev) if rank == 0 else None
+    roof_long = attention_roofline_long(dev) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args, warm_outputs, timed[0])
@@ -208,7 +209,7 @@ def run_ours(args):
                     'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (4 + DL)),
                     'mean_accepted_len_per_step': e2e['mean_edl']},
             'gpu_launches': res['launches'],
-            'roofline': roof, 'roofline_trie_get': trie_roof, 'cpu_baseline': cpu,
+            'roofline': roof, 'roofline_long_context': roof_long, 'roofline_trie_get': trie_roof, 'cpu_baseline': cpu,
         }
         print(json.dumps(line))
     if world > 1:
@@ -250,9 +251,54 @@ def attention_roofline(model, dev):
     by = 2 * L * g['n_kv_heads'] * g['head_dim'] * 2 + 2 * n * g['n_q_heads'] * g['head_dim'] * 2
     hbm, _tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
-    return {'kernel': 'k_tree_attn+k_combine (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
+    return {'kernel': 'k_tree_attn (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
             'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'us_per_launch': us,
             'shape': f'n={n} P={P} Hq={g["n_q_heads"]} Hkv={g["n_kv_heads"]} D={g["head_dim"]}', 'peak_source': src}
+
+
+def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
+    """the same kernel where it is bandwidth- rather than latency-bound: a 4 k-token context (32 KV tiles per head, KV
+    planes of the 4 layers = 270 MB > L2), stand-alone plan, CUDA-graph replay"""
+    import torch
+    from painlessinferenceacceleration_b200.common import ops
+    D, R = 128, 64
+    max_seq = P + n + 64
+    kc = (torch.randn((layers, hkv, max_seq, D), device=dev) * 0.5).to(torch.bfloat16)
+    vc = (torch.randn((layers, hkv, max_seq, D), device=dev) * 0.5).to(torch.bfloat16)
+    q = (torch.randn((R, hq, D), device=dev) * 0.5).to(torch.bfloat16)
+    out = torch.zeros_like(q)
+    plan = ops.AttnPlan(kc, vc, hq, hkv, D, R)
+    rows = np.array([(1 << (i + 1)) - 1 if i < 63 else 0xFFFFFFFFFFFFFFFF for i in range(R)], dtype=np.uint64)
+    mask = torch.from_numpy(rows.view(np.int64)).to(dev).view(R, 1)
+    dn = torch.tensor([n], dtype=torch.int32, device=dev)
+    dP = torch.tensor([P], dtype=torch.int32, device=dev)
+
+    def sweep():
+        for li in range(layers):
+            plan.forward(li, q, mask, dn, dP, 0, out)
+
+    sweep()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        sweep()
+    graph.replay()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * layers)
+    L = P + n
+    by = 2 * L * hkv * D * 2 + 2 * n * hq * D * 2
+    hbm, _tf, src = peaks()
+    ach = by / (us * 1e-6) / 1e9
+    return {'kernel': 'k_tree_attn (one layer, long context)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
+            'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'us_per_launch': us,
+            'shape': f'n={n} P={P} Hq={hq} Hkv={hkv} D={D}', 'peak_source': src}
 
 
 def trie_roofline(dev, n_docs=1500, n_queries=4096):
