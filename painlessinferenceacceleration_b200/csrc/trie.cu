@@ -316,14 +316,14 @@ __global__ void k_put_finish(Dev D, int B, int final, int slot) {
 // ---------------------------------------------------------------------------------------------------
 // CTA-wide breadth-first walk below `start`; visit(id, node) -> descend?
 // ---------------------------------------------------------------------------------------------------
-struct BfsShared { int next_cnt; int err; };
+struct BfsShared { int next_cnt[3]; int err; };  // three rotating level counters: one barrier per BFS level
 
 template <class Visit>
-__device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared *sh, Visit &&visit,
+__device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared *sh, Visit &&visit,
                           unsigned long long &nv, unsigned long long &ne) {
   const int tid = threadIdx.x, lane = lane_id();
   const Node s = D.nodes[start];
-  if (tid == 0) sh->next_cnt = 0;
+  if (tid == 0) { sh->next_cnt[0] = 0; sh->next_cnt[1] = 0; sh->next_cnt[2] = 0; }
   int cnt = s.n_child;
   if (s.cap == 0) {
     if (tid == 0 && cnt == 1) fr0[0] = s.child;
@@ -334,7 +334,9 @@ __device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared
   }
   __syncthreads();
   int *cur = fr0, *nxt = fr1;
-  while (cnt > 0) {
+  for (int level = 0; cnt > 0; ++level) {
+    int *push_cnt = &sh->next_cnt[(level + 1) % 3];
+    if (tid == 0) sh->next_cnt[(level + 2) % 3] = 0;  // the counter of the level after next: idle during this level
     for (int base = 0; base < cnt; base += NT) {
       const int e = base + tid;
       int push = 0;
@@ -360,7 +362,7 @@ __device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared
       const int tot_many = mm ? __shfl_sync(FULL, incl, 31) : 0;
       const int total = __popc(m1) + tot_many;
       int wbase = 0;
-      if (lane == 0 && total > 0) wbase = atomicAdd(&sh->next_cnt, total);
+      if (lane == 0 && total > 0) wbase = atomicAdd(push_cnt, total);
       wbase = __shfl_sync(FULL, wbase, 0);
       if (total > 0 && wbase + total > D.fr_cap) {
         if (lane == 0) atomicOr(&sh->err, ERR_FRONTIER);
@@ -374,19 +376,17 @@ __device__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared
       }
     }
     __syncthreads();
-    cnt = sh->next_cnt;
+    cnt = *push_cnt;
     if (cnt > D.fr_cap) cnt = 0;  // overflowed level: err already set
-    __syncthreads();
-    if (tid == 0) sh->next_cnt = 0;
-    __syncthreads();
     int *t = cur; cur = nxt; nxt = t;
   }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // get
 // ---------------------------------------------------------------------------------------------------
-constexpr int HCAP = 1024;                       // distinct frequency values per histogram
+constexpr int HCAP = 512;                        // distinct frequency values per histogram
 constexpr unsigned long long HEMPTY = ~0ull;
 
 struct Hist { unsigned long long key[HCAP]; unsigned cnt[HCAP]; };
@@ -462,7 +462,7 @@ constexpr int CF_FI = 1, CF_FO = 2, CF_KIDS = 4;
 // threshold filter (lookahead_cache.py:264-272), ordered by fm descending, ties by insertion order (:254-258),
 // truncated to K (no more than K can still be emitted).
 template <int MAXS, int MAXD>
-__device__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int K, int idx, int mode, double omw,
+__device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int K, int idx, int mode, double omw,
                            double w, double min_in, double min_out, double min_mix, int *onode, int *otok,
                            unsigned char *oflag, unsigned long long &nv, unsigned long long &ne) {
   const int tid = threadIdx.x;
@@ -525,7 +525,7 @@ __device__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int
 // Tree.get (lookahead_cache.py:65-144) for the tree rooted at `root`, query suffix q[0..nq).
 // Result is left in S->ids / S->mask / S->n / S->sizes*.  returns PIA_OK / PIA_ERR_INDEX / PIA_ERR_CAPACITY.
 template <int MAXS, int MAXD>
-__device__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree_token, const int *q, int nq,
+__device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree_token, const int *q, int nq,
                         int max_size, int max_length, int min_in_sz, int min_out_sz, int mode, int idx, int *fr0,
                         int *fr1, unsigned long long &nv, unsigned long long &ne) {
   const int tid = threadIdx.x;
@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(NT) k_get(Dev D, GetParams P) {
     if (nq > 16) { qsrc += nq - 16; nq = 16; }
     if (nq < 0) nq = 0;
     if (tid < nq) S->q[tid] = qsrc[tid];
-    if (tid == 0) { S->bfs.err = 0; S->bfs.next_cnt = 0; }
+    if (tid == 0) { S->bfs.err = 0; }
     __syncthreads();
     const int idx = P.d_idx ? P.d_idx[b] : P.idx;
     int status = PIA_OK, n_out = 0, nsizes = 2, sz0 = 0, sz1 = 0;
@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx) {
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
     const int key = D.updin_list[i];
     const int root = D.root_of[key];
-    if (threadIdx.x == 0) { sh.err = 0; sh.next_cnt = 0; D.tree_flags[key] &= ~FLAG_UPDIN; }
+    if (threadIdx.x == 0) { sh.err = 0; D.tree_flags[key] &= ~FLAG_UPDIN; }
     __syncthreads();
     if (root < 0) continue;
     auto visit = [&](int id, const Node &nd) -> bool {

@@ -189,18 +189,11 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         return plans
 
     def _layer_gemm_plans(self, layer, b):
-        """which projections go through k_gemm_ws is decided by measurement (scripts/gemm_bench.py, Llama-2-7B
-        shapes, us per launch): gate_up 33.8 vs cuBLAS 35.6, down (split-K 4) 18.6 vs 19.7, lm_head 42.3 vs 46.6;
-        qkv (96 weight tiles) 22.1 vs 20.3 and o (32 tiles) 10.3 vs 9.8 stay on cuBLAS."""
-        m = layer.mlp
-        plans = {'down': self._mk_gemm(m.down_proj.weight.data, b.act, split_k=4)}
-        inter = m.gate_up_weight.shape[0] // 2
-        if inter % 64 == 0:  # SiLU(gate) * up fused into the GEMM epilogue (no gate_up round trip, one launch less)
-            plans['gate_up_silu'] = ops.Gemm(ops.tile_weight(ops.interleave_gate_up(m.gate_up_weight)), b.y,
-                                             tiled=True).set_silu()
-        else:
-            plans['gate_up'] = self._mk_gemm(m.gate_up_weight, b.y)
-        return plans
+        """Which projections go through k_gemm_ws is decided by measurement (scripts/gemm_bench.py, Llama-2-7B shapes,
+        us per launch incl. the consumer kernel): gate_up 35.5 vs cuBLAS 38.6 (both + k_silu_mul; the fused SiLU
+        epilogue costs 38.3), lm_head 42.3 vs 46.6.  qkv (96 weight tiles: 22.1 vs 20.3), o (32 tiles: 10.3 vs 9.8) and
+        down (split-K 4 + rmsnorm over partials 23.3 vs 22.6) stay on cuBLAS."""
+        return {'gate_up': self._mk_gemm(layer.mlp.gate_up_weight, b.y)}
 
     @staticmethod
     def _mk_gemm(w, x, split_k=1):
@@ -215,12 +208,9 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         m = layer.mlp
         if plans:
             b = rt.decode_bufs
-            if 'gate_up_silu' in plans:
-                plans['gate_up_silu'].run(64, out=b.act)
-            else:
-                plans['gate_up'].run(64, out=b.gu)
-                ops.silu_mul(b.gu, b.act)
-            return None, plans['down'].run(64)
+            plans['gate_up'].run(64, out=b.gu)
+            ops.silu_mul(b.gu, b.act)
+            return torch.mm(b.act, m.down_proj.weight.t()), None
         gu = torch.mm(y, m.gate_up_weight.t())
         act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=gu.dtype, device=gu.device)
         ops.silu_mul(gu, act)

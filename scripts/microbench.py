@@ -79,3 +79,17 @@ rt.seq[:256] = torch.tensor(docs[0], dtype=torch.int32, device=dev)
 rt.seq_len.fill_(200)
 timeit('trie get (1 query, tail mode)', lambda: trie.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=rt.draft), 1)
 print('draft n =', int(rt.n))
+
+# single-request trie get on a large forest (1 M nodes), hot and cold queries
+big = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size, node_capacity=1 << 23)
+docs = bench.phrase_bank_prompts(1500, cfg.vocab_size, seed=7)
+for d in docs:
+    big.put(d, branch_length=9, mode='output', idx=-1)
+st0 = big.stats()
+for name, q in (('hot (3,3)', [3, 3]), ('doc pair', docs[5][100:102]), ('rare', docs[7][40:42])):
+    rt.seq[:2] = torch.tensor(q, dtype=torch.int32, device=dev)
+    rt.seq_len.fill_(2)
+    s0 = big.stats()
+    us = timeit(f'trie get 1M-node forest, {name}', lambda: big.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=rt.draft), 1)
+    s1 = big.stats()
+    print('   draft n =', int(rt.n), ' nodes visited per call ~', (s1['nodes_visited'] - s0['nodes_visited']) // 22)
