@@ -43,6 +43,8 @@ constexpr int SUB = 128 * 128;             // bytes of one [128 rows x 64 bf16] 
 constexpr int TILE_BYTES = 2 * SUB;        // one 128 x 128 bf16 operand tile
 constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_K = 2 * TILE_BYTES, SMEM_V = SMEM_K + NSTAGE * TILE_BYTES;
 constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
+constexpr int MRG_ACC = 0;                        // [n_split * RS][128] fp32 partial rows pushed by the cluster (over dead Q/P/KV tiles)
+constexpr int MRG_ML = 160 * 1024;                // [n_split * RS] (m, l) pairs
 constexpr int SMEM_XCH = SMEM_BAR + 256;           // row max / row sum exchange between the two column halves
 constexpr int SMEM_TOTAL = SMEM_XCH + 3 * 1024 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
@@ -109,6 +111,20 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
@@ -172,7 +188,10 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   int ns = (tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   if (ns > p.n_split) ns = p.n_split;
   if (ns < 1) ns = 1;
-  if (split >= ns) return;
+  if (split >= ns) {
+    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }
+    return;
+  }
   const int tps = (tiles_total + ns - 1) / ns;
   const int t0 = split * tps;
   int t1 = t0 + tps;
@@ -224,6 +243,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         if (i == 0) DBG(2);
       }
     }
+    __syncwarp();
+    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
     if (lane == 0 && ntile > 0) {
@@ -261,6 +282,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       }
       DBG(4);
     }
+    __syncwarp();
+    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }
   } else if (warp_active) {
     // ================================================================ softmax + accumulate
     // two threads per row: `half` selects 64 of the 128 S columns (keys) and 64 of the 128 O columns (head dim)
@@ -394,14 +417,26 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
                               *reinterpret_cast<uint32_t *>(&b2), *reinterpret_cast<uint32_t *>(&b3));
         }
       }
-    } else if (row_live) {
-      const long long o = ((long long)split * p.n_q_heads + hq0 + hs) * p.np + node;
-      if (half == 0) { p.ws_m[o] = m_run; p.ws_l[o] = l_run; }
-      float4 *dst = reinterpret_cast<float4 *>(p.ws_acc + o * HD + half * 64);
+    } else {
+      // several splits: the ns CTAs of this head group form one thread-block cluster.  After everyone has left its
+      // tile loop (barrier A: the Q/P/KV tiles of every CTA are dead) each thread pushes its row half - acc, and the
+      // row's (m, l) - straight into the shared memory of the CTA that owns that row's slice (DSMEM), barrier B,
+      // and every CTA combines its slice locally: no workspace round trip through L2, no serial last-arriver merge.
+      cluster_sync_all();
+      const int RS = (rows_used + ns - 1) / ns;       // rows per owner CTA
+      const int owner = row / RS, rl = row % RS;
+      if (row_live) {
+        const uint32_t slot = base + MRG_ACC + (uint32_t)((split * RS + rl) * HD + half * 64) * 4;
+        const uint32_t dst = map_to_cta(slot, owner);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        for (int j = 0; j < 16; ++j) st_cluster_f4(dst + j * 16, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (half == 0) st_cluster_f2(map_to_cta(base + MRG_ML + (uint32_t)(split * RS + rl) * 8, owner), m_run, l_run);
+      }
+      cluster_sync_all();
     }
     if (row == 0 && half == 0) DBG(10);
+  } else {
+    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }  // idle softmax warps (rows 64..127 of an MHA tile)
   }
   tc_fence_before();
   __threadfence();
@@ -411,60 +446,33 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
   if (ns > 1) {
-    // the last split CTA of this head group to arrive merges the partials (no separate combine launch)
-    __shared__ int s_last;
-    if (tid == 0) {
-      const int prev = atomicAdd(&p.counters[group], 1);
-      s_last = (prev == ns - 1);
-      if (s_last) p.counters[group] = 0;  // self-reset for the next launch
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      // (1) per-row split weights  wn[r][s] = 2^(m_s - M) / sum_s l_s 2^(m_s - M)  into shared memory (P tile is free)
-      float *wn = reinterpret_cast<float *>(sm + SMEM_P);  // [rows_used][MAX_SPLIT]
-      for (int r = tid; r < rows_used; r += NTHREADS) {
-        const int rh = r / p.np, rn = r % p.np;
-        float ms[MAX_SPLIT], ls[MAX_SPLIT];
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
-          const long long o = ((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn;
-          const bool on = s2 < ns && rn < n;
-          ms[s2] = on ? p.ws_m[o] : -INFINITY;
-          ls[s2] = on ? p.ws_l[o] : 0.f;
-        }
-        float M = -INFINITY, den = 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) M = fmaxf(M, ms[s2]);
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) { ms[s2] = ms[s2] == -INFINITY ? 0.f : ex2(ms[s2] - M); den += ls[s2] * ms[s2]; }
-        const float inv = den > 0.f ? 1.f / den : 0.f;
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) wn[r * MAX_SPLIT + s2] = ms[s2] * inv;
+    // combine this CTA's row slice: out[r][:] = sum_i acc_i 2^(m_i - M) / sum_i l_i 2^(m_i - M), all operands local
+    const int RS = (rows_used + ns - 1) / ns;
+    const float *macc = reinterpret_cast<const float *>(sm + MRG_ACC);
+    const float2 *mml = reinterpret_cast<const float2 *>(sm + MRG_ML);
+    const int items = RS * (HD / 4);
+    for (int it = tid; it < items; it += NTHREADS) {
+      const int rl = it / (HD / 4), c4 = it % (HD / 4);
+      const int r = split * RS + rl;
+      if (r >= rows_used) continue;
+      const int rh = r / p.np, rn = r % p.np;
+      if (rn >= n) continue;
+      float M = -INFINITY;
+      for (int i = 0; i < ns; ++i) M = fmaxf(M, mml[i * RS + rl].x);
+      float den = 0.f;
+      float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < ns; ++i) {
+        const float2 ml = mml[i * RS + rl];
+        if (ml.x == -INFINITY) continue;
+        const float w = ex2(ml.x - M);
+        den += ml.y * w;
+        const float4 a4 = reinterpret_cast<const float4 *>(macc + (size_t)(i * RS + rl) * HD)[c4];
+        o4.x += a4.x * w; o4.y += a4.y * w; o4.z += a4.z * w; o4.w += a4.w * w;
       }
-      __syncthreads();
-      // (2) out[r][:] = sum_s wn[r][s] * acc_s[r][:], thread = (row, 4 floats), loads of all splits in flight together
-      const int items = rows_used * (HD / 4);
-      for (int it = tid; it < items; it += NTHREADS) {
-        const int r = it / (HD / 4), c4 = it % (HD / 4);
-        const int rh = r / p.np, rn = r % p.np;
-        if (rn >= n) continue;
-        float4 a[MAX_SPLIT];
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
-          const long long o = ((long long)s2 * p.n_q_heads + hq0 + rh) * p.np + rn;
-          a[s2] = s2 < ns ? reinterpret_cast<const float4 *>(p.ws_acc + o * HD)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int s2 = 0; s2 < MAX_SPLIT; ++s2) {
-          const float w = wn[r * MAX_SPLIT + s2];
-          acc4.x += a[s2].x * w; acc4.y += a[s2].y * w; acc4.z += a[s2].z * w; acc4.w += a[s2].w * w;
-        }
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(acc4.x, acc4.y), b1 = __floats2bfloat162_rn(acc4.z, acc4.w);
-        reinterpret_cast<uint2 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[c4] =
-            make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
-      }
+      const float inv = den > 0.f ? 1.f / den : 0.f;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(o4.x * inv, o4.y * inv), b1 = __floats2bfloat162_rn(o4.z * inv, o4.w * inv);
+      reinterpret_cast<uint2 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[c4] =
+          make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
     }
   }
   if (tid == 0) DBG(11);
@@ -595,7 +603,8 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   a.out = (__nv_bfloat16 *)d_out; a.counters = p->counters; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
-  PIA_CUDA_CHECK(launch_kernel(k_tree_attn, dim3(p->n_split, p->n_groups), dim3(NTHREADS), SMEM_TOTAL, s, p->map_k, p->map_v, a));
+  PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(p->n_split, p->n_groups), dim3(NTHREADS), SMEM_TOTAL, s,
+                                       (unsigned)p->n_split, p->map_k, p->map_v, a));
   count_launch();
   return PIA_OK;
 }
