@@ -379,6 +379,17 @@ def build_cpu_model(name):
     return m.eval()
 
 
+def cpu_probe(model, n_tok=16):
+    """seconds of one eager forward over n_tok tokens on the host (second call, after thread-pool warm-up)"""
+    import torch
+    x = torch.randint(3, 1000, (1, n_tok))
+    with torch.no_grad():
+        model(input_ids=x)
+        t0 = time.time()
+        model(input_ids=x)
+    return time.time() - t0
+
+
 def cpu_sample(model, trie, prompt, budget_s, max_new=NEW_TOKENS):
     """one request through the oracle loop (oracle/loop.py = the reference's CPU path restated), cut off at the first
     step boundary after `budget_s` seconds; returns (new tokens, seconds, edls)"""
@@ -399,12 +410,25 @@ def cpu_epoch2_sample(model, trie, prompt, budget_s):
     return n, secs, edls
 
 
-SAMPLE_NOTE = ('1 request = {p}-token prompt prefill + verify steps regenerating the g tokens that an untimed cold run of '
-               'the same request produced in {b:.0f}s (second-epoch regime of the GPU arm, bounded: the prefill is not '
-               'amortised over {n} tokens as on the GPU)')
+def cpu_plan(model, step_budget_s):
+    """how much of the 256-token prompt a CPU sample may use so that one step (cold run + timed re-run) fits the budget:
+    a 16-token probe forward gives the host's speed; forwards scale ~linearly in rows at these sizes"""
+    f16 = cpu_probe(model, 16)
+    per_tok = f16 / 16.0
+    # one step = 2 prefills of S tokens + about 4 verify forwards of up to 64 rows (cold) + 2 (timed)
+    S = PROMPT_LEN
+    while S > 16 and (2 * S + 6 * 64) * per_tok > step_budget_s:
+        S //= 2
+    cold_budget = max(1.0, step_budget_s - (2 * S + 2 * 64) * per_tok)
+    return S, cold_budget, f16
 
 
-def cpu_baseline(args, warm_outputs, prompt):
+SAMPLE_NOTE = ('1 request = prefill of the first {S} of the {p} prompt tokens + verify steps regenerating the g tokens that an '
+               'untimed cold run of the same request produced in {b:.0f}s (second-epoch regime of the GPU arm; bounded: a '
+               '16-token probe forward took {f:.2f}s on this host, and the prefill is not amortised over {n} tokens)')
+
+
+def cpu_baseline(args, warm_outputs, prompt, total_budget_s=60.0):
     import torch
     from oracle.trie import OracleLookaheadCache
     cores = os.cpu_count() or 1
@@ -415,18 +439,19 @@ def cpu_baseline(args, warm_outputs, prompt):
     for w in warm_outputs:  # same warm-up text as the GPU run (benchmark.py:159-169)
         trie.put(w, branch_length=BL + 1, mode='output', idx=-1)
     build_s = time.time() - t0
-    budget = 12.0
-    ntok, secs, edls = cpu_epoch2_sample(model, trie, prompt, budget)
+    S, cold_budget, f16 = cpu_plan(model, total_budget_s)
+    ntok, secs, edls = cpu_epoch2_sample(model, trie, prompt[:S], cold_budget)
     return {'value': ntok / secs, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port',
             'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host: '
-                      + SAMPLE_NOTE.format(p=PROMPT_LEN, b=budget, n=NEW_TOKENS)
+                      + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, b=cold_budget, f=f16, n=NEW_TOKENS)
                       + f'; {ntok} tokens in {secs:.1f}s over {len(edls)} forwards (model build {build_s:.0f}s untimed)',
             'mean_accepted_len_per_step': float(np.mean(edls[1:])) if len(edls) > 1 else None}
 
 
-def run_reference(args):
+def run_reference(args, total_budget_s=150.0):
     """--impl reference: the reference's own CPU path (restated: oracle/loop.py over the installed HF eager model +
-    the C restatement of its trie) on the host cores; rank 0 only."""
+    the C restatement of its trie) on the host cores; rank 0 only.  The whole run is time-boxed (~total_budget_s of
+    forwards + the model build) whatever --steps/--warmup are."""
     import torch
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -439,17 +464,17 @@ def run_reference(args):
     trie = OracleLookaheadCache(eos_ids=[2])
     allp = phrase_bank_prompts(64 + 8 * max(args.warmup, 1), cfg.vocab_size)
     K, Wm = args.steps, args.warmup
-    budget = max(3.0, min(12.0, 110.0 / max(K, 1)))
-    for i in range(Wm):
-        cpu_sample(model, trie, allp[64 + i], 1.0)
+    S, cold_budget, f16 = cpu_plan(model, total_budget_s / max(K + 0.25 * Wm, 1))
+    for i in range(Wm):  # warm-up: short cold runs (thread pools, allocator, trie)
+        cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
     toks, secs, edls = 0, 0.0, []
     for i in range(K):
-        n, s, e = cpu_epoch2_sample(model, trie, allp[i % 64], budget)
+        n, s_, e = cpu_epoch2_sample(model, trie, allp[i % 64][:S], cold_budget)
         toks += n
-        secs += s
+        secs += s_
         edls += e[1:]
     v = toks / secs
-    sample = ('per step: ' + SAMPLE_NOTE.format(p=PROMPT_LEN, b=budget, n=NEW_TOKENS)
+    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, b=cold_budget, f=f16, n=NEW_TOKENS)
               + f'; {args.model} bf16 on {cores} host threads; {toks} tokens in {secs:.0f}s over {K} steps')
     print(json.dumps({
         'impl': 'reference', 'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
