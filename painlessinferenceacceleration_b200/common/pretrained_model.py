@@ -119,6 +119,25 @@ class _Runtime(object):
         return torch.from_numpy(rows.view(np.int64)).to(self.device)
 
 
+def _chain_without_first(self, k):
+    """chain mask whose first k columns (left-pad tokens of this chunk) are cleared"""
+    cache = self.__dict__.setdefault('_chain_cut', {})
+    if k not in cache:
+        rows = self.chain.cpu().numpy().view(np.uint64).copy()
+        R = self.max_nodes
+        for w in range(R // 64):
+            lo = 64 * w
+            if k >= lo + 64:
+                rows[:, w] = 0
+            elif k > lo:
+                rows[:, w] &= ~np.uint64((1 << (k - lo)) - 1)
+        cache[k] = torch.from_numpy(rows.view(np.int64)).to(self.device)
+    return cache[k]
+
+
+_Runtime.chain_without_first = _chain_without_first
+
+
 class LookaheadPreTrainedModel(nn.Module):
     """Base class of the patched models (reference :48). Subclasses implement geometry(), rope_tables() and
     _verify_layers(rt) (the per-model forward over the static draft buffers)."""
@@ -388,7 +407,13 @@ class LookaheadPreTrainedModel(nn.Module):
             meta = torch.tensor([ns, [pos + R * c for c in range(C)]], dtype=torch.int32).to(rt.device)
             rt.pf_n.copy_(meta[0])
             rt.pf_P.copy_(meta[1])
-            pb.chunks = [(R * c, R * (c + 1), rt.chain, rt.pf_n[c:c + 1], rt.pf_P[c:c + 1]) for c in range(C) if ns[c] > 0]
+            masks = [rt.chain] * C
+            if rt.pad_len > pos:  # left padding (:1123-1131): pad columns are invisible, also inside a chain chunk
+                masks = []
+                for c in range(C):
+                    k = min(max(rt.pad_len - (pos + R * c), 0), R)
+                    masks.append(rt.chain if k == 0 else rt.chain_without_first(k))
+            pb.chunks = [(R * c, R * (c + 1), masks[c], rt.pf_n[c:c + 1], rt.pf_P[c:c + 1]) for c in range(C) if ns[c] > 0]
             last = pos + m >= prompt_len
             self._verify_layers(rt, bufs=pb, last_only=not last)
             pos += m

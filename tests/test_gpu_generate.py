@@ -27,9 +27,10 @@ def _diag(name, **kw):
 def _pair(family, seed):
     """HF oracle model (bf16, on the GPU so that it is fast) and our model with the same weights"""
     from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+    from painlessinferenceacceleration_b200.models.mixtral.modeling_mixtral import MixtralForCausalLM
     hf = tiny_hf_model(family, seed=seed, dtype=torch.bfloat16, device=DEV, vocab=200)
     hf.fp32_twin = None
-    ours = LlamaForCausalLM(hf.config, device=torch.device(DEV))
+    ours = (MixtralForCausalLM if family == 'mixtral' else LlamaForCausalLM)(hf.config, device=torch.device(DEV))
     missing = ours.load_state_dict(hf.state_dict(), strict=False)
     assert not missing.missing_keys, missing
     return hf, ours
@@ -54,7 +55,7 @@ def _legit_divergence(family, hf, prefix, tok_a, tok_b, penalty=1.0):
     return gap <= 4 * noise + 0.05, gap, noise
 
 
-@pytest.mark.parametrize('family,penalty', [('llama', 1.0), ('mistral', 1.0), ('mistral', 1.1)])
+@pytest.mark.parametrize('family,penalty', [('llama', 1.0), ('mistral', 1.0), ('mistral', 1.1), ('mixtral', 1.0)])
 def test_generate_matches_oracle(family, penalty):
     from oracle.loop import lookahead_generate
     from oracle.trie import OracleLookaheadCache
@@ -186,7 +187,7 @@ def test_loop_is_exact_given_the_same_logits(family, penalty):
     assert max(edl_all) > 2
 
 
-@pytest.mark.parametrize('family', ['llama', 'mistral'])
+@pytest.mark.parametrize('family', ['llama', 'mistral', 'mixtral'])
 def test_verify_logits_within_tolerance(family):
     """"verify logits within a stated fp tolerance" (BASELINE north_star): our bf16 forward vs an fp32 evaluation of
     the same weights (the truth), next to the reference-style bf16 eager forward's own error.
@@ -211,3 +212,49 @@ def test_verify_logits_within_tolerance(family):
     # greedy tokens agree wherever the fp32 margin exceeds twice the error
     sure = margin > 2 * e_ours
     assert torch.equal(got.argmax(-1)[sure], truth.argmax(-1)[sure])
+
+
+def test_left_padding_eos_and_streamer():
+    """2-D attention_mask with a left-padded prompt (pretrained_model.py:1123-1131), eos stopping (:1228-1231) and the
+    streamer protocol (:1199-1201: the whole accepted list per step) against the oracle loop"""
+    from oracle.loop import lookahead_generate
+    from oracle.trie import OracleLookaheadCache
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    hf, ours = _pair('llama', seed=12)
+    ours.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
+    otrie = OracleLookaheadCache(eos_ids=[2])
+    p = prompts(91, 1, 70, 200)[0].to(DEV)
+    pad = 5
+    padded = torch.cat([torch.zeros((1, pad), dtype=torch.long, device=DEV), p], dim=1)
+    am = torch.cat([torch.zeros((1, pad), dtype=torch.long, device=DEV), torch.ones_like(p)], dim=1)
+    ref = lookahead_generate(hf, otrie, padded, max_new_tokens=24, eos_token_id=[2], attention_mask=am)
+    eos = ref['sequences'][0, padded.shape[1] + 6].item()  # make the 7th generated token an eos
+
+    class Collect(object):
+        def __init__(self):
+            self.chunks, self.ended = [], False
+
+        def put(self, x):
+            self.chunks.append(x)
+
+        def end(self):
+            self.ended = True
+
+    for rep in range(2):
+        otrie2 = OracleLookaheadCache(eos_ids=[eos])
+        ours.lookahead_cache.fresh()
+        ref = lookahead_generate(hf, otrie2, padded, max_new_tokens=24, eos_token_id=[eos], attention_mask=am)
+        st = Collect()
+        out = ours.generate(input_ids=padded, attention_mask=am, max_new_tokens=24, eos_token_id=eos, streamer=st,
+                            decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
+                            return_dict_in_generate=True)
+        a, b = out.sequences[0].tolist(), ref['sequences'][0].tolist()
+        if a != b:
+            k = next(i for i in range(min(len(a), len(b))) if a[i] != b[i])
+            ok, gap, noise = _legit_divergence('llama', hf, ref['sequences'][:, :k], a[k], b[k])
+            assert ok, f'diverged at {k}: gap {gap:.3f} noise {noise:.3f}'
+        else:
+            assert a[-1] == eos and len(a) < padded.shape[1] + 24
+        assert st.ended
+        streamed = [int(t) for c in st.chunks[1:] for t in (c.reshape(-1).tolist())]
+        assert streamed == a[padded.shape[1]:]
