@@ -123,6 +123,17 @@ int pia_trie_stats(pia_trie_t *t, pia_trie_stats_t *h_out, void *stream);
 /* per-tree counters Tree.n_node / n_output_node (lookahead_cache.py:29-30); -1 when the tree is absent. Synchronous. */
 int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_node, int64_t *h_n_output_node, void *stream);
 
+/* Persistence (LookaheadCache.save_mem / load_mem, lookahead_cache.py:578-587): the forest as raw pools in HOST
+ * memory.  Node record (32 bytes): {int32 token, int32 n_child, int32 child, int32 cap, double fo, float fi, int32 aux};
+ * cap == 0: `child` is the node id of the only child, else the offset of a block of (int32 token, int32 node) entries,
+ * children in insertion order.  h_root_of / h_n_node / h_n_out are indexed by first token ([vocab_capacity]).
+ * All three synchronise `stream`. */
+int pia_trie_export_sizes(pia_trie_t *t, int64_t *n_nodes, int64_t *n_edges, void *stream);
+int pia_trie_export(pia_trie_t *t, void *h_nodes, int64_t n_nodes, void *h_edges, int64_t n_edges, int32_t *h_root_of,
+                    int32_t *h_n_node, int32_t *h_n_out, void *stream);
+int pia_trie_import(pia_trie_t *t, const void *h_nodes, int64_t n_nodes, const void *h_edges, int64_t n_edges,
+                    const int32_t *h_root_of, const int32_t *h_n_node, const int32_t *h_n_out, void *stream);
+
 /* ============================================================================================
  * Tree-masked attention (verify forward)
  *   models/llama/modeling_llama.py:584-588 (mask -> positions) and :243-308 (eager attention);

@@ -323,11 +323,164 @@ class LookaheadCache(object):
                                                        self._t.stream()))
         return a.value, b.value
 
+    # ---- persistence (reference :578-587): the file is json(json(pickle(mem).decode('latin-1'))) with
+    #      mem = {token: Tree}, Tree/Node being the reference's classes; they are re-created here by name so that
+    #      files written by either implementation load in the other
+    def _export_arrays(self):
+        t = self._t
+        nn, ne = C.c_int64(0), C.c_int64(0)
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_export_sizes(t.h, C.byref(nn), C.byref(ne), t.stream()))
+        nodes = np.zeros((max(nn.value, 1),), dtype=_NODE_DTYPE)
+        edges = np.zeros((max(ne.value, 1), 2), dtype=np.int32)
+        V = t.cfg.vocab_capacity
+        root_of = np.zeros((V,), dtype=np.int32)
+        n_node = np.zeros((V,), dtype=np.int32)
+        n_out = np.zeros((V,), dtype=np.int32)
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_export(t.h, nodes.ctypes.data, nn.value, edges.ctypes.data, ne.value,
+                                          root_of.ctypes.data, n_node.ctypes.data, n_out.ctypes.data, t.stream()))
+        return nodes[:nn.value], edges[:ne.value], root_of, n_node, n_out
+
+    def to_reference_mem(self):
+        """the forest as the reference's `mem` structure: {token: Tree} of nested Node dicts"""
+        nodes, edges, root_of, n_node, n_out = self._export_arrays()
+        tok, nch, child, cap = nodes['token'], nodes['n_child'], nodes['child'], nodes['cap']
+        fo, fi = nodes['fo'], nodes['fi']
+
+        def kids(i):
+            if nch[i] == 0:
+                return []
+            if cap[i] == 0:
+                return [int(child[i])]
+            return edges[child[i]:child[i] + nch[i], 1].tolist()
+
+        def build(i):
+            # iterative post-order (tries are at most branch_length+1 deep, but fan-out can be large)
+            freqs = {}
+            if fo[i] != 0.0 or fi[i] == 0.0:
+                freqs[-1] = float(fo[i])
+            if fi[i] != 0.0:
+                freqs[0] = float(fi[i])
+            return _RefNode({int(tok[c]): build(c) for c in kids(i)}, freqs)
+
+        mem = {}
+        for token in np.flatnonzero(root_of >= 0).tolist():
+            r = int(root_of[token])
+            tree = _RefTree.__new__(_RefTree)
+            tree.token_id = token
+            tree.max_node, tree.max_output_node = self._max_node, self._max_output_node
+            tree.n_node, tree.n_output_node = int(n_node[token]), int(n_out[token])
+            tree.nodes = {int(tok[c]): build(c) for c in kids(r)}
+            mem[token] = tree
+        return mem
+
+    def from_reference_mem(self, mem):
+        """replace the forest by a reference-format `mem` ({token: Tree}); freqs[-1] -> fo, freqs[0] -> fi"""
+        recs, edges = [], []
+        V = self._t.cfg.vocab_capacity
+        root_of = np.full((V,), -1, dtype=np.int32)
+        n_node = np.zeros((V,), dtype=np.int32)
+        n_out = np.zeros((V,), dtype=np.int32)
+
+        def add(token, node):
+            i = len(recs)
+            fr = getattr(node, 'freqs', {}) if node is not None else {}
+            recs.append([token, 0, -1, 0, float(fr.get(-1, 0.0)), float(fr.get(0, 0.0))])
+            return i
+
+        def link(i, children):  # children: dict token -> Node, in insertion order
+            ids = [add(int(tk), nd) for tk, nd in children.items()]
+            recs[i][1] = len(ids)
+            if len(ids) == 1:
+                recs[i][2] = ids[0]
+            elif len(ids) > 1:
+                cap_ = 4
+                while cap_ < len(ids):
+                    cap_ *= 2
+                recs[i][2], recs[i][3] = len(edges), cap_
+                edges.extend([[int(tk), c] for tk, c in zip(children.keys(), ids)])
+                edges.extend([[0, 0]] * (cap_ - len(ids)))
+            for c, nd in zip(ids, children.values()):
+                link(c, nd.children)
+
+        for token, tree in mem.items():
+            token = int(token)
+            assert 0 <= token < V
+            r = add(token, None)
+            root_of[token] = r
+            n_node[token], n_out[token] = int(tree.n_node), int(tree.n_output_node)
+            link(r, tree.nodes)
+        nodes = np.zeros((max(len(recs), 1),), dtype=_NODE_DTYPE)
+        for i, (tk, nc, ch, cp, fo_, fi_) in enumerate(recs):
+            nodes[i] = (tk, nc, ch, cp, fo_, fi_, 0)
+        ed = np.asarray(edges if edges else [[0, 0]], dtype=np.int32)
+        t = self._t
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_import(t.h, nodes.ctypes.data, len(recs), ed.ctypes.data, len(edges),
+                                          root_of.ctypes.data, n_node.ctypes.data, n_out.ctypes.data, t.stream()))
+
     def save_mem(self, save_dir):
-        raise NotImplementedError('trie persistence is SURVEY 8f-2 (next row); not built in this round')
+        """reference :578-582"""
+        import json
+        import pickle
+        import io
+
+        class _P(pickle._Pickler):  # writes the reference's class names without needing that package installed
+            def save_global(self, obj, name=None):
+                if obj is _RefTree or obj is _RefNode:
+                    self.write(pickle.GLOBAL + b'lookahead.common.lookahead_cache\n' + obj.__name__.encode() + b'\n')
+                    self.memoize(obj)
+                    return
+                super().save_global(obj, name)
+
+        buf = io.BytesIO()
+        _P(buf, protocol=4).dump(self.to_reference_mem())
+        serialized_object = buf.getvalue()
+        json_string = json.dumps(serialized_object.decode('latin-1'))
+        with open(save_dir, 'w') as f:
+            json.dump(json_string, f)
 
     def load_mem(self, load_dir):
-        raise NotImplementedError('trie persistence is SURVEY 8f-2 (next row); not built in this round')
+        """reference :584-587"""
+        import io
+        import json
+        import pickle
+        with open(load_dir, 'r') as f:
+            json_string = json.load(f)
+
+        class _U(pickle.Unpickler):
+            def find_class(self, module, name):
+                if module.endswith('lookahead_cache') and name == 'Tree':
+                    return _RefTree
+                if module.endswith('lookahead_cache') and name == 'Node':
+                    return _RefNode
+                return super().find_class(module, name)
+
+        self.from_reference_mem(_U(io.BytesIO(json.loads(json_string).encode('latin-1'))).load())
+
+
+_NODE_DTYPE = np.dtype([('token', '<i4'), ('n_child', '<i4'), ('child', '<i4'), ('cap', '<i4'), ('fo', '<f8'),
+                        ('fi', '<f4'), ('aux', '<i4')])
+
+
+class _RefNode(object):
+    """pickles as the reference's lookahead.common.lookahead_cache.Node (:13-21)"""
+    __slots__ = ['freqs', 'children']
+
+    def __init__(self, children, freqs):
+        self.children = children
+        self.freqs = freqs
+
+
+class _RefTree(object):
+    """pickles as the reference's lookahead.common.lookahead_cache.Tree (:24-31); data only"""
+    pass
+
+
+_RefNode.__module__ = _RefTree.__module__ = 'lookahead.common.lookahead_cache'
+_RefNode.__qualname__ = _RefNode.__name__ = 'Node'
+_RefTree.__qualname__ = _RefTree.__name__ = 'Tree'
 
 
 class Tree(object):

@@ -1276,3 +1276,56 @@ extern "C" int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_nod
   if (h_n_output_node) *h_n_output_node = root < 0 ? -1 : b;
   return PIA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// persistence (LookaheadCache.save_mem / load_mem, lookahead_cache.py:578-587): raw pools <-> host
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pia_trie_export_sizes(pia_trie_t *t, int64_t *n_nodes, int64_t *n_edges, void *stream) {
+  PIA_REQUIRE(t && n_nodes && n_edges, "null argument");
+  Hdr h;
+  PIA_CUDA_CHECK(cudaMemcpyAsync(&h, t->dev.hdr, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  PIA_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  *n_nodes = (int64_t)h.node_top; *n_edges = (int64_t)h.edge_top;
+  return PIA_OK;
+}
+
+extern "C" int pia_trie_export(pia_trie_t *t, void *h_nodes, int64_t n_nodes, void *h_edges, int64_t n_edges,
+                               int32_t *h_root_of, int32_t *h_n_node, int32_t *h_n_out, void *stream) {
+  PIA_REQUIRE(t && h_nodes && h_edges && h_root_of && h_n_node && h_n_out, "null argument");
+  PIA_REQUIRE(n_nodes <= t->cfg.node_capacity && n_edges <= t->cfg.edge_capacity, "sizes exceed the pools");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t v = (size_t)t->cfg.vocab_capacity * sizeof(int);
+  PIA_CUDA_CHECK(cudaMemcpyAsync(h_nodes, t->dev.nodes, (size_t)n_nodes * sizeof(Node), cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(h_edges, t->dev.edges, (size_t)n_edges * sizeof(int2), cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(h_root_of, t->dev.root_of, v, cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(h_n_node, t->dev.tree_n_node, v, cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(h_n_out, t->dev.tree_n_out, v, cudaMemcpyDeviceToHost, s));
+  PIA_CUDA_CHECK(cudaStreamSynchronize(s));
+  return PIA_OK;
+}
+
+// replaces the whole forest (like `self.mem = pickle.loads(...)`, :587); pending update sets are dropped
+extern "C" int pia_trie_import(pia_trie_t *t, const void *h_nodes, int64_t n_nodes, const void *h_edges, int64_t n_edges,
+                               const int32_t *h_root_of, const int32_t *h_n_node, const int32_t *h_n_out, void *stream) {
+  PIA_REQUIRE(t && h_nodes && h_edges && h_root_of && h_n_node && h_n_out, "null argument");
+  PIA_REQUIRE(n_nodes <= t->cfg.node_capacity && n_edges <= t->cfg.edge_capacity, "forest does not fit the pools");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t v = (size_t)t->cfg.vocab_capacity * sizeof(int);
+  PIA_CUDA_CHECK(cudaMemcpyAsync(t->dev.nodes, h_nodes, (size_t)n_nodes * sizeof(Node), cudaMemcpyHostToDevice, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(t->dev.edges, h_edges, (size_t)n_edges * sizeof(int2), cudaMemcpyHostToDevice, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(t->dev.root_of, h_root_of, v, cudaMemcpyHostToDevice, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(t->dev.tree_n_node, h_n_node, v, cudaMemcpyHostToDevice, s));
+  PIA_CUDA_CHECK(cudaMemcpyAsync(t->dev.tree_n_out, h_n_out, v, cudaMemcpyHostToDevice, s));
+  PIA_CUDA_CHECK(cudaMemsetAsync(t->dev.tree_flags, 0, v, s));
+  if (t->dev.fi_extra) PIA_CUDA_CHECK(cudaMemsetAsync(t->dev.fi_extra, 0, (size_t)(t->cfg.n_input_slots - 1) * t->cfg.node_capacity * sizeof(float), s));
+  PIA_CUDA_CHECK(cudaStreamSynchronize(s));
+  Hdr h;
+  PIA_CUDA_CHECK(cudaMemcpy(&h, t->dev.hdr, sizeof(h), cudaMemcpyDeviceToHost));
+  h.node_top = (unsigned long long)n_nodes; h.edge_top = (unsigned long long)n_edges;
+  h.n_upd = 0; h.n_updin = 0; h.n_upd_stale = 0;
+  int trees = 0;
+  for (int i = 0; i < t->cfg.vocab_capacity; ++i) trees += h_root_of[i] >= 0;
+  h.n_trees = trees;
+  PIA_CUDA_CHECK(cudaMemcpy(t->dev.hdr, &h, sizeof(h), cudaMemcpyHostToDevice));
+  return PIA_OK;
+}

@@ -243,8 +243,27 @@ def gen_zipf(seed, name, n_docs=30, n_req=12):
     r.dump(name)
 
 
+def gen_mem_file():
+    """a trie persisted by the REFERENCE's save_mem (:578-582) plus what it answers, for load_mem parity"""
+    rng = np.random.default_rng(9)
+    c = LookaheadCache(eos_ids=[2])
+    for _ in range(40):
+        c.put(rng.integers(3, 14, size=int(rng.integers(4, 40))).tolist(), branch_length=9, mode='output', idx=-1)
+    c.put(rng.integers(3, 14, size=30).tolist(), branch_length=9, mode='input', idx=0)
+    c.save_mem(os.path.join(HERE, 'trie_mem_ref.json'))
+    qs = [rng.integers(3, 14, size=2).tolist() for _ in range(25)]
+    outs = []
+    for q in qs:
+        ids, m, sizes = c.hier_get(q, decoding_length=64, branch_length=8, min_output_size=32, mode='mix', idx=0)
+        outs.append({'q': q, 'ids': list(map(int, ids)), 'mask': mask_rows(m), 'sizes': list(map(int, sizes))})
+    with open(os.path.join(HERE, 'trie_mem_ref_gets.json'), 'w') as f:
+        json.dump(outs, f)
+    print('trie_mem_ref.json', os.path.getsize(os.path.join(HERE, 'trie_mem_ref.json')) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
     gen_unit()
+    gen_mem_file()
     gen_small_vocab(1, 'trie_small_v12.json', V=12, n_req=40)
     gen_small_vocab(2, 'trie_small_v6_stop.json', V=6, n_req=30, stop_words=(3, 4), eos=(2, 5))
     gen_small_vocab(3, 'trie_small_v30_batch.json', V=30, n_req=30, with_batch=True, dl=48, bl=6)

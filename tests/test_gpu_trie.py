@@ -128,3 +128,28 @@ def test_batched_get_matches_single():
     for q, row in zip(qs[:64], rows[:64]):
         ids, m, sizes = c.hier_get(q, decoding_length=64, branch_length=8, min_output_size=32)
         assert ids == row[0] and np.array_equal(m, row[1]) and sizes == row[2]
+
+
+def test_load_mem_of_a_reference_file_and_save_roundtrip(tmp_path):
+    """load_mem reads a file written by the REFERENCE's save_mem (lookahead_cache.py:578-587) and answers like the
+    reference did; save_mem -> load_mem into a fresh cache is lossless"""
+    import json
+    import os
+    LookaheadCache = _gpu_cache_cls()
+    c = LookaheadCache(eos_ids=[2], node_capacity=1 << 20)
+    c.load_mem(os.path.join(R.GOLDEN, 'trie_mem_ref.json'))
+    gets = json.load(open(os.path.join(R.GOLDEN, 'trie_mem_ref_gets.json')))
+    for g in gets:
+        ids, m, sizes = c.hier_get(g['q'], decoding_length=64, branch_length=8, min_output_size=32, mode='mix', idx=0)
+        assert ids == g['ids'] and R.mask_rows(m) == g['mask'] and sizes == g['sizes'], g['q']
+    # the loaded forest keeps learning
+    c.put([3, 4, 5, 6, 7, 8], branch_length=9, mode='output', idx=-1)
+    path = str(tmp_path / 'mem.json')
+    c.save_mem(path)
+    d = LookaheadCache(eos_ids=[2], node_capacity=1 << 20)
+    d.load_mem(path)
+    for g in gets + [{'q': [3, 4]}]:
+        a = c.hier_get(g['q'], decoding_length=64, branch_length=8, min_output_size=32)
+        b = d.hier_get(g['q'], decoding_length=64, branch_length=8, min_output_size=32)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    assert c.stats()['n_trees'] == d.stats()['n_trees']
