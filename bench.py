@@ -410,40 +410,49 @@ def cpu_epoch2_sample(model, trie, prompt, budget_s):
     return n, secs, edls
 
 
+def cpu_threads():
+    """host threads for the CPU arms: small-row GEMMs stop scaling (and then degrade) beyond a few dozen threads"""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_plan(model, step_budget_s):
     """how much of the 256-token prompt a CPU sample may use so that one step (cold run + timed re-run) fits the budget:
-    a 16-token probe forward gives the host's speed; forwards scale ~linearly in rows at these sizes"""
+    a 16-token probe forward gives the host's speed; forwards scale ~linearly in rows at these sizes.
+    returns (S, estimated seconds per step, probe seconds)"""
     f16 = cpu_probe(model, 16)
     per_tok = f16 / 16.0
-    # one step = 2 prefills of S tokens + about 4 verify forwards of up to 64 rows (cold) + 2 (timed)
+
+    def est(S):  # cold: prefill S + 1 verify (<= 64 rows); timed: prefill S + 1-2 verify
+        return (2 * S + 3 * 64) * per_tok
+
     S = PROMPT_LEN
-    while S > 16 and (2 * S + 6 * 64) * per_tok > step_budget_s:
+    while S > 16 and est(S) > step_budget_s:
         S //= 2
-    cold_budget = max(1.0, step_budget_s - (2 * S + 2 * 64) * per_tok)
-    return S, cold_budget, f16
+    return S, est(S), f16
 
 
-SAMPLE_NOTE = ('1 request = prefill of the first {S} of the {p} prompt tokens + verify steps regenerating the g tokens that an '
-               'untimed cold run of the same request produced in {b:.0f}s (second-epoch regime of the GPU arm; bounded: a '
-               '16-token probe forward took {f:.2f}s on this host, and the prefill is not amortised over {n} tokens)')
+SAMPLE_NOTE = ('1 request = prefill of the first {S} of the {p} prompt tokens + the verify steps that regenerate the g tokens an '
+               'untimed cold run of the same request produced (cold run cut after its first verify step; second-epoch regime '
+               'of the GPU arm; bounded: a 16-token probe forward took {f:.2f}s on this host with {t} threads, and the '
+               'prefill is not amortised over {n} tokens)')
 
 
 def cpu_baseline(args, warm_outputs, prompt, total_budget_s=60.0):
     import torch
     from oracle.trie import OracleLookaheadCache
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
     t0 = time.time()
     model = build_cpu_model(args.model)
     trie = OracleLookaheadCache(eos_ids=[2])
     for w in warm_outputs:  # same warm-up text as the GPU run (benchmark.py:159-169)
         trie.put(w, branch_length=BL + 1, mode='output', idx=-1)
     build_s = time.time() - t0
-    S, cold_budget, f16 = cpu_plan(model, total_budget_s)
-    ntok, secs, edls = cpu_epoch2_sample(model, trie, prompt[:S], cold_budget)
-    return {'value': ntok / secs, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port',
+    S, est, f16 = cpu_plan(model, total_budget_s)
+    ntok, secs, edls = cpu_epoch2_sample(model, trie, prompt[:S], 0.0)
+    return {'value': ntok / secs, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
             'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host: '
-                      + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, b=cold_budget, f=f16, n=NEW_TOKENS)
+                      + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads)
                       + f'; {ntok} tokens in {secs:.1f}s over {len(edls)} forwards (model build {build_s:.0f}s untimed)',
             'mean_accepted_len_per_step': float(np.mean(edls[1:])) if len(edls) > 1 else None}
 
@@ -451,38 +460,41 @@ def cpu_baseline(args, warm_outputs, prompt, total_budget_s=60.0):
 def run_reference(args, total_budget_s=150.0):
     """--impl reference: the reference's own CPU path (restated: oracle/loop.py over the installed HF eager model +
     the C restatement of its trie) on the host cores; rank 0 only.  The whole run is time-boxed (~total_budget_s of
-    forwards + the model build) whatever --steps/--warmup are."""
+    forwards + the model build) whatever --steps/--warmup are: when a step does not fit --steps times, fewer steps are
+    executed and the sample text says how many."""
     import torch
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     from oracle.trie import OracleLookaheadCache
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
     cfg, _ = make_config(args.model)
     model = build_cpu_model(args.model)
     trie = OracleLookaheadCache(eos_ids=[2])
     allp = phrase_bank_prompts(64 + 8 * max(args.warmup, 1), cfg.vocab_size)
     K, Wm = args.steps, args.warmup
-    S, cold_budget, f16 = cpu_plan(model, total_budget_s / max(K + 0.25 * Wm, 1))
-    for i in range(Wm):  # warm-up: short cold runs (thread pools, allocator, trie)
-        cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
+    S, est, f16 = cpu_plan(model, total_budget_s / max(K, 1))
+    k_exec = max(1, min(K, int(total_budget_s / max(est, 1e-6))))
+    if est * (k_exec + Wm) <= total_budget_s * 1.2:  # warm-up only when it is affordable (the probe already warmed the pools)
+        for i in range(Wm):
+            cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
     toks, secs, edls = 0, 0.0, []
-    for i in range(K):
-        n, s_, e = cpu_epoch2_sample(model, trie, allp[i % 64][:S], cold_budget)
+    for i in range(k_exec):
+        n, s_, e = cpu_epoch2_sample(model, trie, allp[i % 64][:S], 0.0)
         toks += n
         secs += s_
         edls += e[1:]
     v = toks / secs
-    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, b=cold_budget, f=f16, n=NEW_TOKENS)
-              + f'; {args.model} bf16 on {cores} host threads; {toks} tokens in {secs:.0f}s over {K} steps')
+    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads)
+              + f'; {args.model} bf16; {k_exec} of the {K} requested steps executed: {toks} tokens in {secs:.0f}s')
     print(json.dumps({
         'impl': 'reference', 'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
-        'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': secs / K * 1e3,
+        'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': secs / k_exec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None,
         'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft', 'sample': sample},
-        'cpu_baseline': {'value': v, 'unit': 'tokens/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 

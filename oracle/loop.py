@@ -101,7 +101,7 @@ class HFBackend(object):
 def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=None, eos_token_id=(2,),
                        decoding_length=64, branch_length=8, decoding_mode='hier', max_query_length=2,
                        repetition_penalty=1.0, use_lookahead=True, stop_words=None, attention_mask=None,
-                       trace=False, time_budget_s=None, backend=None):
+                       trace=False, time_budget_s=None, backend=None, min_forwards=2):
     """restates lookahead_generation (:947-1268) for one request. input_ids: LongTensor [1, len].
     returns dict(sequences, dls, edls, fts, qts[, steps])"""
     assert input_ids.size(0) == 1
@@ -171,7 +171,7 @@ def lookahead_generate(model, trie, input_ids, max_new_tokens=None, max_length=N
             trie.stream_put(tokens, branch_length=branch_length + 1, final=False, mode='output', idx=0)   # :1203
         done = input_ids.shape[1] >= max_length or any(e in tokens for e in eos)                         # :1225-1231
         te = time.time()
-        if time_budget_s is not None and te - t_start > time_budget_s:  # bounded CPU-baseline sample (bench.py)
+        if time_budget_s is not None and te - t_start > time_budget_s and len(edls) >= min_forwards:  # bounded sample
             done = True
         fts.append(te - ts)
         ts = te

@@ -80,6 +80,7 @@ rt.seq_len.fill_(200)
 timeit('trie get (1 query, tail mode)', lambda: trie.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=rt.draft), 1)
 print('draft n =', int(rt.n))
 
+import sys; sys.exit(0) if __import__("os").environ.get("PIA_ATTN_TILES_PER_CTA") else None
 # single-request trie get on a large forest (1 M nodes), hot and cold queries
 big = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size, node_capacity=1 << 23)
 docs = bench.phrase_bank_prompts(1500, cfg.vocab_size, seed=7)
