@@ -536,7 +536,8 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int max_tiles = (cfg->max_seq + BN - 1) / BN;
-  int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : (2 * n_sm + p->n_groups - 1) / p->n_groups;
+  // one wave: the split CTAs of a head group are one thread-block cluster, so idle splits still occupy an SM each
+  int ns = cfg->kv_split_max > 0 ? cfg->kv_split_max : n_sm / p->n_groups;
   if (ns > max_tiles) ns = max_tiles;
   if (ns < 1) ns = 1;
   if (ns > MAX_SPLIT) ns = MAX_SPLIT;

@@ -228,7 +228,7 @@ def test_left_padding_eos_and_streamer():
     padded = torch.cat([torch.zeros((1, pad), dtype=torch.long, device=DEV), p], dim=1)
     am = torch.cat([torch.zeros((1, pad), dtype=torch.long, device=DEV), torch.ones_like(p)], dim=1)
     ref = lookahead_generate(hf, otrie, padded, max_new_tokens=24, eos_token_id=[2], attention_mask=am)
-    eos = ref['sequences'][0, padded.shape[1] + 6].item()  # make the 7th generated token an eos
+    eos = ref['sequences'][0, min(padded.shape[1] + 6, ref['sequences'].shape[1] - 1)].item()  # an early token as eos
 
     class Collect(object):
         def __init__(self):
