@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv
   if (i >= n) return;
   int depth = -1;
   for (int w = 0; w < mask_words; ++w) depth += __popcll(mask[(long long)i * mask_words + w]);
-  int pos = P - pad_len + depth;  // rowsum(attention_mask) - 1  (modeling_llama.py:587)
+  // rowsum(attention_mask) - 1 (modeling_llama.py:587): visible prefix keys [pad_len, P) + visible draft keys - 1
+  int pos = (P > pad_len ? P - pad_len : 0) + depth;
   if (pos < 0) pos = 0;
   if (pos >= max_pos) pos = max_pos - 1;
   const int half = hd >> 1, cpr = hd >> 3;  // 16-byte chunks per head row

@@ -41,14 +41,14 @@ constexpr int NSTAGE = 2;
 constexpr int NTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two warps per TMEM lane quadrant)
 constexpr int SUB = 128 * 128;             // bytes of one [128 rows x 64 bf16] swizzle-128B sub-tile
 constexpr int TILE_BYTES = 2 * SUB;        // one 128 x 128 bf16 operand tile
-constexpr int SMEM_Q = 0, SMEM_P = TILE_BYTES, SMEM_K = 2 * TILE_BYTES, SMEM_V = SMEM_K + NSTAGE * TILE_BYTES;
+constexpr int SMEM_Q = 0, SMEM_K = TILE_BYTES, SMEM_V = SMEM_K + NSTAGE * TILE_BYTES;  // P lives in TMEM
 constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
 constexpr int MRG_ACC = 0;                        // [n_split * RS][128] fp32 partial rows pushed by the cluster (over dead Q/P/KV tiles)
-constexpr int MRG_ML = 160 * 1024;                // [n_split * RS] (m, l) pairs
+constexpr int MRG_ML = 112 * 1024;                // [n_split * RS] (m, l) pairs
 constexpr int SMEM_XCH = SMEM_BAR + 256;           // row max / row sum exchange between the two column halves
 constexpr int SMEM_TOTAL = SMEM_XCH + 3 * 1024 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
-constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256, TM_P0 = 384, TM_P1 = 448;  // fp32 S x2, fp32 O, bf16x2-packed P x2
 constexpr int MAX_SPLIT = 8;            // KV splits per head group (merge keeps all partial rows in flight)
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -88,6 +88,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
       : "memory");
 }
+// A operand from TMEM (P, bf16 pairs packed in 32-bit columns, lane == row), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t addr, const uint32_t *v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -172,8 +193,9 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
 
   const uint32_t bar0 = base + SMEM_BAR;
   const uint32_t bar_kv_full = bar0, bar_kv_empty = bar0 + 8 * NSTAGE, bar_s_full = bar0 + 16 * NSTAGE,
-                 bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 8, bar_q_full = bar_o_full + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 48);
+                 bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 16, bar_q_full = bar_o_full + 8,
+                 bar_o_free = bar_q_full + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 64);
 
   pdl_launch_dependents();
   pdl_wait();  // the split decision below already reads device state written by the step's earlier kernels
@@ -211,7 +233,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
     mbar_init(bar_s_full, 1); mbar_init(bar_s_full + 8, 1);
-    mbar_init(bar_p_full, 2 * rows_used);
+    mbar_init(bar_p_full, 2 * rows_used); mbar_init(bar_p_full + 8, 2 * rows_used);
+    mbar_init(bar_o_free, 2 * rows_used);
     mbar_init(bar_o_full, 1);
     mbar_init(bar_q_full, 2 * rows_used);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -268,14 +291,16 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       for (int i = 0; i < ntile; ++i) {
         if (i + 1 < ntile) issue_qk(i + 1);  // S is double buffered: next QK^T overlaps this tile's softmax
         const int s = i % NSTAGE;
-        mbar_wait(bar_p_full, i & 1);
+        mbar_wait(bar_p_full + 8 * (i & 1), (i >> 1) & 1);
+        if (i > 0) mbar_wait(bar_o_free, (i - 1) & 1);  // the softmax warps have folded O(i-1) into their registers
         tc_fence_after();
-        const uint32_t pa = base + SMEM_P, va = base + SMEM_V + s * TILE_BYTES;
+        const uint32_t va = base + SMEM_V + s * TILE_BYTES;
+        const uint32_t pa = tmem + ((i & 1) ? TM_P1 : TM_P0);
 #pragma unroll
         for (int j = 0; j < BN / 16; ++j) {
-          // A = P, K-major over keys; B = V, MN-major: 16 keys = 2 groups of 8 rows (SBO 1024 B), d-halves 16 KB apart (LBO)
-          const uint32_t aoff = (j >> 2) * SUB + (j & 3) * 32;
-          umma_bf16(tmem + TM_O, make_desc(pa + aoff, 16, 1024), make_desc(va + j * 2048, SUB, 1024), IDESC_PV, j > 0);
+          // A = P from TMEM (16 keys = 8 packed columns per k-block); B = V, MN-major: 16 keys = 2 groups of 8 rows
+          // (SBO 1024 B), d-halves 16 KB apart (LBO)
+          umma_bf16_ts(tmem + TM_O, pa + j * 8, make_desc(va + j * 2048, SUB, 1024), IDESC_PV, j > 0);
         }
         umma_commit(bar_o_full);
         umma_commit(bar_kv_empty + 8 * s);
@@ -310,7 +335,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     float acc[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     uint32_t sv[64];
     for (int i = 0; i < ntile; ++i) {
       const int key0 = (t0 + i) * BN + half * 64;
@@ -358,40 +383,54 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       const float m_new = fmaxf(m_run, m_tile * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_use);
-      // p = exp2(s*scale - m) -> bf16 -> shared memory (this half = one 64-key sub-tile of P), row sum
+      // p = exp2(s*scale - m) -> bf16 pairs -> TMEM (A operand of the PV MMA: lane = row, one 32-bit column per key
+      // pair; this half owns columns [32*half, 32*half+32)), row sum
       float l_tile = 0.f;
+      uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 x 16 B chunks = 64 keys
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = c * 8 + e * 2;
-          const uint32_t vm = j < 32 ? vm0 : vm1;
-          const float p0 = (vm >> (j & 31)) & 1u ? ex2(__uint_as_float(sv[j]) * p.scale_log2 - m_use) : 0.f;
-          const float p1 = (vm >> ((j + 1) & 31)) & 1u ? ex2(__uint_as_float(sv[j + 1]) * p.scale_log2 - m_use) : 0.f;
-          const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-          // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
-          l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
-          pk[e] = *reinterpret_cast<const uint32_t *>(&b);
-        }
-        *reinterpret_cast<uint4 *>(sm + SMEM_P + half * SUB + row * 128 + ((c ^ (row & 7)) << 4)) =
-            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int e = 0; e < 32; ++e) {
+        const int j = 2 * e;
+        const uint32_t vm = j < 32 ? vm0 : vm1;
+        const float p0 = (vm >> (j & 31)) & 1u ? ex2(__uint_as_float(sv[j]) * p.scale_log2 - m_use) : 0.f;
+        const float p1 = (vm >> ((j + 1) & 31)) & 1u ? ex2(__uint_as_float(sv[j + 1]) * p.scale_log2 - m_use) : 0.f;
+        const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+        // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
+        l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
+        pk[e] = *reinterpret_cast<const uint32_t *>(&b);
       }
+      // P buffer (i & 1) is free: PV(i-2) completed before o_full(i-2), which this thread observed in iteration i-1
+      tmem_st32(tmem + lane_addr + ((i & 1) ? TM_P1 : TM_P0) + half * 32, pk);
+      tmem_st_wait();
       l_run = l_run * alpha + l_tile;
       m_run = m_new;
-      fence_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
-      tc_fence_before();    // order our tcgen05.ld of S before the issuer's next MMA into this S buffer
-      mbar_arrive(bar_p_full);
+      tc_fence_before();    // orders the tcgen05.ld of S and the tcgen05.st of P before the issuer's next MMAs
+      mbar_arrive(bar_p_full + 8 * (i & 1));
       if (row == 0 && half == 0 && i == 0) DBG(7);
-      // accumulate this tile's PV (this half's 64 head-dim columns)
-      mbar_wait(bar_o_full, i & 1);
+      // fold the PREVIOUS tile's PV into the register accumulator (this half's 64 head-dim columns) while the tensor
+      // core works on PV(i) / QK(i+1): O(i-1) was computed against m_{i-1}, so the older sum is rescaled by
+      // alpha_{i-1} = 2^(m_{i-2} - m_{i-1})
+      if (i > 0) {
+        mbar_wait(bar_o_full, (i - 1) & 1);
+        tc_fence_after();
+        tmem_ld32(tmem + lane_addr + TM_O + half * 64, sv);
+        tmem_ld32(tmem + lane_addr + TM_O + half * 64 + 32, sv + 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_o_free);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = acc[j] * alpha_prev + __uint_as_float(sv[j]);
+      }
+      alpha_prev = alpha;
+    }
+    if (ntile > 0) {
+      mbar_wait(bar_o_full, (ntile - 1) & 1);
       tc_fence_after();
-      if (row == 0 && half == 0 && i == 0) DBG(8);
+      if (row == 0 && half == 0) DBG(8);
       tmem_ld32(tmem + lane_addr + TM_O + half * 64, sv);
       tmem_ld32(tmem + lane_addr + TM_O + half * 64 + 32, sv + 32);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 64; ++j) acc[j] = acc[j] * alpha + __uint_as_float(sv[j]);
+      for (int j = 0; j < 64; ++j) acc[j] = acc[j] * alpha_prev + __uint_as_float(sv[j]);
       tc_fence_before();
     }
     if (row == 0 && half == 0) DBG(9);
