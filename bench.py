@@ -392,22 +392,23 @@ def cpu_probe(model, n_tok=16):
 
 def cpu_sample(model, trie, prompt, budget_s, max_new=NEW_TOKENS):
     """one request through the oracle loop (oracle/loop.py = the reference's CPU path restated), cut off at the first
-    step boundary after `budget_s` seconds; returns (new tokens, seconds, edls)"""
+    step boundary after `budget_s` seconds (never before its first verify step); returns (new tokens, seconds, edls,
+    per-forward seconds)"""
     import torch
     from oracle.loop import lookahead_generate
     t0 = time.time()
     r = lookahead_generate(model, trie, torch.tensor([prompt]), max_new_tokens=max_new, eos_token_id=[2],
                            decoding_length=DL, branch_length=BL, time_budget_s=budget_s)
-    return r['sequences'].shape[1] - len(prompt), time.time() - t0, r['edls']
+    return r['sequences'].shape[1] - len(prompt), time.time() - t0, r['edls'], r['fts']
 
 
-def cpu_epoch2_sample(model, trie, prompt, budget_s):
+def cpu_epoch2_sample(model, trie, prompt, step_budget_s):
     """the bench's regime (second epoch: the trie has seen this prompt's answer once) as a bounded CPU sample:
-    an UNTIMED cold run of the request for `budget_s` seconds produces g tokens, then the TIMED run regenerates exactly
-    those g tokens (prefill + verify steps that now draft from the trie)."""
-    g, _, _ = cpu_sample(model, trie, prompt, budget_s)
-    n, secs, edls = cpu_sample(model, trie, prompt, None, max_new=max(g, 1))
-    return n, secs, edls
+    an UNTIMED cold run of the request, cut at the first step boundary after 35 % of the step budget, produces g
+    tokens; the TIMED run then regenerates those g tokens (prefill + verify steps that now draft from the trie), itself
+    cut at the first step boundary after 50 % of the budget."""
+    g, _, _, _ = cpu_sample(model, trie, prompt, 0.35 * step_budget_s)
+    return cpu_sample(model, trie, prompt, 0.5 * step_budget_s, max_new=max(g, 1))
 
 
 def cpu_threads():
@@ -416,28 +417,41 @@ def cpu_threads():
 
 
 def cpu_plan(model, step_budget_s):
-    """how much of the 256-token prompt a CPU sample may use so that one step (cold run + timed re-run) fits the budget:
-    a 16-token probe forward gives the host's speed; forwards scale ~linearly in rows at these sizes.
-    returns (S, estimated seconds per step, probe seconds)"""
+    """how much of the 256-token prompt a CPU sample may use: a 16-token probe forward gives the host's speed
+    (forwards scale ~linearly in rows at these sizes); the prefill may take at most 15 % of a step's budget.
+    returns (S, probe seconds)"""
     f16 = cpu_probe(model, 16)
     per_tok = f16 / 16.0
-
-    def est(S):  # cold: prefill S + 1 verify (<= 64 rows); timed: prefill S + 1-2 verify
-        return (2 * S + 3 * 64) * per_tok
-
     S = PROMPT_LEN
-    while S > 16 and est(S) > step_budget_s:
+    while S > 16 and S * per_tok > 0.15 * step_budget_s:
         S //= 2
-    return S, est(S), f16
+    return S, f16
+
+
+def cpu_summary(S, samples):
+    """tokens/s of the bounded samples + what the same per-forward times give for a full 256 -> 256 request (prefill
+    scaled to the full prompt, verify-step time and accepted length as measured)"""
+    toks = sum(n for n, _, _, _ in samples)
+    secs = sum(s_ for _, s_, _, _ in samples)
+    edls = [e for _, _, ed, _ in samples for e in ed[1:]]
+    pre = float(np.mean([ft[0] for _, _, _, ft in samples]))
+    ver = [t for _, _, _, ft in samples for t in ft[1:]]
+    full = None
+    if edls and ver:
+        edl, step = float(np.mean(edls)), float(np.mean(ver))
+        full = NEW_TOKENS / (pre * PROMPT_LEN / S + NEW_TOKENS / edl * step)
+    return toks, secs, edls, {'prefill_s': pre, 'verify_step_s': float(np.mean(ver)) if ver else None,
+                              'full_request_tokens_per_s_extrapolated': full}
 
 
 SAMPLE_NOTE = ('1 request = prefill of the first {S} of the {p} prompt tokens + the verify steps that regenerate the g tokens an '
-               'untimed cold run of the same request produced (cold run cut after its first verify step; second-epoch regime '
-               'of the GPU arm; bounded: a 16-token probe forward took {f:.2f}s on this host with {t} threads, and the '
-               'prefill is not amortised over {n} tokens)')
+               'untimed cold run of the same request produced (cold run cut at the first step boundary after 35 % of the '
+               "step's {b:.0f}s budget, timed run after 50 %; second-epoch regime of the GPU arm; a 16-token probe forward "
+               'took {f:.2f}s on this host with {t} threads; the prefill is amortised over g, not {n}, tokens - see '
+               'full_request_tokens_per_s_extrapolated)')
 
 
-def cpu_baseline(args, warm_outputs, prompt, total_budget_s=60.0):
+def cpu_baseline(args, warm_outputs, prompt, total_budget_s=45.0):
     import torch
     from oracle.trie import OracleLookaheadCache
     threads = cpu_threads()
@@ -448,20 +462,23 @@ def cpu_baseline(args, warm_outputs, prompt, total_budget_s=60.0):
     for w in warm_outputs:  # same warm-up text as the GPU run (benchmark.py:159-169)
         trie.put(w, branch_length=BL + 1, mode='output', idx=-1)
     build_s = time.time() - t0
-    S, est, f16 = cpu_plan(model, total_budget_s)
-    ntok, secs, edls = cpu_epoch2_sample(model, trie, prompt[:S], 0.0)
-    return {'value': ntok / secs, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
-            'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host: '
-                      + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads)
-                      + f'; {ntok} tokens in {secs:.1f}s over {len(edls)} forwards (model build {build_s:.0f}s untimed)',
-            'mean_accepted_len_per_step': float(np.mean(edls[1:])) if len(edls) > 1 else None}
+    S, f16 = cpu_plan(model, total_budget_s)
+    smp = cpu_epoch2_sample(model, trie, prompt[:S], total_budget_s)
+    ntok, secs, edls, extra = cpu_summary(S, [smp])
+    out = {'value': ntok / secs, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
+           'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host: '
+                     + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads, b=total_budget_s)
+                     + f'; {ntok} tokens in {secs:.1f}s over {len(smp[2])} forwards (model build {build_s:.0f}s untimed)',
+           'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None}
+    out.update(extra)
+    return out
 
 
 def run_reference(args, total_budget_s=150.0):
     """--impl reference: the reference's own CPU path (restated: oracle/loop.py over the installed HF eager model +
     the C restatement of its trie) on the host cores; rank 0 only.  The whole run is time-boxed (~total_budget_s of
-    forwards + the model build) whatever --steps/--warmup are: when a step does not fit --steps times, fewer steps are
-    executed and the sample text says how many."""
+    forwards + the model build) whatever --steps/--warmup are: every step gets total_budget_s / steps seconds, and when
+    the host is too slow for that, fewer steps are executed and the sample text says how many."""
     import torch
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -474,27 +491,35 @@ def run_reference(args, total_budget_s=150.0):
     trie = OracleLookaheadCache(eos_ids=[2])
     allp = phrase_bank_prompts(64 + 8 * max(args.warmup, 1), cfg.vocab_size)
     K, Wm = args.steps, args.warmup
-    S, est, f16 = cpu_plan(model, total_budget_s / max(K, 1))
-    k_exec = max(1, min(K, int(total_budget_s / max(est, 1e-6))))
-    if est * (k_exec + Wm) <= total_budget_s * 1.2:  # warm-up only when it is affordable (the probe already warmed the pools)
-        for i in range(Wm):
-            cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
-    toks, secs, edls = 0, 0.0, []
-    for i in range(k_exec):
-        n, s_, e = cpu_epoch2_sample(model, trie, allp[i % 64][:S], 0.0)
-        toks += n
-        secs += s_
-        edls += e[1:]
+    B = total_budget_s / max(K, 1)
+    S, f16 = cpu_plan(model, B)
+    t_start = time.time()
+    for i in range(Wm):  # warm-up: one prefill + one verify step each, only while it stays cheap
+        if time.time() - t_start > 0.1 * total_budget_s:
+            break
+        cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
+    t_start = time.time()
+    samples, last = [], 0.0
+    for i in range(K):
+        if samples and time.time() - t_start + last > total_budget_s:
+            break
+        t0 = time.time()
+        samples.append(cpu_epoch2_sample(model, trie, allp[i % 64][:S], B))
+        last = time.time() - t0
+    toks, secs, edls, extra = cpu_summary(S, samples)
     v = toks / secs
-    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads)
-              + f'; {args.model} bf16; {k_exec} of the {K} requested steps executed: {toks} tokens in {secs:.0f}s')
+    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads, b=B)
+              + f'; {args.model} bf16; {len(samples)} of the {K} requested steps executed: {toks} tokens in {secs:.0f}s')
+    cpu = {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample}
+    cpu.update(extra)
     print(json.dumps({
         'impl': 'reference', 'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
-        'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm, 'ms_per_step': secs / k_exec * 1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm,
+        'ms_per_step': secs / len(samples) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
         'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None,
         'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft', 'sample': sample},
-        'cpu_baseline': {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': cpu,
         'e2e': {'value': v, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 

@@ -209,7 +209,7 @@ int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t part_strid
                          const void *d_weight, float eps, int rows, int hidden, void *d_residual_out, void *d_y,
                          void *stream);
 /* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; position of node i =
- * P - pad_len + depth_i = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection
+ * max(P - pad_len, 0) + depth_i = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection
  * output).  d_cos / d_sin : [max_pos, D/2] bf16 tables (cos/sin already rounded to the model dtype exactly as
  * LlamaRotaryEmbedding.forward :111-127 returns them).  Writes q (rotated) to d_q_out [rows, Hq, D] and
  * K (rotated) / V to cache rows P + i of the layer's [Hkv, max_seq, D] planes. */
@@ -222,6 +222,14 @@ int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *
 /* embedding gather for the draft nodes: d_out[i] = table[d_ids[i]] (rows >= *d_n are zero filled) */
 int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden, void *d_out,
                      void *stream);
+/* L2 prefetch of immutable weights (no reference counterpart: the reference's eager loop leaves HBM idle while the
+ * small kernels of a layer - RoPE, attention, norms - run; modeling_llama.py:272-292 sits between the qkv and the o
+ * projection).  Issues cp.async.bulk.prefetch.L2 for n_ranges ranges of range_bytes (multiple of 16) that start
+ * stride_bytes apart at d_base, chunk-interleaved across the ranges (every range gets its first bytes first), paced
+ * to gbytes_per_s (0 = as fast as the grid - one warp per SM - issues).  A hint only: no result, nothing to wait for; meant for a side
+ * stream / parallel graph branch next to the kernels whose HBM idle time it fills. */
+int pia_l2_prefetch(const void *d_base, int64_t n_ranges, int64_t stride_bytes, int64_t range_bytes, float gbytes_per_s,
+                    void *stream);
 
 /* ============================================================================================
  * Accept + KV compaction + sequence update

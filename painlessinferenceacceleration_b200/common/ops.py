@@ -67,6 +67,7 @@ class Gemm(object):
         self.splits = self.lib.pia_gemm_plan_splits(self.h)
         self.N = N
         self._keep = (weight, x)
+        self.weight = weight
         if self.splits == 1:
             self.out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=weight.device)
         else:
@@ -101,6 +102,14 @@ def rope_kv_append(qkv, mask, n, prefix_len, pad_len, n_q_heads, n_kv_heads, hea
 def silu_mul(gate_up, out):
     rows, two_inter = gate_up.shape
     L.check(L.load().pia_silu_mul(_p(gate_up), rows, two_inter // 2, _p(out), _s()))
+
+
+def l2_prefetch(t, n_ranges=1, stride_bytes=0, range_bytes=None, gbytes_per_s=0.0, offset_bytes=0):
+    """hint: pull (part of) an immutable weight tensor into L2 on the current stream (pia_l2_prefetch)"""
+    if range_bytes is None:
+        range_bytes = t.numel() * t.element_size() - offset_bytes
+    L.check(L.load().pia_l2_prefetch(t.data_ptr() + offset_bytes, int(n_ranges), int(stride_bytes), int(range_bytes),
+                                     float(gbytes_per_s), _s()))
 
 
 def embed_gather(table, ids, n, out):

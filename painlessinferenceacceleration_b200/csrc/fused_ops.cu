@@ -228,6 +228,53 @@ extern "C" int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_
   return PIA_OK;
 }
 
+// One warp per SM walks the ranges chunk by chunk (the bulk-prefetch issue rate of a single SM's TMA unit is only a
+// few hundred GB/s, so the chunks are dealt round-robin over the whole grid); bytes_per_ns paces the grid against
+// %globaltimer so that the demand loads of the kernels running beside it (attention's KV tiles) are not queued behind
+// tens of MB of prefetch.  No shared memory, 32 threads: fits next to any resident CTA.
+__global__ void __launch_bounds__(32) k_l2_prefetch(const char *base, long long n_ranges, long long stride,
+                                                     long long range_bytes, int chunk, float bytes_per_ns) {
+  const long long cpr = (range_bytes + chunk - 1) / chunk;
+  const long long total = cpr * n_ranges;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (long long c = (long long)threadIdx.x * gridDim.x + blockIdx.x; c < total; c += (long long)blockDim.x * gridDim.x) {
+    const long long k = c / n_ranges, r = c % n_ranges;
+    const long long off = k * chunk;
+    const long long left = range_bytes - off;
+    const unsigned sz = (unsigned)(left < chunk ? left : chunk);
+    if (bytes_per_ns > 0.f) {
+      const unsigned long long due = t0 + (unsigned long long)((float)(c * chunk) / bytes_per_ns);
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      while (now < due) {
+        __nanosleep(64);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      }
+    }
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + r * stride + off), "r"(sz) : "memory");
+  }
+}
+
+extern "C" int pia_l2_prefetch(const void *d_base, int64_t n_ranges, int64_t stride_bytes, int64_t range_bytes,
+                               float gbytes_per_s, void *stream) {
+  PIA_REQUIRE(d_base && n_ranges > 0 && range_bytes > 0 && range_bytes % 16 == 0 && ((uintptr_t)d_base & 15) == 0 &&
+                  (n_ranges == 1 || (stride_bytes >= range_bytes && stride_bytes % 16 == 0)) && gbytes_per_s >= 0.f,
+              "bad prefetch arguments");
+  const int chunk = range_bytes < 16384 ? (int)range_bytes : 16384;
+  // plain launch (no programmatic dependency): the kernel reads nothing its predecessors write
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    PIA_CUDA_CHECK(cudaGetDevice(&dev));
+    PIA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  k_l2_prefetch<<<n_sm, 32, 0, (cudaStream_t)stream>>>((const char *)d_base, (long long)n_ranges, (long long)stride_bytes,
+                                                     (long long)range_bytes, chunk, gbytes_per_s);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
 extern "C" int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden,
                                 void *d_out, void *stream) {
   PIA_REQUIRE(d_table && d_ids && d_n && d_out && rows > 0 && hidden % 8 == 0, "bad embed arguments");

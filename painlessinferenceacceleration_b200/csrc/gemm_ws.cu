@@ -143,18 +143,30 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  pdl_wait();  // barriers + TMEM are set up while the previous kernel drains; global memory only from here on
+  // Barriers + TMEM are set up while the previous kernel drains, and - the weights being immutable - the first
+  // NSTAGE weight tiles are already streaming from HBM before griddepcontrol.wait: only the activation tiles (and
+  // the output stores) depend on the predecessor, so its run time hides this kernel's pipeline fill.
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nch; ++i) {
+      auto load_w = [&](int i, int s) {
+        const uint32_t wd = base + s * STAGE_BYTES;
+        if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, blockIdx.x * p.n_chunks + c0 + i);
+        else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
+      };
+      const int pre = nch < NSTAGE ? nch : NSTAGE;
+      for (int i = 0; i < pre; ++i) {  // all stages start empty
+        mbar_expect_tx(bar_full + 8 * i, STAGE_BYTES);
+        load_w(i, i);
+      }
+      pdl_wait();
+      for (int i = 0; i < pre; ++i) tma_load_2d(base + i * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * i, (c0 + i) * BK, 0);
+      for (int i = pre; i < nch; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-        const uint32_t wd = base + s * STAGE_BYTES, xd = wd + W_BYTES;
-        if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, blockIdx.x * p.n_chunks + c0 + i);
-        else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
-        tma_load_2d(xd, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
+        load_w(i, s);
+        tma_load_2d(base + s * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
       }
     }
   } else if (warp == 1) {
@@ -173,6 +185,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     }
   } else {
     // epilogue: thread = one weight row n (TMEM lane), 64 token values in registers
+    pdl_wait();  // output stores (and the WAR hazard on the output buffer) are ordered after the predecessor
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
     uint32_t v[64];

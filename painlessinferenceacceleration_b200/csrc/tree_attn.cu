@@ -46,7 +46,11 @@ constexpr int SMEM_BAR = SMEM_V + NSTAGE * TILE_BYTES;
 constexpr int MRG_ACC = 0;                        // [n_split * RS][128] fp32 partial rows pushed by the cluster (over dead Q/P/KV tiles)
 constexpr int MRG_ML = 112 * 1024;                // [n_split * RS] (m, l) pairs
 constexpr int SMEM_XCH = SMEM_BAR + 256;           // row max / row sum exchange between the two column halves
-constexpr int SMEM_TOTAL = SMEM_XCH + 3 * 1024 + 1024;  // + alignment slack
+// merge buffers that never alias a live tile (used when the CTA's rows fit: <= 64 rows): peers may push their
+// partial rows as soon as they are done, without first waiting for this CTA to leave its tile loop
+constexpr int MRG_DED_ACC = SMEM_XCH + 3 * 1024, MRG_DED_ACC_BYTES = (64 + 8) * 128 * 4,  // ns * ceil(64 / ns) <= 64 + MAX_SPLIT - 1 rows
+               MRG_DED_ML = MRG_DED_ACC + MRG_DED_ACC_BYTES;
+constexpr int SMEM_TOTAL = MRG_DED_ML + 1024 + 1024;  // + alignment slack
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256, TM_P0 = 384, TM_P1 = 448;  // fp32 S x2, fp32 O, bf16x2-packed P x2
 constexpr int MAX_SPLIT = 8;            // KV splits per head group (merge keeps all partial rows in flight)
@@ -135,6 +139,8 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
@@ -207,6 +213,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const int tiles_total = (L + BN - 1) / BN;
   // Work split decided on the device from the live length: tiles_per_cta tiles per CTA (more only when the
   // plan's split limit is reached); a single split writes the final output directly (no partials, no merge).
+  const int rows_used = p.heads_per_cta * p.np;          // 64 (MHA, 64 nodes) or 128
+  const bool ded = (rows_used + MAX_SPLIT) * HD * 4 <= MRG_DED_ACC_BYTES;
   int ns = (tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   if (ns > p.n_split) ns = p.n_split;
   if (ns < 1) ns = 1;
@@ -219,8 +227,13 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   int t1 = t0 + tps;
   if (t1 > tiles_total) t1 = tiles_total;
   const int ntile = t1 - t0;  // >= 1 for split < ns except possibly the last one
-
-  const int rows_used = p.heads_per_cta * p.np;          // 64 (MHA, 64 nodes) or 128
+  // cluster barrier A ("every CTA of the cluster is running and its merge buffers may be written"): with dedicated
+  // merge buffers the arrive happens right here and the wait just before the push (it has long completed by then);
+  // with aliased buffers (128-row tiles) A is a full barrier after the tile loop
+  if (ns > 1 && ded) cluster_arrive();
+  auto barrier_a = [&]() { if (ded) cluster_wait(); else cluster_sync_all(); };
+  const int mrg_acc = ded ? MRG_DED_ACC : MRG_ACC, mrg_ml = ded ? MRG_DED_ML : MRG_ML;
+  const int mrg_stride = ded ? 64 + MAX_SPLIT : 128 + MAX_SPLIT;  // slots per chunk column
   const bool is_sm_warp = warp >= 2;
   const int half = is_sm_warp ? (warp - 2) >> 2 : 0;     // which 64 columns of S / O this softmax warp owns
   const int row = ((warp & 3) << 5) | lane;              // TMEM lane == row (a warp may only touch its quadrant)
@@ -267,7 +280,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       }
     }
     __syncwarp();
-    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }
+    if (ns > 1) { barrier_a(); cluster_sync_all(); }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one thread)
     if (lane == 0 && ntile > 0) {
@@ -308,7 +321,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       DBG(4);
     }
     __syncwarp();
-    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }
+    if (ns > 1) { barrier_a(); cluster_sync_all(); }
   } else if (warp_active) {
     // ================================================================ softmax + accumulate
     // two threads per row: `half` selects 64 of the 128 S columns (keys) and 64 of the 128 O columns (head dim)
@@ -369,12 +382,16 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         return m;
       };
       const uint32_t vm0 = vis32(key0), vm1 = vis32(key0 + 32);
+      if ((vm0 & vm1) != 0xffffffffu) {  // tree / padded / ragged tile: hidden keys -> -inf once, then the dense code
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (!((vm0 >> j) & 1u)) sv[j] = 0xff800000u;
+          if (!((vm1 >> j) & 1u)) sv[32 + j] = 0xff800000u;
+        }
+      }
       float m_half = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if ((vm0 >> j) & 1u) m_half = fmaxf(m_half, __uint_as_float(sv[j]));
-        if ((vm1 >> j) & 1u) m_half = fmaxf(m_half, __uint_as_float(sv[32 + j]));
-      }
+      for (int j = 0; j < 64; ++j) m_half = fmaxf(m_half, __uint_as_float(sv[j]));
       // row max across the two halves (double-buffered exchange slot, one named barrier per quadrant pair)
       float *xm = reinterpret_cast<float *>(sm + SMEM_XCH) + (i & 1) * 256;
       xm[half * 128 + row] = m_half;
@@ -388,11 +405,9 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       float l_tile = 0.f;
       uint32_t pk[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int j = 2 * e;
-        const uint32_t vm = j < 32 ? vm0 : vm1;
-        const float p0 = (vm >> (j & 31)) & 1u ? ex2(__uint_as_float(sv[j]) * p.scale_log2 - m_use) : 0.f;
-        const float p1 = (vm >> ((j + 1) & 31)) & 1u ? ex2(__uint_as_float(sv[j + 1]) * p.scale_log2 - m_use) : 0.f;
+      for (int e = 0; e < 32; ++e) {  // ex2(-inf) = 0 for the hidden keys (m_use is finite)
+        const float p0 = ex2(__uint_as_float(sv[2 * e]) * p.scale_log2 - m_use);
+        const float p1 = ex2(__uint_as_float(sv[2 * e + 1]) * p.scale_log2 - m_use);
         const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
         // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
         l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
@@ -461,37 +476,32 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       // tile loop (barrier A: the Q/P/KV tiles of every CTA are dead) each thread pushes its row half - acc, and the
       // row's (m, l) - straight into the shared memory of the CTA that owns that row's slice (DSMEM), barrier B,
       // and every CTA combines its slice locally: no workspace round trip through L2, no serial last-arriver merge.
-      cluster_sync_all();
+      barrier_a();
       const int RS = (rows_used + ns - 1) / ns;       // rows per owner CTA
       const int owner = row / RS, rl = row % RS;
       if (row_live) {
-        const uint32_t slot = base + MRG_ACC + (uint32_t)((split * RS + rl) * HD + half * 64) * 4;
-        const uint32_t dst = map_to_cta(slot, owner);
+        // partial rows are stored chunk-major ([32 float4 chunks][slot]) so that the lanes of a warp (= consecutive
+        // rows) write consecutive 16-byte words of the owner's buffer with every store instruction
+        const uint32_t dst = map_to_cta(base + mrg_acc + (uint32_t)((half * 16) * mrg_stride + split * RS + rl) * 16, owner);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) st_cluster_f4(dst + j * 16, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        if (half == 0) st_cluster_f2(map_to_cta(base + MRG_ML + (uint32_t)(split * RS + rl) * 8, owner), m_run, l_run);
+        for (int j = 0; j < 16; ++j)
+          st_cluster_f4(dst + (uint32_t)(j * mrg_stride) * 16, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        if (half == 0) st_cluster_f2(map_to_cta(base + mrg_ml + (uint32_t)(split * RS + rl) * 8, owner), m_run, l_run);
       }
       cluster_sync_all();
     }
     if (row == 0 && half == 0) DBG(10);
   } else {
-    if (ns > 1) { cluster_sync_all(); cluster_sync_all(); }  // idle softmax warps (rows 64..127 of an MHA tile)
-  }
-  tc_fence_before();
-  __threadfence();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+    if (ns > 1) { barrier_a(); cluster_sync_all(); }  // idle softmax warps (rows 64..127 of an MHA tile)
   }
   if (ns > 1) {
     // combine this CTA's row slice: out[r][:] = sum_i acc_i 2^(m_i - M) / sum_i l_i 2^(m_i - M), all operands local
     const int RS = (rows_used + ns - 1) / ns;
-    const float *macc = reinterpret_cast<const float *>(sm + MRG_ACC);
-    const float2 *mml = reinterpret_cast<const float2 *>(sm + MRG_ML);
+    const float4 *macc = reinterpret_cast<const float4 *>(sm + mrg_acc);
+    const float2 *mml = reinterpret_cast<const float2 *>(sm + mrg_ml);
     const int items = RS * (HD / 4);
     for (int it = tid; it < items; it += NTHREADS) {
-      const int rl = it / (HD / 4), c4 = it % (HD / 4);
+      const int rl = it % RS, c4 = it / RS;
       const int r = split * RS + rl;
       if (r >= rows_used) continue;
       const int rh = r / p.np, rn = r % p.np;
@@ -505,7 +515,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         if (ml.x == -INFINITY) continue;
         const float w = ex2(ml.x - M);
         den += ml.y * w;
-        const float4 a4 = reinterpret_cast<const float4 *>(macc + (size_t)(i * RS + rl) * HD)[c4];
+        const float4 a4 = macc[c4 * mrg_stride + i * RS + rl];
         o4.x += a4.x * w; o4.y += a4.y * w; o4.z += a4.z * w; o4.w += a4.w * w;
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
@@ -513,6 +523,13 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       reinterpret_cast<uint2 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[c4] =
           make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
     }
+  }
+  // every tcgen05 access of this CTA is complete (the softmax warps observed the last o_full): release TMEM
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
   }
   if (tid == 0) DBG(11);
 }

@@ -193,7 +193,18 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         us per launch incl. the consumer kernel): gate_up 35.5 vs cuBLAS 38.6 (both + k_silu_mul; the fused SiLU
         epilogue costs 38.3), lm_head 42.3 vs 46.6.  qkv (96 weight tiles: 22.1 vs 20.3), o (32 tiles: 10.3 vs 9.8) and
         down (split-K 4 + rmsnorm over partials 23.3 vs 22.6) stay on cuBLAS."""
-        return {'gate_up': self._mk_gemm(layer.mlp.gate_up_weight, b.y)}
+        import os
+        want = os.environ.get('PIA_GEMM_SET', 'gate_up').split(',')
+        plans = {}
+        if 'gate_up' in want:
+            plans['gate_up'] = self._mk_gemm(layer.mlp.gate_up_weight, b.y)
+        if 'qkv' in want:
+            plans['qkv'] = self._mk_gemm(layer.self_attn.qkv_weight, b.y)
+        if 'o' in want:      # fp32 split-K slices, summed by the following rmsnorm
+            plans['o'] = self._mk_gemm(layer.self_attn.o_proj.weight.data, b.attn, split_k=4)
+        if 'down' in want:
+            plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=4)
+        return plans
 
     @staticmethod
     def _mk_gemm(w, x, split_k=1):
@@ -202,14 +213,57 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             return ops.Gemm(ops.tile_weight(w), x, split_k=split_k, tiled=True)
         return ops.Gemm(w.contiguous(), x, split_k=split_k)
 
+    # ------------------------------------------------------------------ weight prefetch beside the small kernels
+    def _prefetch_cfg(self, rt):
+        """PIA_PREFETCH="o_frac,gate_up_frac,down_frac,gbytes_per_s" (0 disables): which share of the next
+        projections' weights is pulled into L2 on a side stream while RoPE + tree attention (o, gate_up) and
+        SiLU*up (down) keep HBM idle; the step is weight-streaming bound, so HBM time hidden here comes straight
+        off the step.  Decode steps only."""
+        cfg = getattr(rt, 'prefetch_cfg', None)
+        if cfg is None:
+            import os
+            spec = os.environ.get('PIA_PREFETCH', '0')
+            v = [float(t) for t in spec.split(',')] if spec not in ('', '0') else []
+            cfg = False
+            if v and torch.cuda.is_available():
+                v = (v + [0.0] * 4)[:4]
+                cfg = dict(o=v[0], gate_up=v[1], down=v[2], rate=v[3], side=torch.cuda.Stream(device=self.device))
+            rt.prefetch_cfg = cfg
+        return cfg
+
+    @staticmethod
+    def _prefetch(pf, jobs):
+        """fork: the side stream picks up after the kernels launched so far and issues the prefetch jobs"""
+        main = torch.cuda.current_stream()
+        pf['side'].wait_stream(main)
+        with torch.cuda.stream(pf['side']):
+            for (t, frac, tile_bytes) in jobs:
+                if frac <= 0:
+                    continue
+                total = t.numel() * t.element_size()
+                if tile_bytes:   # HBM-tiled weight: the first share of every tile (= its first k chunks)
+                    rb = max(16384, int(tile_bytes * min(frac, 1.0)) // 16384 * 16384)
+                    ops.l2_prefetch(t, n_ranges=total // tile_bytes, stride_bytes=tile_bytes, range_bytes=min(rb, tile_bytes),
+                                    gbytes_per_s=pf['rate'])
+                else:
+                    ops.l2_prefetch(t, range_bytes=int(total * min(frac, 1.0)) // 16 * 16, gbytes_per_s=pf['rate'])
+        pf['dirty'] = True
+
     # ------------------------------------------------------------------ the verify forward on static buffers
-    def _mlp(self, rt, layer, y, plans=None):
+    def _mlp(self, rt, layer, y, plans=None, pf=None):
         """returns (x, parts): the MLP output as a bf16 tensor or as fp32 split-K slices for the next rmsnorm"""
         m = layer.mlp
         if plans:
             b = rt.decode_bufs
-            plans['gate_up'].run(64, out=b.gu)
+            if 'gate_up' in plans:
+                plans['gate_up'].run(64, out=b.gu)
+            else:
+                torch.mm(y, m.gate_up_weight.t(), out=b.gu)
+            if pf:
+                self._prefetch(pf, [(m.down_proj.weight, pf['down'], 0)])
             ops.silu_mul(b.gu, b.act)
+            if 'down' in plans:
+                return None, plans['down'].run(64)
             return torch.mm(b.act, m.down_proj.weight.t()), None
         gu = torch.mm(y, m.gate_up_weight.t())
         act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=gu.dtype, device=gu.device)
@@ -227,6 +281,7 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         eps = self.config.rms_norm_eps
         ops.embed_gather(self.model.embed_tokens.weight, b.ids, b.n_total, b.h)
         plans = self._gemm_plans(rt) if b is rt.decode_bufs else False
+        pf = self._prefetch_cfg(rt) if plans else False
         x, parts, resid_in = b.h, None, None  # norm(x | parts, resid_in) -> (resid = x + resid_in, y = norm(resid))
 
         def norm(w):
@@ -243,15 +298,24 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
                 lp['qkv'].run(64, out=b.qkv)
             else:
                 torch.mm(b.y, a.qkv_weight.t(), out=b.qkv)
+            if pf and lp and 'gate_up' in lp:
+                gw = lp['gate_up'].weight
+                self._prefetch(pf, [(a.o_proj.weight, pf['o'], 0),
+                                    (gw, pf['gate_up'], gw.shape[1] * gw.shape[2] * gw.shape[3] * 2 if gw.dim() == 4 else 0)])
             for (r0, r1, mask, n, P) in b.chunks:
                 ops.rope_kv_append(b.qkv[r0:r1], mask, n, P, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
                                    g['head_dim'], rt.rope_cos, rt.rope_sin, b.q[r0:r1], rt.k_cache[li], rt.v_cache[li],
                                    rt.max_seq)
             for (r0, r1, mask, n, P) in b.chunks:
                 rt.plan.forward(li, b.q[r0:r1], mask, n, P, rt.pad_len, b.attn[r0:r1])
-            x, parts, resid_in = torch.mm(b.attn, a.o_proj.weight.t()), None, b.resid
+            if lp and 'o' in lp:
+                x, parts, resid_in = None, lp['o'].run(64), b.resid
+            else:
+                x, parts, resid_in = torch.mm(b.attn, a.o_proj.weight.t()), None, b.resid
             norm(layer.post_attention_layernorm.weight)
-            x, parts = self._mlp(rt, layer, b.y, lp)
+            x, parts = self._mlp(rt, layer, b.y, lp, pf)
+        if pf and pf.pop('dirty', False):  # join the side stream (required before a capture ends)
+            torch.cuda.current_stream().wait_stream(pf['side'])
         if last_only:
             return
         norm(self.model.norm.weight)

@@ -62,7 +62,7 @@ class MixtralForCausalLM(LlamaForCausalLM):
     def _layer_gemm_plans(self, layer, b):
         return {}
 
-    def _mlp(self, rt, layer, y, plans=None):
+    def _mlp(self, rt, layer, y, plans=None, pf=None):
         moe = layer.mlp
         logits = torch.mm(y, moe.gate.weight.t())                                   # :721
         probs = torch.softmax(logits.float(), dim=1)                                # :723

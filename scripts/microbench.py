@@ -15,6 +15,7 @@ ap.add_argument('--model', default='llama2-7b')
 ap.add_argument('--P', type=int, default=384)
 ap.add_argument('--n', type=int, default=64)
 ap.add_argument('--max-seq', type=int, default=577)
+ap.add_argument('--forward-only', action='store_true')
 a = ap.parse_args()
 from painlessinferenceacceleration_b200.common import ops  # noqa: E402
 from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache  # noqa: E402
@@ -54,6 +55,10 @@ def timeit(name, fn, per, reps=20, bytes_per=None):
 
 NL = g['n_layers']
 layers = model.model.layers
+if a.forward_only:
+    timeit('verify layers (whole forward) PIA_PREFETCH=' + os.environ.get('PIA_PREFETCH', '0'), lambda: model._verify_layers(rt), 1,
+           bytes_per=sum(p.numel() for p in model.parameters()) * 2)
+    sys.exit(0)
 L = a.P + a.n
 kv_bytes = 2 * L * g['n_kv_heads'] * g['head_dim'] * 2 + 2 * a.n * g['n_q_heads'] * g['head_dim'] * 2
 timeit('tree_attn+combine (32 layers)', lambda: [rt.plan.forward(li, rt.q, rt.mask[0], rt.n, rt.prefix_len, 0, rt.attn) for li in range(NL)], NL, bytes_per=kv_bytes)

@@ -63,7 +63,8 @@ def _ref_attention(q, kc, vc, rows, n, P, pad_len, G):
 
 @pytest.mark.parametrize('Hq,Hkv,P,n,pad', [(2, 2, 0, 64, 0), (4, 2, 37, 33, 0), (32, 32, 300, 64, 0),
                                              (32, 8, 1000, 47, 5), (8, 2, 127, 1, 0), (8, 8, 129, 64, 3),
-                                             (32, 8, 2500, 64, 0)])
+                                             (32, 8, 2500, 64, 0), (32, 32, 140, 64, 0), (32, 32, 600, 64, 0),
+                                             (32, 32, 520, 50, 0), (32, 32, 3900, 64, 7)])
 def test_tree_attention(Hq, Hkv, P, n, pad):
     from painlessinferenceacceleration_b200.common import ops
     rng = np.random.default_rng(P + n)
@@ -143,6 +144,18 @@ def test_rope_kv_append_and_silu():
     assert torch.equal(kc[:, P:P + n].transpose(0, 1), ref[:, Hq:])
     assert torch.equal(vc[:, P:P + n].transpose(0, 1), x[:, Hq + Hkv:])
     assert float(kc[:, :P].abs().sum()) == 0 and float(kc[:, P + n:].abs().sum()) == 0
+    # left padding that reaches beyond the cached prefix (first prefill chunk of a padded prompt): no visible prefix
+    # key, position = depth (rowsum(mask) - 1, modeling_llama.py:587)
+    qo2 = torch.zeros_like(qo)
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(vc)
+    P2 = torch.tensor([3], dtype=torch.int32, device=DEV)
+    ops.rope_kv_append(qkv, mask, dn, P2, 9, Hq, Hkv, D, cos, sin, qo2, kc2, vc2, max_seq)
+    pos2 = torch.tensor(list(depth), device=DEV)
+    c2 = torch.cat([cos[pos2], cos[pos2]], -1)[:, None]
+    s2 = torch.cat([sin[pos2], sin[pos2]], -1)[:, None]
+    ref2 = (qk * c2) + (rot(qk) * s2)
+    assert torch.equal(qo2[:n], ref2[:, :Hq])
+    assert torch.equal(kc2[:, 3:3 + n].transpose(0, 1), ref2[:, Hq:])
     gu = torch.randn((64, 2 * 1024), device=DEV).to(torch.bfloat16)
     out = torch.empty((64, 1024), dtype=torch.bfloat16, device=DEV)
     ops.silu_mul(gu, out)
@@ -305,3 +318,22 @@ def test_gemm_fused_silu_epilogue_matches_unfused():
     ops.Gemm(ops.tile_weight(ops.interleave_gate_up(w)), x, tiled=True).set_silu().run(64, out=got)
     torch.cuda.synchronize()
     assert torch.equal(got, ref)
+
+
+def test_l2_prefetch_is_a_pure_hint():
+    """pia_l2_prefetch: contiguous and strided (tile-interleaved) ranges, paced and unpaced; data untouched, bad
+    arguments rejected"""
+    from painlessinferenceacceleration_b200.common import ops
+    w = torch.randn((1 << 22,), device=DEV).to(torch.bfloat16)   # 8 MB
+    ref = w.clone()
+    n0 = ops.launch_count()
+    ops.l2_prefetch(w)
+    ops.l2_prefetch(w, n_ranges=8, stride_bytes=1 << 20, range_bytes=3 * 16384, gbytes_per_s=2000.0)
+    ops.l2_prefetch(w, range_bytes=4096, offset_bytes=32)
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 == 3
+    assert torch.equal(w, ref)
+    with pytest.raises(Exception):
+        ops.l2_prefetch(w, range_bytes=100)                 # not a multiple of 16
+    with pytest.raises(Exception):
+        ops.l2_prefetch(w, n_ranges=2, stride_bytes=16, range_bytes=64)   # overlapping ranges
