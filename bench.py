@@ -216,6 +216,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ncu_traffic(prefix, kernel):
+    """DRAM bytes (read + written) per launch of `kernel` from the newest committed `ncu --set full` summary whose
+    capture name starts with `prefix` (profiles/*_traffic.json, written by scripts/summarize_profiles.py); None when
+    there is no such capture"""
+    import glob
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_traffic.json')),
+                    reverse=True):
+        try:
+            for k, v in json.load(open(f)).items():
+                name, _, kern = k.partition(':')
+                if name.startswith(prefix) and kernel in kern:
+                    return float(v)
+        except (OSError, ValueError):
+            continue
+    return None
+
+
 def attention_roofline(model, dev):
     """k_tree_attn alone at the benchmark shape: 64 draft rows, prefix ~ mid-generation, all layers in turn (the
     layers' KV planes together exceed L2, so every launch reads cold HBM).  CUDA events on the launch stream."""
@@ -252,7 +269,8 @@ def attention_roofline(model, dev):
     hbm, _tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
     return {'kernel': 'k_tree_attn (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
-            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'us_per_launch': us,
+            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_attn_short', 'k_tree_attn'),
+            'bytes_per_launch': by, 'us_per_launch': us,
             'shape': f'n={n} P={P} Hq={g["n_q_heads"]} Hkv={g["n_kv_heads"]} D={g["head_dim"]}', 'peak_source': src}
 
 
@@ -297,7 +315,8 @@ def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
     hbm, _tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
     return {'kernel': 'k_tree_attn (one layer, long context)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
-            'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'us_per_launch': us,
+            'frac': ach / hbm, 'traffic': ncu_traffic('prof_attn_long', 'k_tree_attn') if P > 2000 else None,
+            'bytes_per_launch': by, 'us_per_launch': us,
             'shape': f'n={n} P={P} Hq={hq} Hkv={hkv} D={D}', 'peak_source': src}
 
 
@@ -347,7 +366,7 @@ def trie_roofline(dev, n_docs=1500, n_queries=4096):
     hbm, _tf, src = peaks()
     ach = by / (ms * 1e-3) / 1e9
     return {'kernel': 'k_get<64,16> (4096 hier_get rows)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
-            'frac': ach / hbm, 'traffic': None, 'bytes_per_launch': by, 'ms_per_launch': ms,
+            'frac': ach / hbm, 'traffic': ncu_traffic('prof_trie_batch', 'k_get'), 'bytes_per_launch': by, 'ms_per_launch': ms,
             'forest_nodes': s1['nodes_used'], 'mean_draft': float(o['n'].float().mean()), 'peak_source': src}
 
 

@@ -48,6 +48,7 @@ struct Hdr {
   int eos[8];
   int max_node, max_out;
   int put_len, put_npos;
+  int get_ticket, get_done;  // dynamic row scheduling of batched k_get (self-resetting)
 };
 
 struct Dev {
@@ -90,12 +91,21 @@ __device__ int find_child(const Dev &D, const Node &p, int token) {
     return D.nodes[c].token == token ? c : -1;
   }
   const int lane = lane_id();
-  for (int base = 0; base < p.n_child; base += 32) {
-    int i = base + lane;
-    int2 e = make_int2(-1, -1);
-    if (i < p.n_child) e = D.edges[p.child + i];
-    unsigned m = __ballot_sync(FULL, i < p.n_child && e.x == token);
-    if (m) return __shfl_sync(FULL, e.y, __ffs(m) - 1);
+  // UF x 32 child entries are in flight before the first ballot: with one load per lane and iteration the scan of a
+  // hot node's child block (tens of thousands of entries under a frequent token) was one L2 round trip per 32 entries
+  constexpr int UF = 8;
+  for (int base = 0; base < p.n_child; base += 32 * UF) {
+    int2 e[UF];
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      const int i = base + u * 32 + lane;
+      e[u] = i < p.n_child ? D.edges[p.child + i] : make_int2(-1, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < UF; ++u) {
+      const unsigned m = __ballot_sync(FULL, base + u * 32 + lane < p.n_child && e[u].x == token);
+      if (m) return __shfl_sync(FULL, e[u].y, __ffs(m) - 1);
+    }
   }
   return -1;
 }
@@ -337,41 +347,68 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
   for (int level = 0; cnt > 0; ++level) {
     int *push_cnt = &sh->next_cnt[(level + 1) % 3];
     if (tid == 0) sh->next_cnt[(level + 2) % 3] = 0;  // the counter of the level after next: idle during this level
-    for (int base = 0; base < cnt; base += NT) {
-      const int e = base + tid;
-      int push = 0;
-      Node nd;
-      nd.child = -1; nd.cap = 0;
-      if (e < cnt) {
-        const int id = cur[e];
-        nd = D.nodes[id];
-        ++nv;
-        if (visit(id, nd) && nd.n_child > 0) push = nd.n_child;
-      }
-      // frontier reservation: single-child (inline) nodes - the bulk of an n-gram trie - are placed with one ballot;
-      // the shuffle scan only runs when some lane of the warp has a child block to expand
-      const bool one = push == 1 && nd.cap == 0;
-      const int many = one ? 0 : push;
-      const unsigned m1 = __ballot_sync(FULL, one);
-      const unsigned mm = __ballot_sync(FULL, many > 0);
-      int incl = many;
-      if (mm) {
+    // U frontier entries per thread and iteration: the U node records (dependent on the U frontier loads) are all in
+    // flight before the first is inspected - one record per thread at a time left a hot subtree latency-bound
+    constexpr int U = 2;
+    for (int base = 0; base < cnt; base += NT * U) {
+      int id[U], push[U];
+      Node nd[U];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      for (int u = 0; u < U; ++u) {
+        const int e = base + u * NT + tid;
+        id[u] = e < cnt ? cur[e] : -1;
       }
-      const int tot_many = mm ? __shfl_sync(FULL, incl, 31) : 0;
-      const int total = __popc(m1) + tot_many;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (id[u] >= 0) nd[u] = D.nodes[id[u]];
+        else { nd[u].child = -1; nd[u].cap = 0; nd[u].n_child = 0; }
+      }
+      int many = 0, ones = 0;  // entries this thread appends: single-child (inline) nodes / expanded child blocks
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        push[u] = 0;
+        if (id[u] >= 0) {
+          ++nv;
+          if (visit(id[u], nd[u]) && nd[u].n_child > 0) push[u] = nd[u].n_child;
+        }
+        if (push[u] == 1 && nd[u].cap == 0) ++ones; else many += push[u];
+      }
+      // frontier reservation: one warp scan + one atomic per iteration for all U entries of every lane
+      const int mine = ones + many;
+      const unsigned any = __ballot_sync(FULL, mine > 0);
+      if (any == 0) continue;  // warp-uniform
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+      const int total = __shfl_sync(FULL, incl, 31);
       int wbase = 0;
-      if (lane == 0 && total > 0) wbase = atomicAdd(push_cnt, total);
+      if (lane == 0) wbase = atomicAdd(push_cnt, total);
       wbase = __shfl_sync(FULL, wbase, 0);
-      if (total > 0 && wbase + total > D.fr_cap) {
+      if (wbase + total > D.fr_cap) {
         if (lane == 0) atomicOr(&sh->err, ERR_FRONTIER);
       } else {
-        if (one) nxt[wbase + __popc(m1 & ((1u << lane) - 1u))] = nd.child;
-        if (many > 0) {
-          const int pos = wbase + __popc(m1) + incl - many;
-          for (int k = 0; k < many; ++k) nxt[pos + k] = D.edges[nd.child + k].y;
-          ne += many;
+        int pos = wbase + incl - mine;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool one = push[u] == 1 && nd[u].cap == 0;
+          // child blocks of >= 32 entries (the hot nodes of a Zipf vocabulary hold thousands) are copied by the whole
+          // warp, lane-strided; left to the owning lane they serialise the level behind one thread
+          const bool big = !one && push[u] >= 32;
+          if (one) nxt[pos] = nd[u].child;
+          else if (push[u] > 0 && !big) {
+            for (int k = 0; k < push[u]; ++k) nxt[pos + k] = D.edges[nd[u].child + k].y;
+          }
+          unsigned mb = __ballot_sync(FULL, big);
+          while (mb) {
+            const int src = __ffs(mb) - 1;
+            mb &= mb - 1;
+            const int c0 = __shfl_sync(FULL, nd[u].child, src);
+            const int cn = __shfl_sync(FULL, push[u], src);
+            const int p0 = __shfl_sync(FULL, pos, src);
+            for (int k = lane; k < cn; k += 32) nxt[p0 + k] = D.edges[c0 + k].y;
+          }
+          if (!one) ne += push[u];
+          pos += push[u];
         }
       }
     }
@@ -452,7 +489,7 @@ struct GetSmem {
   int hist_ovf;
   long long n_live, n_in, n_out;
   unsigned long long thr_bits; int thr_found;
-  int pool_n, match_node, n, sizes0, sizes1, depth, state;
+  int pool_n, match_node, n, sizes0, sizes1, depth, state, ticket;
   int best_node, best_tok; unsigned long long best_key; int best_ord;
 };
 
@@ -469,53 +506,71 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
   const Node p = D.nodes[parent];
   const int C = p.n_child;
   int m = 0;  // current size of the running top list (uniform)
-  for (int base = 0; base < C; base += NT) {
-    if (tid == 0) S->pool_n = m;
-    __syncthreads();
-    const int i = base + tid;
-    if (i < C) {
-      int cid;
-      if (p.cap == 0) cid = p.child; else { cid = D.edges[p.child + i].y; ++ne; }
-      const Node c = D.nodes[cid];
-      ++nv;
-      const double fi = (double)load_fi(D, c, cid, idx), fo = c.fo;
-      const double fm = mix_freq(omw, w, fi, fo);
-      bool skip;
-      if (mode == PIA_MODE_MIX) skip = (fi < min_in && fo < min_out && fm < min_mix);
-      else if (mode == PIA_MODE_INPUT) skip = fi < min_in;
-      else skip = fo < min_out;
-      if (!skip) {
-        const int slot = atomicAdd(&S->pool_n, 1);
-        S->pkey[slot] = dbits(fm);
-        S->pord[slot] = i;
-        S->pnode[slot] = cid;
-        S->ptok[slot] = c.token;
-        S->pflag[slot] = (fi > 0.0 ? CF_FI : 0) | (fo > 0.0 ? CF_FO : 0) | (c.n_child > 0 ? CF_KIDS : 0);
-      }
+  constexpr int U = 2;  // child chunks whose records are fetched together (memory-level parallelism on wide nodes)
+  for (int base = 0; base < C; base += NT * U) {
+    int cid[U];
+    Node cn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT + tid;
+      cid[u] = -1;
+      if (i < C) { if (p.cap == 0) cid[u] = p.child; else { cid[u] = D.edges[p.child + i].y; ++ne; } }
     }
-    __syncthreads();
-    const int total = S->pool_n;
-    // rank every pool element; the first K in (key desc, ord asc) order survive
-    for (int e = tid; e < total; e += NT) {
-      const unsigned long long k = S->pkey[e];
-      const int o = S->pord[e];
-      int rank = 0;
-      for (int j = 0; j < total; ++j) {
-        const unsigned long long kj = S->pkey[j];
-        rank += (kj > k) || (kj == k && S->pord[j] < o);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (cid[u] >= 0) { cn[u] = D.nodes[cid[u]]; ++nv; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * NT >= C) break;  // uniform
+      if (tid == 0) S->pool_n = m;
+      __syncthreads();
+      const int i = base + u * NT + tid;
+      if (cid[u] >= 0) {
+        const Node &c = cn[u];
+        const double fi = (double)load_fi(D, c, cid[u], idx), fo = c.fo;
+        const double fm = mix_freq(omw, w, fi, fo);
+        bool skip;
+        if (mode == PIA_MODE_MIX) skip = (fi < min_in && fo < min_out && fm < min_mix);
+        else if (mode == PIA_MODE_INPUT) skip = fi < min_in;
+        else skip = fo < min_out;
+        // once K candidates are held, a later child (larger insertion index) only displaces one of them with a
+        // strictly larger key: ties go to the earlier child (:254-258)
+        if (!skip && m >= K && K > 0 && dbits(fm) <= S->pkey[K - 1]) skip = true;
+        if (!skip && K <= 0) skip = true;
+        if (!skip) {
+          const int slot = atomicAdd(&S->pool_n, 1);
+          S->pkey[slot] = dbits(fm);
+          S->pord[slot] = i;
+          S->pnode[slot] = cid[u];
+          S->ptok[slot] = c.token;
+          S->pflag[slot] = (fi > 0.0 ? CF_FI : 0) | (fo > 0.0 ? CF_FO : 0) | (c.n_child > 0 ? CF_KIDS : 0);
+        }
       }
-      if (rank < K) {
-        S->qkey[rank] = k; S->qord[rank] = o; S->qnode[rank] = S->pnode[e]; S->qtok[rank] = S->ptok[e];
-        S->qflag[rank] = S->pflag[e];
+      __syncthreads();
+      const int total = S->pool_n;
+      if (total == m) continue;  // nothing new (uniform): the running list stands
+      // rank every pool element; the first K in (key desc, ord asc) order survive
+      for (int e = tid; e < total; e += NT) {
+        const unsigned long long k = S->pkey[e];
+        const int o = S->pord[e];
+        int rank = 0;
+        for (int j = 0; j < total; ++j) {
+          const unsigned long long kj = S->pkey[j];
+          rank += (kj > k) || (kj == k && S->pord[j] < o);
+        }
+        if (rank < K) {
+          S->qkey[rank] = k; S->qord[rank] = o; S->qnode[rank] = S->pnode[e]; S->qtok[rank] = S->ptok[e];
+          S->qflag[rank] = S->pflag[e];
+        }
       }
+      __syncthreads();
+      m = total < K ? total : K;
+      for (int e = tid; e < m; e += NT) {
+        S->pkey[e] = S->qkey[e]; S->pord[e] = S->qord[e]; S->pnode[e] = S->qnode[e]; S->ptok[e] = S->qtok[e];
+        S->pflag[e] = S->qflag[e];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    m = total < K ? total : K;
-    for (int e = tid; e < m; e += NT) {
-      S->pkey[e] = S->qkey[e]; S->pord[e] = S->qord[e]; S->pnode[e] = S->qnode[e]; S->ptok[e] = S->qtok[e];
-      S->pflag[e] = S->qflag[e];
-    }
-    __syncthreads();
   }
   for (int e = tid; e < m; e += NT) { onode[e] = S->pnode[e]; otok[e] = S->ptok[e]; oflag[e] = (unsigned char)S->pflag[e]; }
   __syncthreads();
@@ -804,7 +859,7 @@ __device__ int tree_get_one(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int 
 
 // LookaheadCache.hier_get / one_get (lookahead_cache.py:408-439, 490-517): one CTA per query row
 template <int MAXS, int MAXD>
-__global__ void __launch_bounds__(NT) k_get(Dev D, GetParams P) {
+__global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GetSmem<MAXS, MAXD> *S = reinterpret_cast<GetSmem<MAXS, MAXD> *>(smem_raw);
   constexpr int W = (MAXS + 63) / 64;
@@ -813,7 +868,17 @@ __global__ void __launch_bounds__(NT) k_get(Dev D, GetParams P) {
   int *fr1 = fr0 + D.fr_cap;
   unsigned long long nv = 0, ne = 0;
   const int Wout = (P.dl + 63) / 64;
-  for (int b = blockIdx.x; b < P.batch; b += gridDim.x) {
+  // rows are handed out by a ticket counter when there are more rows than CTAs (a batched scan: query cost varies by
+  // three orders of magnitude with the matched subtree, a static stride leaves SMs idle behind the hot rows)
+  const bool dynamic = P.batch > (int)gridDim.x;
+  for (int b = blockIdx.x;; ) {
+    if (dynamic) {
+      __syncthreads();
+      if (tid == 0) S->ticket = atomicAdd(&D.hdr->get_ticket, 1);
+      __syncthreads();
+      b = S->ticket;
+    }
+    if (b >= P.batch) break;
     __syncthreads();
     const int len = P.qlen[b];
     int nq, bl = P.bl;
@@ -886,6 +951,11 @@ __global__ void __launch_bounds__(NT) k_get(Dev D, GetParams P) {
       P.status[b] = status;
       if (status == PIA_ERR_CAPACITY) atomicOr(&D.hdr->err, S->hist_ovf ? ERR_HIST : ERR_FRONTIER);
     }
+    if (!dynamic) break;  // one row per CTA
+  }
+  if (dynamic && tid == 0) {  // the last CTA to leave re-arms the ticket counter for the next launch
+    __threadfence();
+    if (atomicAdd(&D.hdr->get_done, 1) == (int)gridDim.x - 1) { D.hdr->get_ticket = 0; D.hdr->get_done = 0; __threadfence(); }
   }
   // roofline accounting: node records / child entries read
   for (int o = 16; o > 0; o >>= 1) { nv += __shfl_down_sync(FULL, nv, o); ne += __shfl_down_sync(FULL, ne, o); }

@@ -1,6 +1,10 @@
 # -*- coding: utf-8 -*-
 """Turns the raw ncu outputs brought back in gpurun_out/ into the small tracked summaries under profiles/.
-    python scripts/summarize_profiles.py <tag>        e.g. r01a"""
+    python scripts/summarize_profiles.py <tag> [file ...]     e.g. r01c launches_r4_bench.csv prof_tree_attn_r2.ncu-rep
+Without file arguments every launches*.csv / *.ncu-rep in gpurun_out/ is summarised.  Also writes
+profiles/<tag>_traffic.json (DRAM bytes per launch of each fully captured kernel), which bench.py reads for
+roofline.traffic."""
+import json
 import collections
 import csv
 import io
@@ -27,8 +31,9 @@ def launch_list(path, name):
     rows = [(int(r['ID']), r['Kernel Name'], float(r['Metric Value'].replace(',', '')))
             for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
     gets = [i for i, r in enumerate(rows) if 'k_get' in r[1]]
+    cmd = 'bench.py --steps 2 --warmup 3 --no-cpu-baseline' if 'bench' in name else 'scripts/profile_step.py'
     out = [f'# ncu launch list ({name}): `ncu --metrics gpu__time_duration.sum --clock-control none` on '
-           f'scripts/profile_step.py (Llama-2-7B shape)', '',
+           f'`{cmd}` (Llama-2-7B shape)', '',
            'Per-launch times are cold-cache and serialised: read the SHARES, not the absolutes.', '',
            f'{len(rows)} launches captured; one decode step = the launches between two consecutive `k_get`.', '']
     if len(gets) >= 2:
@@ -42,9 +47,10 @@ def launch_list(path, name):
                 '| kernel | launches | total us | share |', '|---|---:|---:|---:|']
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             out.append(f'| `{k}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% |')
-        own = sum(v[1] for k, v in agg.items() if 'nvjet' not in k and 'cutlass' not in k and 'at::' not in k)
-        out += ['', f'own kernels (libpia_b200): {100 * own / tot:.1f}% of the step; cuBLAS GEMMs (`nvjet_*`): '
-                    f'{100 * (tot - own) / tot:.1f}%']
+        own = sum(r[2] for r in seg if re.search(r'\b(gemm|attn|fused|trie|accept)::k_', r[1]))
+        blas = sum(r[2] for r in seg if 'nvjet' in r[1] or 'cutlass' in r[1] or 'gemv' in r[1])
+        out += ['', f'own kernels (libpia_b200, `pia::*`): {100 * own / tot:.1f}% of the step; cuBLAS GEMMs (`nvjet_*`): '
+                    f'{100 * blas / tot:.1f}%; other (torch elementwise): {100 * (tot - own - blas) / tot:.1f}%']
     open(os.path.join(OUT, f'{tag}_launches.md'), 'w').write('\n'.join(out) + '\n')
 
 
@@ -55,6 +61,9 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__block_size', 'launch__shared_mem_per_block_dynamic', 'sm__cycles_active.avg', 'sm__cycles_elapsed.max',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'lts__t_sectors_srcunit_tex_op_read.sum',
         'lts__t_sector_hit_rate.pct', 'smsp__inst_executed.sum']
+
+
+TRAFFIC = {}
 
 
 def full(rep, name):
@@ -70,15 +79,27 @@ def full(rep, name):
         for w in WANT:
             if w in d:
                 out.append(f'| {w} | {d[w]} | {units[hdr.index(w)]} |')
-        rd_b = float(d.get('dram__bytes_read.sum', '0').replace(',', '') or 0)
+        try:
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            tb = sum(float(d[m].replace(',', '')) * scale.get(units[hdr.index(m)], 1.0)
+                     for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+            TRAFFIC.setdefault(name + ':' + short(d.get('Kernel Name', '')), []).append(tb)
+            out.append(f'| dram bytes read + written | {tb / 1e6:.2f} | MB |')
+        except (KeyError, ValueError):
+            pass
         out.append('')
     open(os.path.join(OUT, f'{tag}_{name}.md'), 'w').write('\n'.join(out) + '\n')
 
 
+only = sys.argv[2:]
 for f in sorted(os.listdir(GO)):
+    if only and f not in only:
+        continue
     p = os.path.join(GO, f)
     if f.startswith('launches') and f.endswith('.csv'):
         launch_list(p, f[:-4])
     elif f.endswith('.ncu-rep'):
         full(p, f[:-8])
+if TRAFFIC:
+    json.dump({k: float(sum(v) / len(v)) for k, v in TRAFFIC.items()}, open(os.path.join(OUT, f'{tag}_traffic.json'), 'w'), indent=1)
 print(sorted(os.listdir(OUT)))
