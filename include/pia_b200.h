@@ -159,8 +159,6 @@ int pia_attn_plan_destroy(pia_attn_plan_t *p);
  * disable; grid geometry of the plan (n_split x n_groups CTAs). */
 int pia_attn_plan_set_debug(pia_attn_plan_t *p, void *d_timestamps);
 int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n_groups);
-/* bytes of fp32 workspace the forward needs (split-KV partials) */
-int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p);
 
 /* One layer of tree attention over the cache (rows [0, P+n) must already hold K/V, RoPE applied).
  *   d_q    : [max_nodes, n_q_heads, head_dim] bf16 (rows >= n ignored)
@@ -168,10 +166,10 @@ int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p);
  *   d_prefix_len : device int P (tokens already in the cache before this step's nodes)
  *   pad_len : left-pad columns [0, pad_len) are masked for every row (pretrained_model.py:1123-1131)
  *   d_out  : [max_nodes, n_q_heads, head_dim] bf16
- * softmax scale = 1/sqrt(head_dim) * `scale_mul` (1.0 for the reference models). */
+ * softmax scale = 1/sqrt(head_dim) * `scale_mul` (1.0 for the reference models).  Needs no workspace: KV splits are
+ * merged through the distributed shared memory of a thread-block cluster. */
 int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask, const int32_t *d_n,
-                      const int32_t *d_prefix_len, int pad_len, float scale_mul, void *d_out, void *d_workspace,
-                      void *stream);
+                      const int32_t *d_prefix_len, int pad_len, float scale_mul, void *d_out, void *stream);
 
 /* ============================================================================================
  * Weight-streaming GEMM of the verify forward: Y[t, n] = sum_k X[t, k] W[n, k]  (X: <= 64 draft rows, W = an

@@ -118,7 +118,7 @@ def embed_gather(table, ids, n, out):
 
 
 class AttnPlan(object):
-    """pia_attn_plan_t: TMA descriptors over one model's KV cache + split-KV workspace"""
+    """pia_attn_plan_t: TMA descriptors over one model's KV cache (KV splits merge on chip: no workspace)"""
 
     def __init__(self, k_cache, v_cache, n_q_heads, n_kv_heads, head_dim, max_nodes, kv_split_max=0):
         n_layers, hkv, max_seq, hd = k_cache.shape
@@ -128,13 +128,11 @@ class AttnPlan(object):
         self.lib = L.load()
         with torch.cuda.device(k_cache.device):
             L.check(self.lib.pia_attn_plan_create(C.byref(self.cfg), _p(k_cache), _p(v_cache), C.byref(self.h)))
-            nbytes = self.lib.pia_attn_workspace_bytes(self.h)
-        self.workspace = torch.empty((nbytes // 4,), dtype=torch.float32, device=k_cache.device)
         self._keep = (k_cache, v_cache)
 
     def forward(self, layer, q, mask, n, prefix_len, pad_len, out, scale_mul=1.0):
         L.check(self.lib.pia_tree_attn_fwd(self.h, layer, _p(q), _p(mask), _p(n), _p(prefix_len), int(pad_len),
-                                           float(scale_mul), _p(out), _p(self.workspace), _s()))
+                                           float(scale_mul), _p(out), _s()))
 
     def close(self):
         if self.h:

@@ -12,14 +12,16 @@
 //                            warp 1 = TMEM owner + single-thread tcgen05.mma issuer,
 //                            warps 2-9 = softmax / accumulate, two threads per row (TMEM lane == row; each
 //                            takes 64 S columns and 64 O columns, row max / sum exchanged through smem).
-// Per 128-key tile:  S = Q K^T (8 x UMMA 128x128x16, fp32 in TMEM, double buffered)
-//                    -> thread-local online softmax in fp32 (no shuffles: a thread owns its row)
-//                    -> P (bf16) to shared memory in the UMMA K-major SWIZZLE_128B layout
-//                    -> O_tile = P V (8 x UMMA, V consumed MN-major straight from the TMA tile)
-//                    -> acc = acc * alpha + O_tile in registers.
-// The KV range is split across CTAs only when it is long (>= 4 tiles per CTA, decided on the device from the
-// live length): a single-split CTA normalises and writes bf16 directly; otherwise partials (acc, m, l) go to a
-// workspace and the last split CTA of the head group to arrive merges them (no separate combine launch).
+// Per 128-key tile:  S = Q K^T (8 x UMMA 128x128x16 SS, fp32 in TMEM, double buffered)
+//                    -> hidden keys to -inf (one 32-bit visibility word per 32 keys), online softmax in fp32
+//                    -> P (bf16 pairs) back to TMEM (tcgen05.st, double buffered) = the A operand of
+//                    -> O_tile = P V (8 x UMMA TS form, V consumed MN-major straight from the TMA tile)
+//                    -> acc = acc * alpha + O_tile in registers, one tile late, so that PV(i) and QK^T(i+1) run on
+//                       the tensor core while the softmax warps are busy with tile i+1.
+// The KV range is split across the CTAs of a thread-block cluster (one wave of clusters, split count decided on the
+// device from the live length): a single-split CTA normalises and writes bf16 directly; otherwise every thread
+// pushes its partial row (acc, m, l) into the shared memory of the CTA that owns the row (DSMEM) and each CTA
+// combines its row slice locally - no workspace in HBM, no separate combine launch.
 // HBM-bound by design (arithmetic intensity = rows per KV byte: 64 FLOP/B for MHA, 256 for GQA-4;
 // DESIGN.md gives the roofline).
 #include <cuda.h>
@@ -174,12 +176,9 @@ struct Params {
   const __nv_bfloat16 *q;  // [max_nodes, Hq, HD]
   const unsigned long long *mask;
   const int *d_n, *d_prefix;
-  float *ws_acc;           // [n_split, Hq, np, HD]
-  float *ws_m, *ws_l;      // [n_split, Hq, np]
   int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split, tiles_per_cta;
   float scale_log2;
   __nv_bfloat16 *out;            // [max_nodes, Hq, HD]
-  int *counters;                 // [n_groups] arrival counters of the split CTAs (self-resetting)
   unsigned long long *dbg;       // optional per-CTA phase timestamps (pia_attn_plan_set_debug)
 };
 
@@ -545,7 +544,6 @@ struct pia_attn_plan {
   pia_attn_config_t cfg;
   CUtensorMap map_k, map_v;
   int heads_per_cta, n_groups, n_split, mask_words, tiles_per_cta;
-  int *counters;
   unsigned long long *dbg;
 };
 
@@ -606,15 +604,8 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
     cudaError_t e = cudaFuncSetAttribute(k_tree_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
-  p->counters = nullptr;
   p->dbg = nullptr;
-  if (rc == PIA_OK) {
-    cudaError_t e = cudaMalloc((void **)&p->counters, sizeof(int) * p->n_groups);
-    if (e == cudaSuccess) e = cudaMemset(p->counters, 0, sizeof(int) * p->n_groups);
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { set_error("attn plan: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
-  }
-  if (rc != PIA_OK) { if (p->counters) cudaFree(p->counters); delete p; return rc; }
+  if (rc != PIA_OK) { delete p; return rc; }
   *out = p;
   return PIA_OK;
 }
@@ -631,33 +622,23 @@ extern "C" int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n
 }
 
 extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) {
-  if (p) { if (p->counters) cudaFree(p->counters); delete p; }
+  if (p) delete p;
   return PIA_OK;
-}
-
-extern "C" int64_t pia_attn_workspace_bytes(const pia_attn_plan_t *p) {
-  if (!p) return 0;
-  const int64_t rows = (int64_t)p->n_split * p->cfg.n_q_heads * p->cfg.max_nodes;
-  return rows * (HD + 2) * (int64_t)sizeof(float);
 }
 
 extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask,
                                  const int32_t *d_n, const int32_t *d_prefix_len, int pad_len, float scale_mul,
-                                 void *d_out, void *d_workspace, void *stream) {
-  PIA_REQUIRE(p && d_q && d_mask && d_n && d_prefix_len && d_out && d_workspace, "null argument");
+                                 void *d_out, void *stream) {
+  PIA_REQUIRE(p && d_q && d_mask && d_n && d_prefix_len && d_out, "null argument");
   PIA_REQUIRE(layer >= 0 && layer < p->cfg.n_layers, "layer %d outside [0,%d)", layer, p->cfg.n_layers);
   Params a;
-  const int64_t rows = (int64_t)p->n_split * p->cfg.n_q_heads * p->cfg.max_nodes;
   a.q = (const __nv_bfloat16 *)d_q;
   a.mask = (const unsigned long long *)d_mask;
   a.d_n = d_n; a.d_prefix = d_prefix_len;
-  a.ws_acc = (float *)d_workspace;
-  a.ws_m = a.ws_acc + rows * HD;
-  a.ws_l = a.ws_m + rows;
   a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
   a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.pad_len = pad_len; a.max_seq = p->cfg.max_seq;
   a.n_split = p->n_split; a.tiles_per_cta = p->tiles_per_cta;
-  a.out = (__nv_bfloat16 *)d_out; a.counters = p->counters; a.dbg = p->dbg;
+  a.out = (__nv_bfloat16 *)d_out; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
   PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(p->n_split, p->n_groups), dim3(NTHREADS), SMEM_TOTAL, s,
