@@ -52,6 +52,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -105,6 +116,7 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOK 
 
 struct Params {
   int N, K, n_split, chunks_per_split, n_chunks, rows, tiled;
+  int cluster;              // > 1: the K splits of a tile are one thread-block cluster and reduce through DSMEM (bf16 out)
   int silu;                 // 1: tile rows are 64 gate rows + 64 up rows of the same columns -> out = silu(g) * u
   __nv_bfloat16 *out_bf16;  // [rows_cap, N]  (or [rows_cap, N/2] with silu)   (n_split == 1)
   float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
@@ -123,7 +135,9 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t bar_full = base + SMEM_BAR, bar_empty = bar_full + 8 * NSTAGE, bar_acc = bar_empty + 8 * NSTAGE;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 16);
-  const int n0 = blockIdx.x * BMW, split = blockIdx.y;
+  // grid = (tiles, splits), or (splits, tiles) when the splits of a tile form a cluster (clusters run along x)
+  const int tile = p.cluster ? blockIdx.y : blockIdx.x, split = p.cluster ? blockIdx.x : blockIdx.y;
+  const int n0 = tile * BMW;
   const int c0 = split * p.chunks_per_split;
   int c1 = c0 + p.chunks_per_split;
   if (c1 > p.n_chunks) c1 = p.n_chunks;
@@ -151,7 +165,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     if (lane == 0) {
       auto load_w = [&](int i, int s) {
         const uint32_t wd = base + s * STAGE_BYTES;
-        if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, blockIdx.x * p.n_chunks + c0 + i);
+        if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, tile * p.n_chunks + c0 + i);
         else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
       };
       const int pre = nch < NSTAGE ? nch : NSTAGE;
@@ -169,6 +183,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
         tma_load_2d(base + s * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
       }
     }
+    __syncwarp();
+    if (p.cluster) { cluster_sync_all(); cluster_sync_all(); }
   } else if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < nch; ++i) {
@@ -183,6 +199,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       }
       umma_commit(bar_acc);
     }
+    __syncwarp();
+    if (p.cluster) { cluster_sync_all(); cluster_sync_all(); }
   } else {
     // epilogue: thread = one weight row n (TMEM lane), 64 token values in registers
     pdl_wait();  // output stores (and the WAR hazard on the output buffer) are ordered after the predecessor
@@ -200,6 +218,45 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
 #pragma unroll
       for (int t = 0; t < 64; ++t) v[t] = 0u;
     }
+    if (p.cluster) {
+      // split-K inside a cluster: after everyone has left its main loop (barrier A: the pipeline stages of every CTA
+      // are dead) each thread pushes its fp32 row - 16 token quads, quad-major so that the lanes of a warp write
+      // consecutive 16-byte words - into the CTA that owns that row slice, barrier B, and the owner adds the
+      // cluster's partials in split order (deterministic) and writes bf16.  No fp32 round trip through HBM/L2.
+      const int cs = p.cluster, RS = BMW / cs;      // rows per owner CTA: 64 (2 splits) or 32 (4 splits)
+      cluster_sync_all();
+      {
+        const int row = q * 32 + lane;
+        const int owner = row / RS, rl = row % RS;
+        const uint32_t dst = map_to_cta(base + (uint32_t)((split * 16) * RS + rl) * 16, owner);
+#pragma unroll
+        for (int tq = 0; tq < 16; ++tq)
+          st_cluster_f4(dst + (uint32_t)(tq * RS) * 16, __uint_as_float(v[4 * tq]), __uint_as_float(v[4 * tq + 1]),
+                        __uint_as_float(v[4 * tq + 2]), __uint_as_float(v[4 * tq + 3]));
+      }
+      cluster_sync_all();
+      {
+        const int e = (warp - 2) * 32 + lane;       // 0..127
+        const int rl = e % RS, tg = e / RS;         // row of this CTA's slice, token group
+        const int qpt = RS / 8;                     // token quads per thread: 16 / (128 / RS)
+        const int n_out = n0 + split * RS + rl;     // this CTA's rank in the cluster == its split index
+        const float4 *buf = reinterpret_cast<const float4 *>(sm);
+        if (n_out < p.N) {
+          for (int tq = tg * qpt; tq < (tg + 1) * qpt; ++tq) {
+            float4 a = buf[(0 * 16 + tq) * RS + rl];
+            for (int src = 1; src < cs; ++src) {
+              const float4 b = buf[(src * 16 + tq) * RS + rl];
+              a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            const int t0 = 4 * tq;
+            if (t0 < p.rows) p.out_bf16[(long long)t0 * p.N + n_out] = __float2bfloat16_rn(a.x);
+            if (t0 + 1 < p.rows) p.out_bf16[(long long)(t0 + 1) * p.N + n_out] = __float2bfloat16_rn(a.y);
+            if (t0 + 2 < p.rows) p.out_bf16[(long long)(t0 + 2) * p.N + n_out] = __float2bfloat16_rn(a.z);
+            if (t0 + 3 < p.rows) p.out_bf16[(long long)(t0 + 3) * p.N + n_out] = __float2bfloat16_rn(a.w);
+          }
+        }
+      }
+    } else
     if (p.silu) {
       // act(gate) * up (modeling_llama.py:185-186) in the epilogue: lanes 0-63 hold gate rows, lanes 64-127 the up
       // rows of the same 64 output columns.  Rounding points as in eager bf16: GEMM out -> bf16, silu -> bf16, * -> bf16
@@ -211,7 +268,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (q < 2) {
-        const int col = blockIdx.x * 64 + rr;
+        const int col = tile * 64 + rr;
         const int inter = p.N >> 1;
         if (col < inter) {
 #pragma unroll
@@ -498,12 +555,20 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   PIA_REQUIRE(g, "out of host memory");
   const int n_chunks = K / BK;
   const int want_stream_k = (split_k == -1);
+  const int want_cluster = (split_k == -2 || split_k == -4) ? -split_k : 0;
+  if (split_k < -1 && !want_cluster) { delete g; set_error("cluster split-K supports 2 or 4 CTAs"); return PIA_ERR_INVALID; }
+  if (want_cluster) split_k = want_cluster;
   if (split_k < 1) split_k = 1;
   if (split_k > n_chunks) split_k = n_chunks;
   g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks;
   g->p.chunks_per_split = (n_chunks + split_k - 1) / split_k;
   g->p.n_split = (n_chunks + g->p.chunks_per_split - 1) / g->p.chunks_per_split;
   g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr; g->p.silu = 0;
+  g->p.cluster = 0;
+  if (want_cluster) {
+    if (g->p.n_split != want_cluster) { delete g; set_error("K = %d is too short for %d cluster splits", K, want_cluster); return PIA_ERR_INVALID; }
+    g->p.cluster = want_cluster;
+  }
   g->p.tiled = w_tiled ? 1 : 0;
   if (w_tiled && N % BMW != 0) { delete g; set_error("a tiled weight needs N %% %d == 0", BMW); return PIA_ERR_INVALID; }
   int rc = w_tiled ? encode_tiled_w(&g->map_w, d_w, (uint64_t)(N / BMW) * n_chunks)
@@ -554,7 +619,7 @@ extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) {
   }
   return PIA_OK;
 }
-extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? g->p.n_split : 0; }
+extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? (g->p.cluster ? 1 : g->p.n_split) : 0; }
 extern "C" int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on) {
   PIA_REQUIRE(g && g->p.n_split == 1 && !g->stream_k && g->p.N % BMW == 0, "the SiLU*up epilogue needs split_k == 1 and N %% 128 == 0");
   g->p.silu = on ? 1 : 0;
@@ -574,7 +639,14 @@ extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *str
   }
   Params p = g->p;
   p.rows = rows;
-  if (p.n_split == 1) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
+  if (p.n_split == 1 || p.cluster) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
+  if (p.cluster) {
+    dim3 cgrid(p.n_split, (p.N + BMW - 1) / BMW);
+    if (g->nstage == 8) PIA_CUDA_CHECK(launch_kernel_cluster(k_gemm_ws<8>, cgrid, dim3(NTHREADS), smem_total(8), (cudaStream_t)stream, (unsigned)p.cluster, g->map_w, g->map_x, p));
+    else PIA_CUDA_CHECK(launch_kernel_cluster(k_gemm_ws<4>, cgrid, dim3(NTHREADS), smem_total(4), (cudaStream_t)stream, (unsigned)p.cluster, g->map_w, g->map_x, p));
+    count_launch();
+    return PIA_OK;
+  }
   dim3 grid((p.N + BMW - 1) / BMW, p.n_split);
   if (g->nstage == 8) PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<8>, grid, dim3(NTHREADS), smem_total(8), (cudaStream_t)stream, g->map_w, g->map_x, p));
   else PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<4>, grid, dim3(NTHREADS), smem_total(4), (cudaStream_t)stream, g->map_w, g->map_x, p));

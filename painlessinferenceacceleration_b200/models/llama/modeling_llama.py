@@ -189,21 +189,26 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         return plans
 
     def _layer_gemm_plans(self, layer, b):
-        """Which projections go through k_gemm_ws is decided by measurement (scripts/gemm_bench.py, Llama-2-7B shapes,
-        us per launch incl. the consumer kernel): gate_up 35.5 vs cuBLAS 38.6 (both + k_silu_mul; the fused SiLU
-        epilogue costs 38.3), lm_head 42.3 vs 46.6.  qkv (96 weight tiles: 22.1 vs 20.3), o (32 tiles: 10.3 vs 9.8) and
-        down (split-K 4 + rmsnorm over partials 23.3 vs 22.6) stay on cuBLAS."""
+        """Which projections go through k_gemm_ws is decided by measurement (Llama-2-7B shapes; whole verify forward
+        as one CUDA graph, scripts/microbench.py --forward-only, us per forward): gate_up only 3453; + down as a
+        4-CTA cluster split-K (fp32 partials reduced through DSMEM) 3421; + o (cluster 4) 3527; + qkv (cluster 2)
+        3482; everything 3740 - a k_gemm_ws launched behind the 200 KB-per-SM attention kernel cannot use its early
+        weight streaming, and cuBLAS' 64x32 tiles win on the 32/96-tile projections.  Per launch (scripts/gemm_bench.py):
+        gate_up 31.5 us vs cuBLAS 34.6, lm_head 42.3 vs 46.6.  PIA_GEMM_SET overrides the set."""
         import os
-        want = os.environ.get('PIA_GEMM_SET', 'gate_up').split(',')
+        want = os.environ.get('PIA_GEMM_SET', 'gate_up,down').split(',')
         plans = {}
         if 'gate_up' in want:
             plans['gate_up'] = self._mk_gemm(layer.mlp.gate_up_weight, b.y)
         if 'qkv' in want:
             plans['qkv'] = self._mk_gemm(layer.self_attn.qkv_weight, b.y)
-        if 'o' in want:      # fp32 split-K slices, summed by the following rmsnorm
-            plans['o'] = self._mk_gemm(layer.self_attn.o_proj.weight.data, b.attn, split_k=4)
+        sk = int(os.environ.get('PIA_GEMM_SPLIT', '-4'))   # > 1: fp32 slices summed by the next rmsnorm; < -1: cluster
+        if 'qkv2' in want:
+            plans['qkv'] = self._mk_gemm(layer.self_attn.qkv_weight, b.y, split_k=-2)
+        if 'o' in want:
+            plans['o'] = self._mk_gemm(layer.self_attn.o_proj.weight.data, b.attn, split_k=sk)
         if 'down' in want:
-            plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=4)
+            plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=sk)
         return plans
 
     @staticmethod
@@ -263,7 +268,8 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
                 self._prefetch(pf, [(m.down_proj.weight, pf['down'], 0)])
             ops.silu_mul(b.gu, b.act)
             if 'down' in plans:
-                return None, plans['down'].run(64)
+                o = plans['down'].run(64)
+                return (o, None) if plans['down'].splits == 1 else (None, o)
             return torch.mm(b.act, m.down_proj.weight.t()), None
         gu = torch.mm(y, m.gate_up_weight.t())
         act = torch.empty((gu.shape[0], gu.shape[1] // 2), dtype=gu.dtype, device=gu.device)
@@ -309,7 +315,8 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             for (r0, r1, mask, n, P) in b.chunks:
                 rt.plan.forward(li, b.q[r0:r1], mask, n, P, rt.pad_len, b.attn[r0:r1])
             if lp and 'o' in lp:
-                x, parts, resid_in = None, lp['o'].run(64), b.resid
+                o = lp['o'].run(64)
+                x, parts, resid_in = (o, None, b.resid) if lp['o'].splits == 1 else (None, o, b.resid)
             else:
                 x, parts, resid_in = torch.mm(b.attn, a.o_proj.weight.t()), None, b.resid
             norm(layer.post_attention_layernorm.weight)

@@ -271,6 +271,23 @@ def test_gemm_weight_streaming(N, K, split):
         torch.cuda.synchronize()
         assert torch.equal(o1, o2)
         assert torch.allclose(o1.float(), ref, atol=2e-2, rtol=1.6e-2), (o1.float() - ref).abs().max().item()
+        # cluster split-K: 2 / 4 K splits of a tile reduce through DSMEM in split order; bf16 out, deterministic
+        for cs in (2, 4):
+            if K // 64 < cs:
+                continue
+            for tiled, wt in ((True, ops.tile_weight(w)), (False, w)):
+                gc = ops.Gemm(wt, x, split_k=-cs, tiled=tiled)
+                assert gc.splits == 1
+                c1 = gc.run(64).clone()
+                c2 = gc.run(64).clone()
+                torch.cuda.synchronize()
+                assert torch.equal(c1, c2)
+                assert torch.allclose(c1.float(), ref, atol=2e-2, rtol=1.6e-2), (cs, (c1.float() - ref).abs().max().item())
+            oc = gc.out
+            oc.fill_(7.0)
+            gc.run(5)
+            torch.cuda.synchronize()
+            assert torch.allclose(oc[:5].float(), ref[:5], atol=2e-2, rtol=1.6e-2) and float(oc[5:].float().min()) == 7.0
     if g.splits == 1:
         got = out.float()
     else:
