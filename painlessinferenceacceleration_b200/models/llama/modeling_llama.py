@@ -207,7 +207,7 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             plans['qkv'] = self._mk_gemm(layer.self_attn.qkv_weight, b.y, split_k=-2)
         if 'o' in want:
             plans['o'] = self._mk_gemm(layer.self_attn.o_proj.weight.data, b.attn, split_k=sk)
-        if 'down' in want:
+        if 'down' in want and layer.mlp.down_proj.weight.shape[1] % 64 == 0 and layer.mlp.down_proj.weight.shape[1] >= 64 * abs(sk):
             plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=sk)
         return plans
 
