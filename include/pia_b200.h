@@ -187,6 +187,11 @@ typedef struct pia_gemm_plan pia_gemm_plan_t;
  * (W.view(N/128,128,K/64,64).permute(0,2,1,3)), so that every CTA streams one contiguous slab of HBM. */
 int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d_x, int x_rows, int split_k, int w_tiled,
                          pia_gemm_plan_t **out);
+/* Grouped GEMM, one launch for all MoE experts (mixtral/modeling_mixtral.py:692-759): for g in [0, groups):
+ *   out[g] ([64, N] bf16, consecutive) = X[:, g*K : (g+1)*K] @ W[g]^T,   W : [groups * N, K] bf16 row-major (the stacked
+ * expert weights), X : [x_rows >= 64, groups * K] bf16.  N % 128 == 0, K % 64 == 0.  Run with pia_gemm_run. */
+int pia_gemm_plan_create_grouped(const void *d_w, int groups, int N, int K, const void *d_x, int x_rows,
+                                 pia_gemm_plan_t **out);
 int pia_gemm_plan_destroy(pia_gemm_plan_t *g);
 int pia_gemm_plan_splits(const pia_gemm_plan_t *g);
 /* fused SiLU(gate) * up epilogue (modeling_llama.py:185-186): the weight must be laid out so that every 128-row tile
@@ -222,6 +227,12 @@ int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *
 /* embedding gather for the draft nodes: d_out[i] = table[d_ids[i]] (rows >= *d_n are zero filled) */
 int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d_n, int rows, int hidden, void *d_out,
                      void *stream);
+/* MoE combine (mixtral/modeling_mixtral.py:734-759, dense restatement): d_out[t] = sum_e d_expert_out[e][t] * w[t][e]
+ * in expert-index order, product and partial sums rounded to bf16 as the eager bf16 loop does.
+ * d_expert_out : [n_experts, rows_cap, hidden] bf16; d_weights : [rows, n_experts] bf16 routing weights (0 = expert not
+ * selected by that token); d_out : [rows, hidden] bf16. */
+int pia_moe_combine(const void *d_expert_out, const void *d_weights, int n_experts, int rows, int rows_cap, int hidden,
+                    void *d_out, void *stream);
 /* L2 prefetch of immutable weights (no reference counterpart: the reference's eager loop leaves HBM idle while the
  * small kernels of a layer - RoPE, attention, norms - run; modeling_llama.py:272-292 sits between the qkv and the o
  * projection).  Issues cp.async.bulk.prefetch.L2 for n_ranges ranges of range_bytes (multiple of 16) that start

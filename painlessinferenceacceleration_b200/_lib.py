@@ -72,6 +72,7 @@ SYMBOLS = {
     'pia_rmsnorm': (C.c_int, [vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     'pia_rmsnorm_partials': (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     'pia_gemm_plan_create': (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    'pia_gemm_plan_create_grouped': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(vp)]),
     'pia_gemm_plan_destroy': (C.c_int, [vp]),
     'pia_gemm_plan_splits': (C.c_int, [vp]),
     'pia_gemm_plan_set_silu': (C.c_int, [vp, C.c_int]),
@@ -80,6 +81,7 @@ SYMBOLS = {
                                      C.c_int, vp, vp, vp, C.c_int, vp]),
     'pia_silu_mul': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     'pia_embed_gather': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
+    'pia_moe_combine': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     'pia_l2_prefetch': (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, vp]),
     'pia_accept': (C.c_int, [C.POINTER(AcceptConfig), vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp,
                              vp, vp, vp, vp]),

@@ -73,6 +73,21 @@ class Gemm(object):
         else:
             self.out = torch.empty((self.splits, 64, N), dtype=torch.float32, device=weight.device)
 
+    @classmethod
+    def grouped(cls, weight, x):
+        """one launch for all experts: weight [G, N, K] (stacked, contiguous), x [rows >= 64, G * K];
+        out [G, 64, N] bf16 (pia_gemm_plan_create_grouped)"""
+        G, N, K = weight.shape
+        assert weight.is_contiguous() and x.is_contiguous() and x.shape[1] == G * K
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.h = L.vp()
+        with torch.cuda.device(weight.device):
+            L.check(self.lib.pia_gemm_plan_create_grouped(_p(weight), G, N, K, _p(x), x.shape[0], C.byref(self.h)))
+        self.splits, self.N, self.weight, self._keep = 1, N, weight, (weight, x)
+        self.out = torch.empty((G, 64, N), dtype=torch.bfloat16, device=weight.device)
+        return self
+
     def set_silu(self, on=True):
         L.check(self.lib.pia_gemm_plan_set_silu(self.h, int(on)))
         return self
@@ -102,6 +117,14 @@ def rope_kv_append(qkv, mask, n, prefix_len, pad_len, n_q_heads, n_kv_heads, hea
 def silu_mul(gate_up, out):
     rows, two_inter = gate_up.shape
     L.check(L.load().pia_silu_mul(_p(gate_up), rows, two_inter // 2, _p(out), _s()))
+
+
+def moe_combine(expert_out, weights, out):
+    """out[t] = sum_e expert_out[e, t] * weights[t, e] in expert order, bf16 rounding per step (pia_moe_combine)"""
+    E, rows_cap, hidden = expert_out.shape
+    rows = weights.shape[0]
+    assert weights.shape[1] == E and weights.is_contiguous() and expert_out.is_contiguous() and out.shape[0] >= rows
+    L.check(L.load().pia_moe_combine(_p(expert_out), _p(weights), E, rows, rows_cap, hidden, _p(out), _s()))
 
 
 def l2_prefetch(t, n_ranges=1, stride_bytes=0, range_bytes=None, gbytes_per_s=0.0, offset_bytes=0):

@@ -228,6 +228,41 @@ extern "C" int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_
   return PIA_OK;
 }
 
+// MoE combine (mixtral/modeling_mixtral.py:734-759 restated densely): out[t] = sum over experts e, in expert-index
+// order, of ye[e][t] * w[t][e]; the product and every partial sum are rounded to bf16 like the eager bf16 loop
+// (`final_hidden_states.index_add_`), w = 0 for the experts a token did not select.  grid = rows, thread = 8 columns.
+__global__ void __launch_bounds__(256) k_moe_combine(const __nv_bfloat16 *ye, const __nv_bfloat16 *w, int n_exp, int rows_cap,
+                                                     int hidden, __nv_bfloat16 *out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x;
+  for (int v = threadIdx.x; v * 8 < hidden; v += blockDim.x) {
+    Pack8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.h[j] = __float2bfloat16_rn(0.f);
+    for (int e = 0; e < n_exp; ++e) {
+      const float we = __bfloat162float(w[(long long)t * n_exp + e]);
+      Pack8 y;
+      y.u = *reinterpret_cast<const uint4 *>(ye + ((long long)e * rows_cap + t) * hidden + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc.h[j] = __float2bfloat16_rn(__bfloat162float(acc.h[j]) + bf(__bfloat162float(y.h[j]) * we));
+    }
+    *reinterpret_cast<uint4 *>(out + (long long)t * hidden + v * 8) = acc.u;
+  }
+}
+
+extern "C" int pia_moe_combine(const void *d_expert_out, const void *d_weights, int n_experts, int rows, int rows_cap,
+                               int hidden, void *d_out, void *stream) {
+  PIA_REQUIRE(d_expert_out && d_weights && d_out && n_experts > 0 && rows > 0 && rows <= rows_cap && hidden % 8 == 0,
+              "bad combine arguments");
+  PIA_CUDA_CHECK(launch_kernel(k_moe_combine, dim3(rows), dim3(256), 0, (cudaStream_t)stream,
+                              (const __nv_bfloat16 *)d_expert_out, (const __nv_bfloat16 *)d_weights, n_experts, rows_cap,
+                              hidden, (__nv_bfloat16 *)d_out));
+  count_launch();
+  return PIA_OK;
+}
+
 // One warp per SM walks the ranges chunk by chunk (the bulk-prefetch issue rate of a single SM's TMA unit is only a
 // few hundred GB/s, so the chunks are dealt round-robin over the whole grid); bytes_per_ns paces the grid against
 // %globaltimer so that the demand loads of the kernels running beside it (attention's KV tiles) are not queued behind

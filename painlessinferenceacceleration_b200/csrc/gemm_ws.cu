@@ -116,6 +116,9 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TOK 
 
 struct Params {
   int N, K, n_split, chunks_per_split, n_chunks, rows, tiled;
+  int groups, w_group_rows, x_group_chunks;  // grouped GEMM (gridDim.z = groups): group g uses weight rows
+                                             // [g*w_group_rows, +N) and activation columns [g*x_group_chunks*64, +K)
+  long long out_group_stride;                // elements between the groups' [rows_cap, N] outputs
   int cluster;              // > 1: the K splits of a tile are one thread-block cluster and reduce through DSMEM (bf16 out)
   int silu;                 // 1: tile rows are 64 gate rows + 64 up rows of the same columns -> out = silu(g) * u
   __nv_bfloat16 *out_bf16;  // [rows_cap, N]  (or [rows_cap, N/2] with silu)   (n_split == 1)
@@ -138,6 +141,8 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
   // grid = (tiles, splits), or (splits, tiles) when the splits of a tile form a cluster (clusters run along x)
   const int tile = p.cluster ? blockIdx.y : blockIdx.x, split = p.cluster ? blockIdx.x : blockIdx.y;
   const int n0 = tile * BMW;
+  const int grp = blockIdx.z;  // 0 unless the plan is a grouped GEMM (one group = one MoE expert)
+  const int xk0 = grp * p.x_group_chunks;
   const int c0 = split * p.chunks_per_split;
   int c1 = c0 + p.chunks_per_split;
   if (c1 > p.n_chunks) c1 = p.n_chunks;
@@ -166,7 +171,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       auto load_w = [&](int i, int s) {
         const uint32_t wd = base + s * STAGE_BYTES;
         if (p.tiled) tma_load_3d(wd, &map_w, bar_full + 8 * s, 0, 0, tile * p.n_chunks + c0 + i);
-        else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, n0);
+        else tma_load_2d(wd, &map_w, bar_full + 8 * s, (c0 + i) * BK, grp * p.w_group_rows + n0);
       };
       const int pre = nch < NSTAGE ? nch : NSTAGE;
       for (int i = 0; i < pre; ++i) {  // all stages start empty
@@ -174,13 +179,13 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
         load_w(i, i);
       }
       pdl_wait();
-      for (int i = 0; i < pre; ++i) tma_load_2d(base + i * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * i, (c0 + i) * BK, 0);
+      for (int i = 0; i < pre; ++i) tma_load_2d(base + i * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * i, (xk0 + c0 + i) * BK, 0);
       for (int i = pre; i < nch; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         load_w(i, s);
-        tma_load_2d(base + s * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * s, (c0 + i) * BK, 0);
+        tma_load_2d(base + s * STAGE_BYTES + W_BYTES, &map_x, bar_full + 8 * s, (xk0 + c0 + i) * BK, 0);
       }
     }
     __syncwarp();
@@ -241,6 +246,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
         const int qpt = RS / 8;                     // token quads per thread: 16 / (128 / RS)
         const int n_out = n0 + split * RS + rl;     // this CTA's rank in the cluster == its split index
         const float4 *buf = reinterpret_cast<const float4 *>(sm);
+        __nv_bfloat16 *ob = p.out_bf16 + grp * p.out_group_stride;
         if (n_out < p.N) {
           for (int tq = tg * qpt; tq < (tg + 1) * qpt; ++tq) {
             float4 a = buf[(0 * 16 + tq) * RS + rl];
@@ -249,10 +255,10 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
               a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
             }
             const int t0 = 4 * tq;
-            if (t0 < p.rows) p.out_bf16[(long long)t0 * p.N + n_out] = __float2bfloat16_rn(a.x);
-            if (t0 + 1 < p.rows) p.out_bf16[(long long)(t0 + 1) * p.N + n_out] = __float2bfloat16_rn(a.y);
-            if (t0 + 2 < p.rows) p.out_bf16[(long long)(t0 + 2) * p.N + n_out] = __float2bfloat16_rn(a.z);
-            if (t0 + 3 < p.rows) p.out_bf16[(long long)(t0 + 3) * p.N + n_out] = __float2bfloat16_rn(a.w);
+            if (t0 < p.rows) ob[(long long)t0 * p.N + n_out] = __float2bfloat16_rn(a.x);
+            if (t0 + 1 < p.rows) ob[(long long)(t0 + 1) * p.N + n_out] = __float2bfloat16_rn(a.y);
+            if (t0 + 2 < p.rows) ob[(long long)(t0 + 2) * p.N + n_out] = __float2bfloat16_rn(a.z);
+            if (t0 + 3 < p.rows) ob[(long long)(t0 + 3) * p.N + n_out] = __float2bfloat16_rn(a.w);
           }
         }
       }
@@ -286,7 +292,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       if (p.n_split == 1) {
 #pragma unroll
         for (int t = 0; t < TOK; ++t)
-          if (t < p.rows) p.out_bf16[(long long)t * p.N + n] = __float2bfloat16_rn(__uint_as_float(v[t]));
+          if (t < p.rows) p.out_bf16[grp * p.out_group_stride + (long long)t * p.N + n] = __float2bfloat16_rn(__uint_as_float(v[t]));
       } else {
         float *o = p.out_f32 + (long long)split * TOK * p.N;
 #pragma unroll
@@ -564,6 +570,7 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   g->p.chunks_per_split = (n_chunks + split_k - 1) / split_k;
   g->p.n_split = (n_chunks + g->p.chunks_per_split - 1) / g->p.chunks_per_split;
   g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr; g->p.silu = 0;
+  g->p.groups = 1; g->p.w_group_rows = 0; g->p.x_group_chunks = 0; g->p.out_group_stride = 0;
   g->p.cluster = 0;
   if (want_cluster) {
     if (g->p.n_split != want_cluster) { delete g; set_error("K = %d is too short for %d cluster splits", K, want_cluster); return PIA_ERR_INVALID; }
@@ -626,6 +633,38 @@ extern "C" int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on) {
   return PIA_OK;
 }
 
+// Grouped GEMM (MoE experts, mixtral/modeling_mixtral.py:692-759): out[g] = X[:, g*K:(g+1)*K] @ W[g]^T for `groups`
+// stacked weights W [groups*N, K] (row-major) and activations X [x_rows, groups*K]; one launch, gridDim.z = groups.
+extern "C" int pia_gemm_plan_create_grouped(const void *d_w, int groups, int N, int K, const void *d_x, int x_rows,
+                                            pia_gemm_plan_t **out) {
+  PIA_REQUIRE(d_w && d_x && out, "null argument");
+  PIA_REQUIRE(groups >= 1 && groups <= 65535 && N > 0 && N % BMW == 0 && K > 0 && K % BK == 0,
+              "grouped GEMM needs N %% %d == 0 and K %% %d == 0", BMW, BK);
+  PIA_REQUIRE(x_rows >= TOK, "the activation buffer must hold at least %d rows", TOK);
+  PIA_REQUIRE((reinterpret_cast<uintptr_t>(d_w) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0, "operands must be 16-byte aligned");
+  pia_gemm_plan *g = new (std::nothrow) pia_gemm_plan();
+  PIA_REQUIRE(g, "out of host memory");
+  const int n_chunks = K / BK;
+  g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks; g->p.chunks_per_split = n_chunks; g->p.n_split = 1;
+  g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr; g->p.silu = 0; g->p.tiled = 0; g->p.cluster = 0;
+  g->p.groups = groups; g->p.w_group_rows = N; g->p.x_group_chunks = n_chunks; g->p.out_group_stride = (long long)TOK * N;
+  g->stream_k = 0;
+  int rc = encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)groups * N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc == PIA_OK) rc = encode_2d(&g->map_x, d_x, (uint64_t)groups * K, (uint64_t)x_rows, BK, TOK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc == PIA_OK) {
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    g->nstage = (N / BMW) * groups <= n_sm ? 8 : 4;
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_ws<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(8));
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
+  }
+  if (rc != PIA_OK) { delete g; return rc; }
+  *out = g;
+  return PIA_OK;
+}
+
 extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream) {
   PIA_REQUIRE(g && d_out, "null argument");
   PIA_REQUIRE(rows >= 1 && rows <= TOK, "rows %d outside [1,%d]", rows, TOK);
@@ -647,7 +686,7 @@ extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *str
     count_launch();
     return PIA_OK;
   }
-  dim3 grid((p.N + BMW - 1) / BMW, p.n_split);
+  dim3 grid((p.N + BMW - 1) / BMW, p.n_split, p.groups);
   if (g->nstage == 8) PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<8>, grid, dim3(NTHREADS), smem_total(8), (cudaStream_t)stream, g->map_w, g->map_x, p));
   else PIA_CUDA_CHECK(launch_kernel(k_gemm_ws<4>, grid, dim3(NTHREADS), smem_total(4), (cudaStream_t)stream, g->map_w, g->map_x, p));
   count_launch();

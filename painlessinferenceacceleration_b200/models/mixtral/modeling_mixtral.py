@@ -60,7 +60,24 @@ class MixtralForCausalLM(LlamaForCausalLM):
         return g
 
     def _layer_gemm_plans(self, layer, b):
-        return {}
+        """decode steps (64-row buffers): all experts' gate_up as ONE k_gemm_ws launch over the stacked [E*2I, H] weight,
+        SiLU*up over the [64*E, 2I] view, all experts' down projections as one grouped launch, then the routing-weighted
+        sum in expert order.  Dense over experts like the cuBLAS path below: at n = 64 draft rows every expert is hit
+        (SURVEY 8d), and the step is bound by the expert weight bytes either way.  PIA_MOE_GEMM=0 keeps cuBLAS."""
+        import os
+        moe = layer.mlp
+        E, two_i, H = moe.experts.gate_up_proj.shape
+        inter = two_i // 2
+        if os.environ.get('PIA_MOE_GEMM', '1') == '0' or H % 128 or H % 64 or inter % 64 or (E * two_i) % 128:
+            return {}
+        dev = b.y.device
+        if not hasattr(b, 'moe_gu'):
+            b.moe_gu = torch.zeros((b.rows, E * two_i), dtype=torch.bfloat16, device=dev)
+            b.moe_act = torch.zeros((b.rows, E * inter), dtype=torch.bfloat16, device=dev)
+            b.moe_out = torch.zeros((b.rows, H), dtype=torch.bfloat16, device=dev)
+            b.moe_dense = torch.zeros((b.rows, E), dtype=torch.bfloat16, device=dev)
+        return {'moe_gate_up': ops.Gemm(moe.experts.gate_up_proj.data.view(E * two_i, H), b.y),
+                'moe_down': ops.Gemm.grouped(moe.experts.down_proj.data, b.moe_act)}
 
     def _mlp(self, rt, layer, y, plans=None, pf=None):
         moe = layer.mlp
@@ -68,6 +85,16 @@ class MixtralForCausalLM(LlamaForCausalLM):
         probs = torch.softmax(logits.float(), dim=1)                                # :723
         w, sel = torch.topk(probs, moe.top_k, dim=-1)                               # :724
         w = (w / w.sum(dim=-1, keepdim=True)).to(y.dtype)                           # :725-727
+        if plans:
+            b = rt.decode_bufs
+            E = moe.num_experts
+            inter = moe.experts.down_proj.shape[2]
+            b.moe_dense.zero_().scatter_(1, sel, w)
+            plans['moe_gate_up'].run(64, out=b.moe_gu)
+            ops.silu_mul(b.moe_gu.view(b.rows * E, 2 * inter), b.moe_act.view(b.rows * E, inter))
+            ye = plans['moe_down'].run(64)                                          # [E, 64, H]
+            ops.moe_combine(ye, b.moe_dense, b.moe_out)
+            return b.moe_out, None
         dense = torch.zeros((y.shape[0], moe.num_experts), dtype=y.dtype, device=y.device).scatter_(1, sel, w)
         out = torch.zeros_like(y)
         inter = moe.experts.down_proj.shape[2]

@@ -354,3 +354,30 @@ def test_l2_prefetch_is_a_pure_hint():
         ops.l2_prefetch(w, range_bytes=100)                 # not a multiple of 16
     with pytest.raises(Exception):
         ops.l2_prefetch(w, n_ranges=2, stride_bytes=16, range_bytes=64)   # overlapping ranges
+
+
+def test_grouped_gemm_and_moe_combine():
+    """all experts in one launch (pia_gemm_plan_create_grouped) + the routing-weighted sum in expert order
+    (pia_moe_combine) vs the eager per-expert loop (mixtral/modeling_mixtral.py:734-759, dense restatement)"""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(5)
+    E, N, K, R = 4, 256, 320, 64
+    w = (torch.randn((E, N, K), device=DEV) * 0.05).to(torch.bfloat16)
+    x = torch.randn((R, E * K), device=DEV).to(torch.bfloat16)
+    g = ops.Gemm.grouped(w, x)
+    ye = g.run(64)
+    torch.cuda.synchronize()
+    assert ye.shape == (E, 64, N)
+    for e in range(E):
+        ref = x[:, e * K:(e + 1) * K].float() @ w[e].float().t()
+        assert torch.allclose(ye[e].float(), ref, atol=2e-2, rtol=1.6e-2), (e, (ye[e].float() - ref).abs().max().item())
+    dense = torch.zeros((R, E), device=DEV, dtype=torch.bfloat16)
+    sel = torch.stack([torch.randperm(E, device=DEV)[:2] for _ in range(R)])
+    dense.scatter_(1, sel, torch.rand((R, 2), device=DEV).to(torch.bfloat16))
+    out = torch.empty((R, N), dtype=torch.bfloat16, device=DEV)
+    ops.moe_combine(ye, dense, out)
+    ref = torch.zeros((R, N), dtype=torch.bfloat16, device=DEV)
+    for e in range(E):
+        ref += ye[e] * dense[:, e:e + 1]
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
