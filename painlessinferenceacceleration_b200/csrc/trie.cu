@@ -506,6 +506,7 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
   const Node p = D.nodes[parent];
   const int C = p.n_child;
   int m = 0;  // current size of the running top list (uniform)
+  bool pool_stale = true;  // S->pool_n != m (uniform)
   constexpr int U = 2;  // child chunks whose records are fetched together (memory-level parallelism on wide nodes)
   for (int base = 0; base < C; base += NT * U) {
     int cid[U];
@@ -522,7 +523,9 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (base + u * NT >= C) break;  // uniform
-      if (tid == 0) S->pool_n = m;
+      // pool_n is only rewritten when it differs from m: after a chunk that added nothing it still equals m, and the
+      // other threads may not have read it yet (no barrier on that path)
+      if (pool_stale && tid == 0) S->pool_n = m;
       __syncthreads();
       const int i = base + u * NT + tid;
       if (cid[u] >= 0) {
@@ -548,7 +551,8 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
       }
       __syncthreads();
       const int total = S->pool_n;
-      if (total == m) continue;  // nothing new (uniform): the running list stands
+      if (total == m) { pool_stale = false; continue; }  // nothing new (uniform): the running list stands
+      pool_stale = true;
       // rank every pool element; the first K in (key desc, ord asc) order survive
       for (int e = tid; e < total; e += NT) {
         const unsigned long long k = S->pkey[e];
