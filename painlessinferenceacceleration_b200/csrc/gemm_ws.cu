@@ -153,6 +153,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();  // warp 0 reconverges before the block barrier below
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -356,6 +357,7 @@ k_gemm_sk(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     mbar_init(bar_acc_empty, 128); mbar_init(bar_acc_empty + 8, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();  // warp 0 reconverges before the block barrier below
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(SK_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");

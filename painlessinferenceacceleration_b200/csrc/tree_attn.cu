@@ -251,6 +251,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     mbar_init(bar_q_full, 2 * rows_used);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncwarp();  // warp 0 reconverges before the (warp-aligned) block barrier below (synccheck: divergent lane 0)
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
