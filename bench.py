@@ -91,11 +91,14 @@ class ClockSampler(threading.Thread):
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source): the pool's measured numbers (MEASURED_PEAKS.json, driver-written) or the
+    fallback B200_PROFILING.md states"""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(p):
+    try:
         d = json.load(open(p))
-        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d['bf16_tflops'])), 'measured'
-    return 6650.0, 1400.0, 'fallback'
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0))), 'measured'
+    except (OSError, ValueError, KeyError, TypeError):
+        return 6650.0, 1400.0, 'fallback'
 
 
 # ----------------------------------------------------------------------------------------------- our arm
