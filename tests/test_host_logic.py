@@ -96,3 +96,23 @@ def test_replica_sharding_and_aggregation_gloo_world2(tmp_path):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert 'OK 11.0 1536.0' in out.stdout
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """bench.py --impl reference under the driver's N>1 launch: rank 0 alone runs the CPU path (oracle loop + oracle
+    trie on the tiny shape here) and prints the one JSON line with its cpu_baseline / e2e objects; the other rank
+    exits 0 without output"""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29573', os.path.join(root, 'bench.py'),
+                          '--impl', 'reference', '--model', 'tiny', '--gpus', '2', '--steps', '2', '--warmup', '1'],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['steps'] == 2 and d['unit'] == 'tokens/s'
+    assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['mean_accepted_len_per_step'] >= 1.0
