@@ -50,3 +50,30 @@ def test_left_padding_and_max_length():
     assert a['sequences'].tolist() == b['sequences'].tolist()
     assert a['sequences'].shape[1] <= 12 + 20
     assert max(b['edls']) > 1  # second run drafts the first run's output from the trie
+
+
+@pytest.mark.parametrize('family,mseed,pseed', [('llama', 3, 16), ('llama', 4, 17), ('mistral', 2, 15)])
+def test_batched_loop_is_lossless_fp32(family, mseed, pseed):
+    """oracle/loop_batch.py (pretrained_model_batch.py:664-1330 restated): every request of a batch yields
+    exactly the tokens plain greedy decoding yields for it; per-slot trie input/output puts, bat_get drafts of
+    decoding_length // active requests, requests leaving the batch as they finish (the seeds give requests of
+    different lengths: some end on eos early, some run to max_length).
+    Token id 0 must not occur in the answers: `ids[0] = match_token_id or self.token_id` (lookahead_cache.py:129)
+    replaces a root token 0 by the tree's key token - a quirk of the reference that both restatements and the CUDA
+    trie keep, and that breaks the lossless property for that (in real vocabularies never generated) id."""
+    from oracle.loop_batch import lookahead_generate_batch
+    torch.set_num_threads(4)
+    model = tiny_hf_model(family, seed=mseed)
+    trie = OracleLookaheadCache(eos_ids=[2])
+    ps = prompts(pseed, 3, 12, 64)
+    batch = torch.cat(ps, 0)
+    refs = [greedy_generate(model, p, max_new_tokens=30)['sequences'][0].tolist() for p in ps]
+    assert all(0 not in r[12:] for r in refs)
+    for rep in range(2):
+        out = lookahead_generate_batch(model, trie, batch, max_new_tokens=30, decoding_length=48, branch_length=6)
+        for b in range(3):
+            got = out['sequences'][b, :out['lengths'][b]].tolist()
+            assert got == refs[b], (family, rep, b, got, refs[b])
+        assert sum(out['edls']) == sum(out['lengths']) - 3 * 12
+        if rep == 1:  # the second pass drafts the first pass's answers from the per-slot output tries
+            assert max(out['edls']) > 1, out['edls']
