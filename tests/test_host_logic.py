@@ -116,3 +116,21 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['mean_accepted_len_per_step'] >= 1.0
+
+
+def test_bench_helpers_traffic_lookup_and_cpu_summary():
+    """bench.py host helpers: roofline.traffic comes from the newest committed ncu summary whose capture name and
+    kernel match; the CPU arms' summary extrapolates bounded samples to a full 256 -> 256 request"""
+    import bench
+    t = bench.ncu_traffic('prof_attn_short', 'k_tree_attn')
+    assert t is not None and 1e6 < t < 1e9
+    assert bench.ncu_traffic('no_such_capture', 'k_tree_attn') is None
+    # two samples: (tokens, seconds, edls, per-forward seconds); prefill 1 s for S = 64 prompt tokens, 0.5 s per verify step
+    smp = [(8, 2.0, [1, 4, 4], [1.0, 0.5, 0.5]), (6, 2.0, [1, 3, 3], [1.0, 0.5, 0.5])]
+    toks, secs, edls, extra = bench.cpu_summary(64, smp)
+    assert toks == 14 and secs == 4.0 and edls == [4, 4, 3, 3]
+    full = bench.NEW_TOKENS / (1.0 * bench.PROMPT_LEN / 64 + bench.NEW_TOKENS / 3.5 * 0.5)
+    assert abs(extra['full_request_tokens_per_s_extrapolated'] - full) < 1e-9
+    assert extra['prefill_s'] == 1.0 and extra['verify_step_s'] == 0.5
+    hbm, tf, src = bench.peaks()
+    assert hbm > 1000 and tf > 100 and src in ('measured', 'fallback')
