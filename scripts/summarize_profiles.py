@@ -47,7 +47,7 @@ def launch_list(path, name):
                 '| kernel | launches | total us | share |', '|---|---:|---:|---:|']
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             out.append(f'| `{k}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% |')
-        own = sum(r[2] for r in seg if re.search(r'\b(gemm|attn|fused|trie|accept)::k_', r[1]))
+        own = sum(r[2] for r in seg if re.search(r'\b(gemm|attn|fused|trie|accept)::k_|\bk_(moe_combine|l2_prefetch)\b', r[1]))
         blas = sum(r[2] for r in seg if 'nvjet' in r[1] or 'cutlass' in r[1] or 'gemv' in r[1])
         out += ['', f'own kernels (libpia_b200, `pia::*`): {100 * own / tot:.1f}% of the step; cuBLAS GEMMs (`nvjet_*`): '
                     f'{100 * blas / tot:.1f}%; other (torch elementwise): {100 * (tot - own - blas) / tot:.1f}%']
