@@ -488,6 +488,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
           st_cluster_f4(dst + (uint32_t)(j * mrg_stride) * 16, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         if (half == 0) st_cluster_f2(map_to_cta(base + mrg_ml + (uint32_t)(split * RS + rl) * 8, owner), m_run, l_run);
       }
+      __syncwarp();  // the live-row branch above diverges; the cluster barrier is warp-aligned
       cluster_sync_all();
     }
     if (row == 0 && half == 0) DBG(10);
