@@ -134,3 +134,21 @@ def test_bench_helpers_traffic_lookup_and_cpu_summary():
     assert extra['prefill_s'] == 1.0 and extra['verify_step_s'] == 0.5
     hbm, tf, src = bench.peaks()
     assert hbm > 1000 and tf > 100 and src in ('measured', 'fallback')
+
+
+def test_weight_layout_helpers_are_permutations():
+    """ops.tile_weight ([N, K] -> [N/128, K/64, 128, 64] blocks, the unit k_gemm_ws' TMA box moves) and
+    ops.interleave_gate_up (64 gate rows + the 64 up rows of the same columns per 128-row tile) only permute rows /
+    blocks: every element survives exactly once (CPU tensors, no library call)"""
+    from painlessinferenceacceleration_b200.common import ops
+    w = torch.arange(256 * 192, dtype=torch.float32).view(256, 192).to(torch.bfloat16)
+    t = ops.tile_weight(w)
+    assert t.shape == (2, 3, 128, 64) and t.pia_shape == (256, 192) and t.is_contiguous()
+    assert torch.equal(t.permute(0, 2, 1, 3).reshape(256, 192), w)
+    assert torch.equal(t[1, 2], w[128:256, 128:192])
+    gu = torch.arange(512 * 64, dtype=torch.float32).view(512, 64)
+    il = ops.interleave_gate_up(gu)
+    assert il.shape == gu.shape
+    assert torch.equal(il[0:64], gu[0:64]) and torch.equal(il[64:128], gu[256:320])
+    assert torch.equal(il[128:192], gu[64:128]) and torch.equal(il[192:256], gu[320:384])
+    assert torch.equal(il.sort(0).values, gu.sort(0).values)
