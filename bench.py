@@ -245,13 +245,14 @@ def attention_roofline(model, dev):
     P, n = PROMPT_LEN + NEW_TOKENS // 2, DL
     rt.n.fill_(n)
     rt.prefix_len.fill_(P)
-    rt.mask[0].copy_(rt.chain if hasattr(rt, 'chain') else rt.chain_mask_rows())
+    rt.pad.zero_()
+    rt.mask.copy_(rt.chain)
     L = P + n
     reps = 20
 
     def sweep():
         for li in range(g['n_layers']):
-            rt.plan.forward(li, rt.q, rt.mask[0], rt.n, rt.prefix_len, 0, rt.attn)
+            rt.plan.forward(li, rt.q, rt.mask, rt.decode_bufs.slots, rt.attn)
 
     sweep()
     torch.cuda.synchronize()
@@ -291,12 +292,12 @@ def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
     plan = ops.AttnPlan(kc, vc, hq, hkv, D, R)
     rows = np.array([(1 << (i + 1)) - 1 if i < 63 else 0xFFFFFFFFFFFFFFFF for i in range(R)], dtype=np.uint64)
     mask = torch.from_numpy(rows.view(np.int64)).to(dev).view(R, 1)
-    dn = torch.tensor([n], dtype=torch.int32, device=dev)
-    dP = torch.tensor([P], dtype=torch.int32, device=dev)
+    slots = ops.Slots(torch.tensor([n], dtype=torch.int32, device=dev), torch.tensor([P], dtype=torch.int32, device=dev),
+                      None, R)
 
     def sweep():
         for li in range(layers):
-            plan.forward(li, q, mask, dn, dP, 0, out)
+            plan.forward(li, q, mask, slots, out)
 
     sweep()
     torch.cuda.synchronize()
@@ -346,7 +347,7 @@ def trie_roofline(dev, n_docs=1500, n_queries=4096):
 
     def launch():
         L.check(t.lib.pia_trie_get(t.h, dq.data_ptr(), dl.data_ptr(), n_queries, 2, 2, None, 0, 64, 8, 0, 32,
-                                   L.MODE['mix'], L.GET_HIER, 0, 0, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                   L.MODE['mix'], L.GET_HIER, 0, 0, None, o['ids'].data_ptr(), o['mask'].data_ptr(),
                                    o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
                                    o['status'].data_ptr(), t.stream()))
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PIA_ABI_VERSION 1
+#define PIA_ABI_VERSION 2
 
 typedef enum {
   PIA_OK = 0,
@@ -93,16 +93,19 @@ int pia_trie_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d
                  int idx, int final, void *stream);
 /* Tree.put (lookahead_cache.py:33-63) on the tree keyed by `tree_token` alone (created when absent). */
 int pia_trie_tree_put(pia_trie_t *t, int tree_token, const int32_t *d_tokens, int n, int mode, int idx, void *stream);
-/* LookaheadCache.stream_put (lookahead_cache.py:375-406); the per-idx carry buffer lives on the device. */
+/* LookaheadCache.stream_put (lookahead_cache.py:375-406); the per-idx carry buffer lives on the device.
+ * d_idx != NULL: the request idx is read on the device (*d_idx, must be in [0, n_input_slots)) instead of `idx` -
+ * the batched loop's slot -> request map changes as requests finish (pretrained_model_batch.py:937-980). */
 int pia_trie_stream_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n, int branch_length, int idx,
-                        int final, void *stream);
+                        const int32_t *d_idx, int final, void *stream);
 
 /* LookaheadCache.hier_get / one_get -> Tree.get / get_one_branch (lookahead_cache.py:408-439, 490-517,
  * 65-144, 171-222), `batch` independent queries in one launch.
  *   d_queries : [batch, q_stride] int32;  d_qlen : [batch] valid tokens per row
  *   d_idx     : [batch] request idx per row, or NULL -> `idx` for all rows
  *   max_seq_length > 0 (PIA_GET_TAIL only): branch_length is clamped on the device to
- *               min(branch_length, max_seq_length - len - 1)   (pretrained_model.py:680)
+ *               min(branch_length, max_seq_length - len - 1)   (pretrained_model.py:680);
+ *               d_max_seq_length != NULL: the limit is read on the device (one CUDA graph for every max_length)
  * outputs (per row b):
  *   d_out_ids  [batch, decoding_length] ; d_out_mask [batch, decoding_length, W], W = ceil(decoding_length/64)
  *   d_out_n    [batch] number of nodes incl. the root (>= 1 unless the query was empty)
@@ -111,8 +114,8 @@ int pia_trie_stream_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int
 int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32_t *d_qlen, int batch, int q_stride,
                  int max_query_length, const int32_t *d_idx, int idx, int decoding_length, int branch_length,
                  int min_input_size, int min_output_size, int mode, int kind, int flags, int max_seq_length,
-                 int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n, int32_t *d_out_sizes,
-                 int32_t *d_out_nsizes, int32_t *d_status, void *stream);
+                 const int32_t *d_max_seq_length, int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n,
+                 int32_t *d_out_sizes, int32_t *d_out_nsizes, int32_t *d_status, void *stream);
 
 /* reset_input_freqs :566-570 ; squeeze_branch_counts :572-576 ; fresh :563-564 */
 int pia_trie_reset_input_freqs(pia_trie_t *t, int idx, void *stream);
@@ -135,6 +138,30 @@ int pia_trie_import(pia_trie_t *t, const void *h_nodes, int64_t n_nodes, const v
                     const int32_t *h_root_of, const int32_t *h_n_node, const int32_t *h_n_out, void *stream);
 
 /* ============================================================================================
+ * Request slots of one verify step.
+ *   - the per-request loop (common/pretrained_model.py:947-1268, bs == 1 :1152) runs ONE slot;
+ *   - the batched loop (common/pretrained_model_batch.py:1002-1330) runs one slot per active request: every request
+ *     drafts decoding_length // active nodes (:713), so all slots together still fill <= max_nodes activation rows;
+ *   - a prefill pass runs one slot per 64-row chain chunk of the same prompt (kv_slot_stride == 0: the chunks share
+ *     one cache and chunk c sees the rows chunk c-1 appended).
+ * Slot s owns rows [s * rows_per_slot, (s + 1) * rows_per_slot) of every activation buffer (qkv, q, attention out,
+ * logits) and of the draft buffers (ids, mask rows); its KV cache starts kv_slot_stride elements after slot s-1's.
+ * All arrays are DEVICE memory read at kernel run time, so one captured CUDA graph serves every prompt length,
+ * padding and max_length.
+ * ============================================================================================ */
+typedef struct {
+  int32_t batch;                /* number of slots, >= 1                                                       */
+  int32_t rows_per_slot;        /* rows reserved per slot; batch * rows_per_slot <= rows of the buffers        */
+  const int32_t *d_n;           /* [batch] live draft nodes of the slot (<= rows_per_slot; 0 = idle slot)       */
+  const int32_t *d_prefix_len;  /* [batch] P: tokens of the slot already in its KV cache                        */
+  const int32_t *d_pad_len;     /* [batch] left-pad columns [0, pad) masked for every row (:1123-1131); NULL = 0 */
+  int64_t kv_slot_stride;       /* elements between the [n_layers, n_kv_heads, max_seq, head_dim] caches of
+                                   consecutive slots (0: all slots address the same cache)                     */
+  int32_t kv_first_slot;        /* TMA-addressed kernels (pia_tree_attn_fwd): cache index slot 0 addresses; the
+                                   pointer-addressed ones take the pointer of that cache instead               */
+} pia_slots_t;
+
+/* ============================================================================================
  * Tree-masked attention (verify forward)
  *   models/llama/modeling_llama.py:584-588 (mask -> positions) and :243-308 (eager attention);
  *   mistral/modeling_mistral.py:979-982,241-320; pretrained_model.py:725-734 (mask builder).
@@ -149,9 +176,10 @@ typedef struct {
   int32_t max_nodes;                       /* 64 (W=1) or 128 (W=2)                                  */
   int32_t n_layers;
   int32_t kv_split_max;                    /* upper bound of KV splits per head (0 = auto)            */
+  int32_t n_slots;                         /* KV caches behind the plan (0/1 = one; batched loop: one per request) */
 } pia_attn_config_t;
 
-/* d_k_cache / d_v_cache : [n_layers, n_kv_heads, max_seq, head_dim] bf16, owned by the caller for the
+/* d_k_cache / d_v_cache : [n_slots, n_layers, n_kv_heads, max_seq, head_dim] bf16, owned by the caller for the
  * plan's lifetime (TMA descriptors are encoded over them). Synchronous; not capturable. */
 int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cache, void *d_v_cache, pia_attn_plan_t **out);
 int pia_attn_plan_destroy(pia_attn_plan_t *p);
@@ -160,16 +188,15 @@ int pia_attn_plan_destroy(pia_attn_plan_t *p);
 int pia_attn_plan_set_debug(pia_attn_plan_t *p, void *d_timestamps);
 int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n_groups);
 
-/* One layer of tree attention over the cache (rows [0, P+n) must already hold K/V, RoPE applied).
- *   d_q    : [max_nodes, n_q_heads, head_dim] bf16 (rows >= n ignored)
- *   d_mask : [max_nodes, W] uint64 ancestor rows;  d_n : device int, number of draft nodes
- *   d_prefix_len : device int P (tokens already in the cache before this step's nodes)
- *   pad_len : left-pad columns [0, pad_len) are masked for every row (pretrained_model.py:1123-1131)
- *   d_out  : [max_nodes, n_q_heads, head_dim] bf16
+/* One layer of tree attention over the cache(s), every slot of the table in one launch (gridDim.z = slot; rows
+ * [P_s, P_s + n_s) of slot s's cache must already hold this step's K/V, RoPE applied).
+ *   d_q    : [batch * rows_per_slot, n_q_heads, head_dim] bf16 (rows >= n_s of a slot are ignored and not written)
+ *   d_mask : [batch * rows_per_slot, W] uint64 ancestor rows (bit j = draft node j of the SAME slot)
+ *   d_out  : [batch * rows_per_slot, n_q_heads, head_dim] bf16
  * softmax scale = 1/sqrt(head_dim) * `scale_mul` (1.0 for the reference models).  Needs no workspace: KV splits are
  * merged through the distributed shared memory of a thread-block cluster. */
-int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask, const int32_t *d_n,
-                      const int32_t *d_prefix_len, int pad_len, float scale_mul, void *d_out, void *stream);
+int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask, const pia_slots_t *slots,
+                      float scale_mul, void *d_out, void *stream);
 
 /* ============================================================================================
  * Weight-streaming GEMM of the verify forward: Y[t, n] = sum_k X[t, k] W[n, k]  (X: <= 64 draft rows, W = an
@@ -213,15 +240,15 @@ int pia_rmsnorm(const void *d_x, const void *d_residual_in, const void *d_weight
 int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t part_stride, const void *d_residual_in,
                          const void *d_weight, float eps, int rows, int hidden, void *d_residual_out, void *d_y,
                          void *stream);
-/* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; position of node i =
- * max(P - pad_len, 0) + depth_i = rowsum(mask) - 1, :587).  d_qkv : [rows, (Hq + 2*Hkv) * D] bf16 (fused projection
- * output).  d_cos / d_sin : [max_pos, D/2] bf16 tables (cos/sin already rounded to the model dtype exactly as
- * LlamaRotaryEmbedding.forward :111-127 returns them).  Writes q (rotated) to d_q_out [rows, Hq, D] and
- * K (rotated) / V to cache rows P + i of the layer's [Hkv, max_seq, D] planes. */
-int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const int32_t *d_n,
-                       const int32_t *d_prefix_len, int pad_len, int rows, int n_q_heads, int n_kv_heads, int head_dim,
-                       const void *d_cos, const void *d_sin, int max_pos, void *d_q_out, void *d_k_cache_layer,
-                       void *d_v_cache_layer, int max_seq, void *stream);
+/* RoPE at tree positions + KV append (modeling_llama.py:261-268, 93-169; batched: modeling_llama_batch.py:375-405;
+ * position of node i of slot s = max(P_s - pad_s, 0) + depth_i = rowsum(mask) - 1, :587).
+ * d_qkv : [batch * rows_per_slot, (Hq + 2*Hkv) * D] bf16 (fused projection output).  d_cos / d_sin : [max_pos, D/2]
+ * bf16 tables (cos/sin already rounded to the model dtype exactly as LlamaRotaryEmbedding.forward :111-127 returns
+ * them).  Writes q (rotated) to d_q_out [batch * rows_per_slot, Hq, D] and K (rotated) / V to cache rows P_s + i of
+ * the layer's [Hkv, max_seq, D] planes of slot s (d_*_cache_layer + s * kv_slot_stride). */
+int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const pia_slots_t *slots,
+                       int n_q_heads, int n_kv_heads, int head_dim, const void *d_cos, const void *d_sin, int max_pos,
+                       void *d_q_out, void *d_k_cache_layer, void *d_v_cache_layer, int max_seq, void *stream);
 /* SiLU(gate) * up (modeling_llama.py:185-186). d_gate_up : [rows, 2*inter] (gate | up) -> d_out [rows, inter] */
 int pia_silu_mul(const void *d_gate_up, int rows, int inter, void *d_out, void *stream);
 /* embedding gather for the draft nodes: d_out[i] = table[d_ids[i]] (rows >= *d_n are zero filled) */
@@ -252,28 +279,38 @@ typedef struct {
   int32_t max_nodes;
   float repetition_penalty;    /* 1.0 = none                                                     */
   int32_t n_eos; int32_t eos[8];
-  int32_t max_length;          /* generation stops when seq_len >= max_length (MaxLengthCriteria) */
+  int32_t max_length;          /* generation stops when seq_len >= max_length (MaxLengthCriteria); overridden by
+                                  *d_max_length when that pointer is given                          */
+  int32_t bound_walk;          /* 1: the walk accepts at most max_length - seq_len tokens, the batched loop's
+                                  range(-1, min(max_branch_length, max_length - cur - 2)) (pretrained_model_batch.py:862);
+                                  0: unbounded (the per-request loop clamps the draft depth instead, :680) */
 } pia_accept_config_t;
 
-/* Row arg-max of the (penalised) logits of every draft node, then the walk of :827-860.
- *   d_logits : [max_nodes, vocab] bf16 ; d_ids/d_mask/d_n : the draft (as produced by pia_trie_get)
- *   d_seq : [seq_capacity] int32 token sequence (prompt + generated), d_seq_len : its length; the
- *           accepted tokens are appended and *d_seq_len advanced.
- *   d_accept_tokens [max_nodes] accepted tokens (draft matches + bonus); d_accept_count their number (edl)
- *   d_accept_nodes  [max_nodes] draft node index whose logits produced each token (logit_indices :845)
- *   d_prefix_len    : P, advanced to P + count on return
- *   d_finished      : set to 1 when an eos was accepted or max_length reached (:1225-1231)          */
+/* Row arg-max of the (penalised) logits of every draft node, then the walk of :827-860 (batched loop:
+ * pretrained_model_batch.py:810-905), one slot per request (slot layout as pia_slots_t).
+ *   d_logits : [batch * rows_per_slot, vocab] bf16 ; d_ids [batch * rows_per_slot] / d_mask / d_n [batch] : the drafts
+ *   d_seq : [batch, seq_stride] int32 token sequences (prompt + generated), d_seq_len [batch] their lengths; the
+ *           accepted tokens are appended and d_seq_len advanced.
+ *   d_max_length : device int overriding cfg->max_length, or NULL
+ *   d_accept_tokens [batch, cfg->max_nodes] accepted tokens (draft matches + bonus); d_accept_count [batch] (edl)
+ *   d_accept_nodes  [batch, cfg->max_nodes] draft node index (slot relative) whose logits produced each token
+ *                   (logit_indices :845)
+ *   d_prefix_len [batch] : P, advanced to P + count on return
+ *   d_finished   [batch] : set to 1 when an eos was accepted or max_length reached (:1225-1231)
+ * batch * rows_per_slot <= cfg->max_nodes.  A slot with d_n == 0 is idle (count 0). */
 int pia_accept(const pia_accept_config_t *cfg, const void *d_logits, const int32_t *d_ids, const uint64_t *d_mask,
-               int mask_words, const int32_t *d_n, int32_t *d_seq, int32_t *d_seq_len, int seq_capacity, int pad_len,
-               int32_t *d_accept_tokens, int32_t *d_accept_count, int32_t *d_accept_nodes, int32_t *d_prefix_len,
-               int32_t *d_finished, void *d_workspace, void *stream);
+               int mask_words, int batch, int rows_per_slot, const int32_t *d_n, int32_t *d_seq, int32_t *d_seq_len,
+               int seq_stride, const int32_t *d_max_length, int32_t *d_accept_tokens, int32_t *d_accept_count,
+               int32_t *d_accept_nodes, int32_t *d_prefix_len, int32_t *d_finished, void *d_workspace, void *stream);
 int64_t pia_accept_workspace_bytes(const pia_accept_config_t *cfg);
 
-/* KV compaction (pretrained_model.py:863-875, 894-907) in place: cache row P_old + node -> row P_old + k for the
- * k-th accepted draft node, all layers, K and V.  d_prefix_len is the value *after* pia_accept. */
-int pia_kv_compact(void *d_k_cache, void *d_v_cache, int n_layers, int n_kv_heads, int max_seq, int head_dim,
-                   const int32_t *d_accept_nodes, const int32_t *d_accept_count, const int32_t *d_prefix_len,
-                   void *stream);
+/* KV compaction (pretrained_model.py:863-875, 894-907; batched :907-918, 986-989) in place: cache row
+ * P_old + node -> row P_old + k for the k-th accepted draft node, all layers, K and V, every slot.
+ * d_*_cache : [batch (stride kv_slot_stride elements), n_layers, n_kv_heads, max_seq, head_dim];
+ * d_accept_nodes [batch, nodes_stride]; d_prefix_len [batch] holds the values *after* pia_accept. */
+int pia_kv_compact(void *d_k_cache, void *d_v_cache, int n_layers, int n_kv_heads, int max_seq, int head_dim, int batch,
+                   int64_t kv_slot_stride, const int32_t *d_accept_nodes, int nodes_stride,
+                   const int32_t *d_accept_count, const int32_t *d_prefix_len, void *stream);
 
 #ifdef __cplusplus
 }

@@ -17,10 +17,11 @@ Face eager model, rank-4 0/1 mask -> additive mask, positions = row sum - 1): re
 [ones(cursor_b) | its slice of the bat_get mask], which is exactly the columns the batched mask
 cat([full[:, :, min_cur:min_cur+n, :min_cur], decoding_masks]) (:729-731) makes visible to it.
 
-"parity unpinned": like the bs=1 loop, the reference module cannot be imported under transformers 5.5 and ships no
-recorded outputs for this path; the restatement is pinned by the lossless property only (tests/test_oracle_loop.py:
-every request's tokens == plain greedy decoding of the same fp32 model) and by the bat_get golden streams recorded from
-the live reference trie (tests/golden/trie_small_v30_batch.json)."""
+Pinned: tests/golden/batchloop_*.npz hold verify-step records of the reference's OWN batched loop code (imported from
+/root/reference with four unused transformers names stubbed, tests/golden/ref_loop.py) and tests/test_loop_golden.py
+replays them through this restatement: drafts, accepted tokens, dls, edls, the order requests leave the batch and
+the padded output must be identical; plus the lossless property (tests/test_oracle_loop.py) and the bat_get golden
+streams recorded from the live reference trie (tests/golden/trie_small_v30_batch.json)."""
 import numpy as np
 import torch
 
@@ -67,7 +68,7 @@ def _accept_batch(draft_ids, draft_masks, logits, seq, cur, max_length, penalty)
 @torch.no_grad()
 def lookahead_generate_batch(model, trie, input_ids, max_new_tokens=None, max_length=None, eos_token_id=(2,),
                              decoding_length=64, branch_length=8, decoding_mode='hier', repetition_penalty=1.0,
-                             pad_token_id=2, stop_words=None):
+                             pad_token_id=2, stop_words=None, backend_factory=None, trace=False):
     """restates lookahead_generation of the batch variant (:1002-1330) for equal-length, unpadded prompts.
     input_ids: LongTensor [bs, len].  returns dict(sequences [bs, <= max_length] padded with pad_token_id like the
     reference's output_ids, lengths = tokens known per request, dls, edls)"""
@@ -80,7 +81,8 @@ def lookahead_generate_batch(model, trie, input_ids, max_new_tokens=None, max_le
     trie.stop_words = stop_words if stop_words is not None else {}
     for i, ids in enumerate(input_ids.tolist()):                              # :1203-1206
         trie.put(ids[1:-1], branch_length=branch_length + 1, mode='input', idx=i)
-    backends = [HFBackend(model) for _ in range(bs)]
+    backends = [backend_factory(b) if backend_factory is not None else HFBackend(model) for b in range(bs)]
+    steps = []
     seqs = [torch.cat([input_ids[b:b + 1], torch.full((1, max_length - prompt_len), pad_token_id, dtype=torch.long,
                                                       device=dev)], 1) for b in range(bs)]
     dls, edls = [], []
@@ -137,6 +139,8 @@ def lookahead_generate_batch(model, trie, input_ids, max_new_tokens=None, max_le
                 backends[b].compact(torch.tensor(keep, dtype=torch.long, device=dev))
             cursors[b] = cur + len(tokens)
             step_tokens.append(tokens)
+        if trace:
+            steps.append(dict(active=list(active), ids=[list(x) for x in ids_list], cursors=curs, tokens=step_tokens))
         for k, b in enumerate(active):                                        # :1243-1248
             trie.stream_put(step_tokens[k], branch_length=branch_length + 1, final=False, mode='output', idx=b)
         still = []
@@ -149,4 +153,7 @@ def lookahead_generate_batch(model, trie, input_ids, max_new_tokens=None, max_le
         trie.stream_put([], branch_length=branch_length + 1, final=True, mode='output', idx=i)
     lengths = [cursors[b] + 1 for b in range(bs)]
     max_cur = max(cursors)
-    return dict(sequences=torch.cat([s[:, :max_cur + 1] for s in seqs], 0), lengths=lengths, dls=dls, edls=edls)
+    res = dict(sequences=torch.cat([s[:, :max_cur + 1] for s in seqs], 0), lengths=lengths, dls=dls, edls=edls)
+    if trace:
+        res['steps'] = steps
+    return res

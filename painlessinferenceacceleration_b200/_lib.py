@@ -33,12 +33,18 @@ class TrieStats(C.Structure):
 
 class AttnConfig(C.Structure):
     _fields_ = [('n_q_heads', C.c_int32), ('n_kv_heads', C.c_int32), ('head_dim', C.c_int32), ('max_seq', C.c_int32),
-                ('max_nodes', C.c_int32), ('n_layers', C.c_int32), ('kv_split_max', C.c_int32)]
+                ('max_nodes', C.c_int32), ('n_layers', C.c_int32), ('kv_split_max', C.c_int32), ('n_slots', C.c_int32)]
 
 
 class AcceptConfig(C.Structure):
     _fields_ = [('vocab', C.c_int32), ('max_nodes', C.c_int32), ('repetition_penalty', C.c_float),
-                ('n_eos', C.c_int32), ('eos', C.c_int32 * 8), ('max_length', C.c_int32)]
+                ('n_eos', C.c_int32), ('eos', C.c_int32 * 8), ('max_length', C.c_int32), ('bound_walk', C.c_int32)]
+
+
+class Slots(C.Structure):
+    """pia_slots_t: the request slots of one verify step (device arrays, read at kernel run time)"""
+    _fields_ = [('batch', C.c_int32), ('rows_per_slot', C.c_int32), ('d_n', C.c_void_p), ('d_prefix_len', C.c_void_p),
+                ('d_pad_len', C.c_void_p), ('kv_slot_stride', C.c_int64), ('kv_first_slot', C.c_int32)]
 
 
 # every symbol include/pia_b200.h declares: name -> (restype, argtypes)
@@ -53,9 +59,9 @@ SYMBOLS = {
     'pia_trie_set_limits': (C.c_int, [vp, C.c_int, C.c_int]),
     'pia_trie_put': (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     'pia_trie_tree_put': (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
-    'pia_trie_stream_put': (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+    'pia_trie_stream_put': (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     'pia_trie_get': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                               C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+                               C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
     'pia_trie_reset_input_freqs': (C.c_int, [vp, C.c_int, vp]),
     'pia_trie_squeeze_branch_counts': (C.c_int, [vp, vp]),
     'pia_trie_fresh': (C.c_int, [vp, vp]),
@@ -68,7 +74,7 @@ SYMBOLS = {
     'pia_attn_plan_destroy': (C.c_int, [vp]),
     'pia_attn_plan_set_debug': (C.c_int, [vp, vp]),
     'pia_attn_plan_grid': (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    'pia_tree_attn_fwd': (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_float, vp, vp]),
+    'pia_tree_attn_fwd': (C.c_int, [vp, C.c_int, vp, vp, C.POINTER(Slots), C.c_float, vp, vp]),
     'pia_rmsnorm': (C.c_int, [vp, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     'pia_rmsnorm_partials': (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
     'pia_gemm_plan_create': (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
@@ -77,16 +83,17 @@ SYMBOLS = {
     'pia_gemm_plan_splits': (C.c_int, [vp]),
     'pia_gemm_plan_set_silu': (C.c_int, [vp, C.c_int]),
     'pia_gemm_run': (C.c_int, [vp, C.c_int, vp, vp]),
-    'pia_rope_kv_append': (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+    'pia_rope_kv_append': (C.c_int, [vp, vp, C.c_int, C.POINTER(Slots), C.c_int, C.c_int, C.c_int, vp, vp,
                                      C.c_int, vp, vp, vp, C.c_int, vp]),
     'pia_silu_mul': (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     'pia_embed_gather': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     'pia_moe_combine': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     'pia_l2_prefetch': (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, vp]),
-    'pia_accept': (C.c_int, [C.POINTER(AcceptConfig), vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp,
-                             vp, vp, vp, vp]),
+    'pia_accept': (C.c_int, [C.POINTER(AcceptConfig), vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp,
+                             vp, vp, vp, vp, vp, vp, vp]),
     'pia_accept_workspace_bytes': (C.c_int64, [C.POINTER(AcceptConfig)]),
-    'pia_kv_compact': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    'pia_kv_compact': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp,
+                                 vp]),
 }
 
 

@@ -163,8 +163,8 @@ class LookaheadCache(object):
         assert mode == 'output' and idx >= 0
         d, n = self._tokens(token_ids)
         with torch.cuda.device(self._t.device):
-            L.check(self._t.lib.pia_trie_stream_put(self._t.h, d.data_ptr(), n, None, branch_length, idx, int(final),
-                                                    self._t.stream()))
+            L.check(self._t.lib.pia_trie_stream_put(self._t.h, d.data_ptr(), n, None, branch_length, idx, None,
+                                                    int(final), self._t.stream()))
 
     def put_device(self, d_tokens, n_max, d_n=None, branch_length=8, final=False, mode='output', idx=0):
         """put() on tokens already in HBM (int32 tensor); the live length may itself be a device scalar"""
@@ -172,10 +172,13 @@ class LookaheadCache(object):
                                          d_n.data_ptr() if d_n is not None else None, branch_length, L.MODE[mode],
                                          idx, int(final), self._t.stream()))
 
-    def stream_put_device(self, d_tokens, n_max, d_n=None, branch_length=8, final=False, idx=0):
+    def stream_put_device(self, d_tokens, n_max, d_n=None, branch_length=8, final=False, idx=0, d_idx=None):
+        """stream_put() on tokens in HBM; `d_idx` (int32 device scalar) overrides idx on the device: the batched
+        loop's slot -> request map changes as requests finish (pretrained_model_batch.py:937-980)"""
         L.check(self._t.lib.pia_trie_stream_put(self._t.h, d_tokens.data_ptr(), n_max,
                                                 d_n.data_ptr() if d_n is not None else None, branch_length, idx,
-                                                int(final), self._t.stream()))
+                                                d_idx.data_ptr() if d_idx is not None else None, int(final),
+                                                self._t.stream()))
 
     # ---- reads
     def _get_batch(self, queries, decoding_length, branch_length, min_input_size, min_output_size, mode, indices,
@@ -197,7 +200,7 @@ class LookaheadCache(object):
         with torch.cuda.device(dev):
             L.check(self._t.lib.pia_trie_get(self._t.h, dq.data_ptr(), dl.data_ptr(), bs, stride, stride,
                                              didx.data_ptr(), 0, cap, branch_length, min_input_size, min_output_size,
-                                             L.MODE[mode], kind, flags, 0, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                             L.MODE[mode], kind, flags, 0, None, o['ids'].data_ptr(), o['mask'].data_ptr(),
                                              o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
                                              o['status'].data_ptr(), self._t.stream()))
         ids = o['ids'].cpu().numpy()
@@ -282,14 +285,21 @@ class LookaheadCache(object):
         return id_list, masks, size_list
 
     def get_device(self, d_seq, d_seq_len, decoding_length, branch_length, max_query_length=2, min_input_size=0,
-                   min_output_size=0, mode='mix', idx=0, kind='hier', max_seq_length=0, out=None):
-        """hier_get/one_get for the generation loop: the query is the tail of the device token sequence
-        (pretrained_model.py:708) and the draft stays in HBM. `out` is the dict of out_buffers(1, dl)."""
-        o = out if out is not None else self._t.out_buffers(1, max(decoding_length, 1))
-        L.check(self._t.lib.pia_trie_get(self._t.h, d_seq.data_ptr(), d_seq_len.data_ptr(), 1, d_seq.numel(),
-                                         max_query_length, None, idx, decoding_length, branch_length, min_input_size,
+                   min_output_size=0, mode='mix', idx=0, kind='hier', max_seq_length=0, out=None, batch=1,
+                   d_idx=None, d_max_seq_length=None):
+        """hier_get/one_get for the generation loops: the query of row b is the tail of the device token sequence
+        d_seq[b, :d_seq_len[b]] (pretrained_model.py:708; batched :705-707) and the drafts stay in HBM.  `out` is a
+        dict like out_buffers(batch, dl).  d_idx [batch]: request idx per row (bat_get's `indices`);
+        d_max_seq_length: int32 device scalar replacing max_seq_length (the :680 clamp of branch_length)."""
+        o = out if out is not None else self._t.out_buffers(batch, max(decoding_length, 1))
+        stride = d_seq.shape[-1] if d_seq.dim() == 2 else d_seq.numel()
+        L.check(self._t.lib.pia_trie_get(self._t.h, d_seq.data_ptr(), d_seq_len.data_ptr(), int(batch), int(stride),
+                                         max_query_length, d_idx.data_ptr() if d_idx is not None else None, idx,
+                                         decoding_length, branch_length, min_input_size,
                                          min_output_size, L.MODE[mode], L.GET_HIER if kind == 'hier' else L.GET_ONE,
-                                         L.GET_TAIL, max_seq_length, o['ids'].data_ptr(), o['mask'].data_ptr(),
+                                         L.GET_TAIL, max_seq_length,
+                                         d_max_seq_length.data_ptr() if d_max_seq_length is not None else None,
+                                         o['ids'].data_ptr(), o['mask'].data_ptr(),
                                          o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
                                          o['status'].data_ptr(), self._t.stream()))
         return o

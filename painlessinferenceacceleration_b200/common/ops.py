@@ -106,12 +106,37 @@ class Gemm(object):
             pass
 
 
-def rope_kv_append(qkv, mask, n, prefix_len, pad_len, n_q_heads, n_kv_heads, head_dim, cos, sin, q_out, k_layer,
-                   v_layer, max_seq):
-    rows = qkv.shape[0]
-    L.check(L.load().pia_rope_kv_append(_p(qkv), _p(mask), mask.shape[1], _p(n), _p(prefix_len), int(pad_len), rows,
-                                        n_q_heads, n_kv_heads, head_dim, _p(cos), _p(sin), cos.shape[0], _p(q_out),
-                                        _p(k_layer), _p(v_layer), max_seq, _s()))
+class Slots(object):
+    """pia_slots_t: the request slots of one verify step.  `n`, `prefix_len`, `pad_len` are int32 DEVICE tensors of
+    `batch` entries read when the kernels run (so one CUDA graph serves every length / padding); slot s owns rows
+    [s * rows_per_slot, (s + 1) * rows_per_slot) of the activation and draft buffers and the KV cache that starts
+    kv_slot_stride elements after slot s-1's (0: all slots share one cache, e.g. the chain chunks of a prefill pass)."""
+
+    def __init__(self, n, prefix_len, pad_len=None, rows_per_slot=64, kv_slot_stride=0, batch=None, kv_first_slot=0):
+        batch = int(batch if batch is not None else n.numel())
+        assert n.dtype == torch.int32 and prefix_len.dtype == torch.int32 and n.numel() >= batch <= prefix_len.numel()
+        assert pad_len is None or (pad_len.dtype == torch.int32 and pad_len.numel() >= batch)
+        self.batch, self.rows_per_slot, self.kv_slot_stride = batch, int(rows_per_slot), int(kv_slot_stride)
+        self.n, self.prefix_len, self.pad_len = n, prefix_len, pad_len
+        self.kv_first_slot = int(kv_first_slot)
+        self.c = L.Slots(batch, int(rows_per_slot), _p(n), _p(prefix_len), _p(pad_len), int(kv_slot_stride),
+                         int(kv_first_slot))
+
+    @property
+    def rows(self):
+        return self.batch * self.rows_per_slot
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def rope_kv_append(qkv, mask, slots, n_q_heads, n_kv_heads, head_dim, cos, sin, q_out, k_layer, v_layer, max_seq):
+    """qkv / q_out: >= slots.rows rows; mask: [>= slots.rows, W] int64 ancestor rows; k_layer / v_layer: the layer's
+    [n_kv_heads, max_seq, head_dim] planes of slot 0"""
+    assert qkv.shape[0] >= slots.rows and mask.shape[0] >= slots.rows
+    L.check(L.load().pia_rope_kv_append(_p(qkv), _p(mask), mask.shape[-1], slots.ref(), n_q_heads, n_kv_heads,
+                                        head_dim, _p(cos), _p(sin), cos.shape[0], _p(q_out), _p(k_layer), _p(v_layer),
+                                        max_seq, _s()))
 
 
 def silu_mul(gate_up, out):
@@ -141,21 +166,24 @@ def embed_gather(table, ids, n, out):
 
 
 class AttnPlan(object):
-    """pia_attn_plan_t: TMA descriptors over one model's KV cache (KV splits merge on chip: no workspace)"""
+    """pia_attn_plan_t: TMA descriptors over one model's KV cache(s) (KV splits merge on chip: no workspace).
+    k_cache / v_cache: [n_layers, n_kv_heads, max_seq, head_dim], or [n_slots, ...] for the batched loop"""
 
     def __init__(self, k_cache, v_cache, n_q_heads, n_kv_heads, head_dim, max_nodes, kv_split_max=0):
-        n_layers, hkv, max_seq, hd = k_cache.shape
+        n_slots = k_cache.shape[0] if k_cache.dim() == 5 else 1
+        n_layers, hkv, max_seq, hd = k_cache.shape[-4:]
         assert hkv == n_kv_heads and hd == head_dim and k_cache.is_contiguous() and v_cache.is_contiguous()
-        self.cfg = L.AttnConfig(n_q_heads, n_kv_heads, head_dim, max_seq, max_nodes, n_layers, kv_split_max)
+        self.cfg = L.AttnConfig(n_q_heads, n_kv_heads, head_dim, max_seq, max_nodes, n_layers, kv_split_max, n_slots)
+        self.slot_stride = n_layers * hkv * max_seq * hd
         self.h = L.vp()
         self.lib = L.load()
         with torch.cuda.device(k_cache.device):
             L.check(self.lib.pia_attn_plan_create(C.byref(self.cfg), _p(k_cache), _p(v_cache), C.byref(self.h)))
         self._keep = (k_cache, v_cache)
 
-    def forward(self, layer, q, mask, n, prefix_len, pad_len, out, scale_mul=1.0):
-        L.check(self.lib.pia_tree_attn_fwd(self.h, layer, _p(q), _p(mask), _p(n), _p(prefix_len), int(pad_len),
-                                           float(scale_mul), _p(out), _s()))
+    def forward(self, layer, q, mask, slots, out, scale_mul=1.0):
+        assert q.shape[0] >= slots.rows and mask.shape[0] >= slots.rows and out.shape[0] >= slots.rows
+        L.check(self.lib.pia_tree_attn_fwd(self.h, layer, _p(q), _p(mask), slots.ref(), float(scale_mul), _p(out), _s()))
 
     def close(self):
         if self.h:
@@ -170,26 +198,38 @@ class AttnPlan(object):
 
 
 class Accept(object):
-    """pia_accept + pia_kv_compact with their config/workspace"""
+    """pia_accept + its config/workspace.  max_length is a device scalar (d_max_length) when given, so that one
+    captured step serves every request length."""
 
-    def __init__(self, vocab, max_nodes, repetition_penalty, eos_ids, max_length, device):
+    def __init__(self, vocab, max_nodes, repetition_penalty, eos_ids, max_length, device, bound_walk=False):
         eos = [int(e) for e in (eos_ids or []) if e is not None][:8]
         arr = (C.c_int32 * 8)(*(eos + [-1] * (8 - len(eos))))
-        self.cfg = L.AcceptConfig(vocab, max_nodes, float(repetition_penalty), len(eos), arr, int(max_length))
+        self.cfg = L.AcceptConfig(vocab, max_nodes, float(repetition_penalty), len(eos), arr, int(max_length),
+                                  int(bool(bound_walk)))
+        self.max_nodes = max_nodes
         self.lib = L.load()
         self.workspace = torch.empty((max(self.lib.pia_accept_workspace_bytes(C.byref(self.cfg)) // 4, 1),),
                                      dtype=torch.int32, device=device)
 
-    def run(self, logits, ids, mask, n, seq, seq_len, pad_len, acc_tokens, acc_count, acc_nodes, prefix_len, finished):
-        L.check(self.lib.pia_accept(C.byref(self.cfg), _p(logits), _p(ids), _p(mask), mask.shape[1], _p(n), _p(seq),
-                                    _p(seq_len), seq.numel(), int(pad_len), _p(acc_tokens), _p(acc_count),
-                                    _p(acc_nodes), _p(prefix_len), _p(finished), _p(self.workspace), _s()))
+    def run(self, logits, ids, mask, n, seq, seq_len, acc_tokens, acc_count, acc_nodes, prefix_len, finished,
+            batch=1, rows_per_slot=None, max_length=None):
+        """ids [batch * rows_per_slot], mask [batch * rows_per_slot, W], n / seq_len / prefix_len / finished /
+        acc_count [batch], seq [batch, stride] (or 1-D for one slot), acc_tokens / acc_nodes [batch, max_nodes];
+        max_length: optional int32 device scalar overriding the config's"""
+        rps = int(rows_per_slot if rows_per_slot is not None else self.max_nodes // batch)
+        stride = seq.shape[-1] if seq.dim() == 2 else seq.numel()
+        L.check(self.lib.pia_accept(C.byref(self.cfg), _p(logits), _p(ids), _p(mask), mask.shape[-1], int(batch), rps,
+                                    _p(n), _p(seq), _p(seq_len), int(stride), _p(max_length), _p(acc_tokens),
+                                    _p(acc_count), _p(acc_nodes), _p(prefix_len), _p(finished), _p(self.workspace), _s()))
 
 
-def kv_compact(k_cache, v_cache, acc_nodes, acc_count, prefix_len):
-    n_layers, hkv, max_seq, hd = k_cache.shape
-    L.check(L.load().pia_kv_compact(_p(k_cache), _p(v_cache), n_layers, hkv, max_seq, hd, _p(acc_nodes), _p(acc_count),
-                                    _p(prefix_len), _s()))
+def kv_compact(k_cache, v_cache, acc_nodes, acc_count, prefix_len, batch=1):
+    """k_cache / v_cache [n_layers, Hkv, S, D] (batch 1) or [batch_cap, n_layers, Hkv, S, D]"""
+    n_layers, hkv, max_seq, hd = k_cache.shape[-4:]
+    stride = n_layers * hkv * max_seq * hd if k_cache.dim() == 5 else 0
+    nodes_stride = acc_nodes.shape[-1] if acc_nodes.dim() == 2 else acc_nodes.numel()
+    L.check(L.load().pia_kv_compact(_p(k_cache), _p(v_cache), n_layers, hkv, max_seq, hd, int(batch), int(stride),
+                                    _p(acc_nodes), int(nodes_stride), _p(acc_count), _p(prefix_len), _s()))
 
 
 def launch_count():

@@ -10,11 +10,16 @@ The reference loop crosses the host/device boundary several times per step (draf
     trie get -> embed -> L x [rmsnorm, qkv GEMM, rope+kv-append, tree attention, o GEMM, rmsnorm, gate/up GEMM,
     silu*mul, down GEMM] -> norm -> lm_head GEMM -> accept walk -> KV compaction -> trie stream_put
 
-runs entirely on the device from device-resident state (token sequence, lengths, KV cache, trie) and is replayed
-as ONE CUDA graph; the host reads back a single small pinned buffer (count, finished flag, accepted tokens) per
-step to drive streamers / stopping.  GEMMs are cuBLAS (plain library GEMMs); everything else is libpia_b200.so.
+runs entirely on the device from device-resident state (token sequences, lengths, KV caches, trie) and is replayed
+as ONE CUDA graph; the host reads back a single small pinned record (count, finished flag, accepted tokens) per
+step to drive streamers / stopping, one step late: step k+1 is already enqueued when record k is read (a step that
+runs after its request finished is a no-op on the device).  Everything per-request that varies - prompt length,
+left padding, max_length - lives in device scalars, so one captured graph serves every request of a configuration.
+The runtime is organised in request SLOTS (include/pia_b200.h pia_slots_t): this per-request loop runs one slot,
+the batched loop (pretrained_model_batch.py) one slot per request, a prefill pass one slot per 64-row prompt chunk.
 There is no CPU fallback."""
 import time
+from collections import OrderedDict
 from threading import Thread
 
 import numpy as np
@@ -25,9 +30,12 @@ from . import ops
 from .lookahead_cache import LookaheadCache
 from .lookahead_generation_utils import GenerationMode, LookaheadDecoderOnlyOutput
 
+MAX_GRAPHS = 8  # captured step graphs kept per runtime (LRU)
+
 
 class _Bufs(object):
-    """activation buffers of one forward pass over `rows` token rows split into 64|128-row attention chunks"""
+    """activation buffers of one forward pass over `rows` token rows; `slots` (ops.Slots) says which request slot
+    owns which rows and `mask` holds the rows' ancestor bit sets"""
 
     def __init__(self, g, rows, dev, with_logits):
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -42,68 +50,95 @@ class _Bufs(object):
         self.q = torch.zeros((rows, g['n_q_heads'], g['head_dim']), **bf)
         self.attn = torch.zeros((rows, g['n_q_heads'] * g['head_dim']), **bf)
         self.logits = torch.zeros((rows, g['vocab']), **bf) if with_logits else None
-        self.chunks = []
-
-    def set_chunk_rows(self, n):
-        pass
+        self.mask = None
+        self.slots = None
+        self.kv_slot = 0   # cache the pointer-addressed kernels (rope / KV append) start from
 
 
 class _Runtime(object):
-    """device-resident state of one model's draft-verify loop (built once per (max_seq, max_nodes))"""
+    """device-resident state of one model's draft-verify loop: `n_slots` request slots sharing max_nodes draft rows"""
 
-    def __init__(self, model, max_seq, max_nodes):
+    def __init__(self, model, max_seq, max_nodes, n_slots=1):
         dev = model.device
         self.device = dev
-        self.max_seq, self.max_nodes = int(max_seq), int(max_nodes)
+        self.max_seq, self.max_nodes, self.n_slots = int(max_seq), int(max_nodes), int(n_slots)
         g = model.geometry()
         self.g = g
         i32 = dict(dtype=torch.int32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
-        W = self.max_nodes // 64
-        R = self.max_nodes
-        self.k_cache = torch.zeros((g['n_layers'], g['n_kv_heads'], self.max_seq, g['head_dim']), **bf)
+        W, R, S = self.max_nodes // 64, self.max_nodes, self.n_slots
+        self.k_cache = torch.zeros((S, g['n_layers'], g['n_kv_heads'], self.max_seq, g['head_dim']), **bf)
         self.v_cache = torch.zeros_like(self.k_cache)
+        self.cache_elems = self.k_cache[0].numel()
         self.plan = ops.AttnPlan(self.k_cache, self.v_cache, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], R)
-        # draft (filled by the trie kernel or, for prefill chunks, by the host)
-        self.ids = torch.zeros((1, R), **i32)
-        self.mask = torch.zeros((1, R, W), dtype=torch.int64, device=dev)
-        self.n = torch.ones((1,), **i32)
-        self.sizes = torch.zeros((1, 2), **i32)
-        self.nsizes = torch.zeros((1,), **i32)
-        self.status = torch.zeros((1,), **i32)
-        self.draft = dict(ids=self.ids, mask=self.mask, n=self.n, sizes=self.sizes, nsizes=self.nsizes,
-                          status=self.status)
-        # sequence state
-        self.seq = torch.zeros((self.max_seq + 8,), **i32)
-        self.seq_len = torch.zeros((1,), **i32)
-        self.prefix_len = torch.zeros((1,), **i32)
-        self.finished = torch.zeros((1,), **i32)
-        self.acc_tokens = torch.zeros((R,), **i32)
-        self.acc_count = torch.zeros((1,), **i32)
-        self.acc_nodes = torch.zeros((R,), **i32)
-        # host-visible step record: [count, finished, n, status, tokens...]
-        self.record = torch.zeros((4 + R,), **i32)
-        self.record_host = torch.zeros((4 + R,), dtype=torch.int32).pin_memory()
-        # activations of a decode step: one chunk = the draft
+        # drafts (filled by the trie kernel or, for prefill chunks, by the host): R rows shared by the slots
+        self.ids = torch.zeros((R,), **i32)
+        self.mask = torch.zeros((R, W), dtype=torch.int64, device=dev)
+        self.n = torch.ones((S,), **i32)
+        self.sizes = torch.zeros((S, 2), **i32)
+        self.nsizes = torch.zeros((S,), **i32)
+        self.status = torch.zeros((S,), **i32)
+        # per-slot sequence state
+        self.seq = torch.zeros((S, self.max_seq + 8), **i32)
+        self.seq_len = torch.zeros((S,), **i32)
+        self.prefix_len = torch.zeros((S,), **i32)
+        self.finished = torch.zeros((S,), **i32)
+        self.pad = torch.zeros((S,), **i32)            # left-pad columns (pretrained_model.py:1123-1131)
+        self.trie_idx = torch.arange(S, **i32)         # slot -> request idx of the trie (batched loop)
+        self.max_length = torch.zeros((1,), **i32)     # MaxLengthCriteria, read on the device
+        self.acc_tokens = torch.zeros((S, R), **i32)
+        self.acc_count = torch.zeros((S,), **i32)
+        self.acc_nodes = torch.zeros((S, R), **i32)
+        # host-visible step record per slot: [count, finished, n, status, tokens...]; two pinned copies so that the
+        # step launched ahead does not overwrite the record the host is still reading
+        self.record = torch.zeros((S, 4 + R), **i32)
+        self.record_host = [torch.zeros((S, 4 + R), dtype=torch.int32).pin_memory() for _ in range(2)]
+        # activations of a decode step
         db = _Bufs(g, R, dev, with_logits=True)
-        db.ids = self.ids[0]
-        db.n_total = self.n
-        db.chunks = [(0, R, self.mask[0], self.n, self.prefix_len)]
+        db.ids = self.ids
+        db.mask = self.mask
+        db.slots = ops.Slots(self.n, self.prefix_len, self.pad, R, 0, batch=1)
+        db.n_total = self.n  # one slot: live rows = n[0]
         self.decode_bufs = db
         self.h, self.resid, self.y, self.qkv, self.q, self.attn, self.logits = db.h, db.resid, db.y, db.qkv, db.q, \
             db.attn, db.logits
-        # activations of a prefill pass: up to PF_CHUNKS chain chunks of R rows through one set of GEMMs
-        self.pf_chunks = max(1, 256 // R)
-        pb = _Bufs(g, R * self.pf_chunks, dev, with_logits=False)
-        self.pf_n = torch.zeros((self.pf_chunks,), **i32)
-        self.pf_P = torch.zeros((self.pf_chunks,), **i32)
+        # activations of a prefill pass: up to pf_chunks chain chunks of R rows through one set of GEMMs, one slot each
+        C = max(1, 256 // R)
+        self.pf_chunks = C
+        pb = _Bufs(g, R * C, dev, with_logits=False)
+        self.pf_meta = torch.zeros((3, C), **i32)       # rows: n, P, pad of every chunk
+        self.pf_meta_host = torch.zeros((3, C), dtype=torch.int32).pin_memory()
+        self.chain = self.chain_mask_rows()
+        pb.mask = self.chain.repeat(C, 1).contiguous()
+        self.pf_mask_dirty = False
+        self.pf_slots = {}
         self.prefill_bufs = pb
         self.rope_cos, self.rope_sin = model.rope_tables(self.max_seq + 8)
-        self.graphs = {}
+        self.graphs = OrderedDict()
         self.replays = 0
         self.kernels_per_graph = 0
         self.accepts = {}
-        self.pad_len = 0
+        self.pad_host = 0
+
+    def k_layer(self, layer, slot=0):
+        return self.k_cache[slot, layer]
+
+    def v_layer(self, layer, slot=0):
+        return self.v_cache[slot, layer]
+
+    def prefill_slots(self, slot):
+        """slot table of a prefill pass into request slot `slot`'s cache: one table slot per 64-row chain chunk"""
+        if slot not in self.pf_slots:
+            self.pf_slots[slot] = ops.Slots(self.pf_meta[0], self.pf_meta[1], self.pf_meta[2], self.max_nodes, 0,
+                                            batch=self.pf_chunks, kv_first_slot=slot)
+        return self.pf_slots[slot]
+
+    def decode_slots(self, batch, rows_per_slot):
+        key = ('dec', batch, rows_per_slot)
+        if key not in self.pf_slots:
+            self.pf_slots[key] = ops.Slots(self.n, self.prefix_len, self.pad, rows_per_slot,
+                                           self.cache_elems if batch > 1 else 0, batch=batch)
+        return self.pf_slots[key]
 
     # -- prefill: the prompt is fed as chain drafts of <= max_nodes tokens through the same verify kernels
     def chain_mask_rows(self):
@@ -118,24 +153,26 @@ class _Runtime(object):
                     rows[i, w] = np.uint64((1 << (i - lo + 1)) - 1)
         return torch.from_numpy(rows.view(np.int64)).to(self.device)
 
+    def chain_without_first(self, k):
+        """chain mask whose first k columns (left-pad tokens of this chunk) are cleared"""
+        cache = self.__dict__.setdefault('_chain_cut', {})
+        if k not in cache:
+            rows = self.chain.cpu().numpy().view(np.uint64).copy()
+            R = self.max_nodes
+            for w in range(R // 64):
+                lo = 64 * w
+                if k >= lo + 64:
+                    rows[:, w] = 0
+                elif k > lo:
+                    rows[:, w] &= ~np.uint64((1 << (k - lo)) - 1)
+            cache[k] = torch.from_numpy(rows.view(np.int64)).to(self.device)
+        return cache[k]
 
-def _chain_without_first(self, k):
-    """chain mask whose first k columns (left-pad tokens of this chunk) are cleared"""
-    cache = self.__dict__.setdefault('_chain_cut', {})
-    if k not in cache:
-        rows = self.chain.cpu().numpy().view(np.uint64).copy()
-        R = self.max_nodes
-        for w in range(R // 64):
-            lo = 64 * w
-            if k >= lo + 64:
-                rows[:, w] = 0
-            elif k > lo:
-                rows[:, w] &= ~np.uint64((1 << (k - lo)) - 1)
-        cache[k] = torch.from_numpy(rows.view(np.int64)).to(self.device)
-    return cache[k]
-
-
-_Runtime.chain_without_first = _chain_without_first
+    def set_request(self, slot, pad_len, max_length):
+        """per-request scalars the captured graphs read on the device"""
+        self.pad_host = int(pad_len)
+        self.pad[slot:slot + 1].fill_(int(pad_len))
+        self.max_length.fill_(int(max_length))
 
 
 class LookaheadPreTrainedModel(nn.Module):
@@ -154,11 +191,14 @@ class LookaheadPreTrainedModel(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
-    def _runtime(self, max_seq, max_nodes):
+    def _runtime(self, max_seq, max_nodes, n_slots=1, keep_cache=False):
         rt = self._rt
-        if rt is None or rt.max_seq < max_seq or rt.max_nodes != max_nodes:
+        if rt is None or rt.max_seq < max_seq or rt.max_nodes != max_nodes or rt.n_slots < n_slots:
+            assert not keep_cache or rt is None, \
+                (f'the KV cache holds a context but the runtime has to be rebuilt ({max_seq=} {max_nodes=} '
+                 f'vs {rt.max_seq=} {rt.max_nodes=}): past tokens would be dropped')
             self._rt = None
-            rt = _Runtime(self, max(max_seq, 128), max_nodes)
+            rt = _Runtime(self, max(max_seq, 128), max_nodes, n_slots)
             self._rt = rt
             # one-time weight preparation must never end up inside a captured step graph
             if hasattr(self, 'fuse'):
@@ -235,42 +275,56 @@ class LookaheadPreTrainedModel(nn.Module):
                                          repetition_penalty=float(opt('repetition_penalty', 1.0)))
 
     # ------------------------------------------------------------------ the loop (reference :947-1268)
-    def _capture_step(self, rt, key, use_trie, dl, bl, mql, min_out, tmode, kind, max_length, accept):
-        """one decode step as a CUDA graph over the static buffers"""
-        trie = self.lookahead_cache
+    def _graph_entry(self, rt, key, build):
+        """LRU cache of captured step graphs; an entry keeps alive what its graph points into (trie, accept config)"""
+        ent = rt.graphs.get(key)
+        if ent is None:
+            ent = build()
+            rt.graphs[key] = ent
+            while len(rt.graphs) > MAX_GRAPHS:
+                rt.graphs.popitem(last=False)
+        else:
+            rt.graphs.move_to_end(key)
+        return ent
+
+    def _capture_step(self, rt, trie, use_trie, dl, bl, mql, min_out, tmode, kind, accept):
+        """one decode step of the per-request loop as a CUDA graph over the static buffers (slot 0)"""
+        draft = dict(ids=rt.ids, mask=rt.mask, n=rt.n, sizes=rt.sizes, nsizes=rt.nsizes, status=rt.status)
 
         def step():
             if use_trie:
-                # lookahead_prepare_inputs_for_generation :708-723 (query = last tokens of the device sequence)
+                # lookahead_prepare_inputs_for_generation :708-723 (query = last tokens of the device sequence;
+                # branch_length clamped by the device-resident max_length, :680)
                 trie.get_device(rt.seq, rt.seq_len, dl, bl, max_query_length=mql, min_input_size=0,
-                                min_output_size=min_out, mode=tmode, idx=0, kind=kind, max_seq_length=max_length,
-                                out=rt.draft)
+                                min_output_size=min_out, mode=tmode, idx=0, kind=kind, max_seq_length=1,
+                                d_max_seq_length=rt.max_length, out=draft)
             else:  # plain greedy: the draft is the last token alone
-                rt.ids[0, 0:1] = rt.seq.gather(0, (rt.seq_len - 1).long())
+                rt.ids[0:1] = rt.seq[0].gather(0, (rt.seq_len - 1).long())
                 rt.n.fill_(1)
-                rt.mask[0, 0, 0:1].fill_(1)
+                rt.mask[0, 0:1].fill_(1)
             self._verify_layers(rt)
-            accept.run(rt.logits, rt.ids[0], rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens,
-                       rt.acc_count, rt.acc_nodes, rt.prefix_len, rt.finished)
-            ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len)
+            accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
+                       rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length)
+            ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len, batch=1)
             if use_trie:  # :1203
                 trie.stream_put_device(rt.acc_tokens, rt.max_nodes, rt.acc_count, branch_length=self._put_bl,
                                        final=False, idx=0)
-            rt.record[0:1] = rt.acc_count
-            rt.record[1:2] = rt.finished
-            rt.record[2:3] = rt.n
-            rt.record[3:4] = rt.status
-            rt.record[4:] = rt.acc_tokens
-            rt.record_host.copy_(rt.record, non_blocking=True)
+            rt.record[0, 0:1] = rt.acc_count
+            rt.record[0, 1:2] = rt.finished
+            rt.record[0, 2:3] = rt.n
+            rt.record[0, 3:4] = rt.status
+            rt.record[0, 4:] = rt.acc_tokens[0]
 
-        # warm up (cuBLAS handles/workspaces, lazy attributes) on a side stream, then capture
-        g = torch.cuda.CUDAGraph()
+        graphs = []
         l0 = ops.launch_count()
-        with torch.cuda.graph(g):
-            step()
-        rt.kernels_per_graph = ops.launch_count() - l0  # libpia_b200 kernels per replay (bench.py gpu_launches)
-        rt.graphs[key] = g
-        return g
+        for host in rt.record_host:  # one graph per pinned record copy (the step launched ahead writes the other)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+                host.copy_(rt.record, non_blocking=True)
+            graphs.append(g)
+        rt.kernels_per_graph = (ops.launch_count() - l0) // 2  # libpia_b200 kernels per replay (bench.py gpu_launches)
+        return dict(graphs=graphs, keep=(trie, accept))
 
     @torch.no_grad()
     def lookahead_generation(self, input_ids, logits_processor=None, stopping_criteria=None, max_length=None,
@@ -321,22 +375,20 @@ class LookaheadPreTrainedModel(nn.Module):
             if am is not None:
                 nz = torch.nonzero(am.to('cpu') != 0)
                 pad_len = int(nz[0]) if nz.numel() else 0
-        rt.pad_len = pad_len
+        rt.set_request(0, pad_len, max_length)
 
         ts = time.time()
         prompt = input_ids[0].to(device=dev, dtype=torch.int32)
-        rt.seq[:prompt_len] = prompt
+        rt.seq[0, :prompt_len] = prompt
         rt.finished.zero_()
         if use_trie:  # (:1153-1156)
-            trie.put_device(rt.seq[1:], max(prompt_len - 1, 0), None, branch_length=bl + 1, final=False, mode='input',
+            trie.put_device(rt.seq[0, 1:], max(prompt_len - 1, 0), None, branch_length=bl + 1, final=False, mode='input',
                             idx=0)
-        key = (use_trie, dl, bl, mql, tmode, fmt, max_length, float(repetition_penalty),
-               tuple(eos_token_id or ()), pad_len)
-        # the accept config/workspace is referenced by the captured graph: it lives as long as the runtime
-        accept = rt.accepts.get(key)
-        if accept is None:
+        akey = (float(repetition_penalty), tuple(eos_token_id or ()), max_nodes)
+        accept = rt.accepts.get(akey)
+        if accept is None:  # referenced by captured graphs: lives as long as the runtime
             accept = ops.Accept(self.geometry()['vocab'], max_nodes, repetition_penalty, eos_token_id, max_length, dev)
-            rt.accepts[key] = accept
+            rt.accepts[akey] = accept
         first = self._prefill(rt, prompt_len, accept)
         new_tokens = [first]
         decoding_kwargs['dls'].append(1)  # the prefill step counts as one fed token (:797-798)
@@ -345,93 +397,118 @@ class LookaheadPreTrainedModel(nn.Module):
             streamer.put(input_ids.cpu())
             streamer.put(np.array([[first]]))
         if use_trie:
-            trie.stream_put_device(rt.seq[prompt_len:], 1, None, branch_length=bl + 1, final=False, idx=0)
+            trie.stream_put_device(rt.seq[0, prompt_len:], 1, None, branch_length=bl + 1, final=False, idx=0)
         finished = (eos_token_id is not None and first in eos_token_id) or prompt_len + 1 >= max_length
         te = time.time()
         decoding_kwargs['fts'].append(te - ts)
         ts = te
 
-        graph = rt.graphs.get(key)
         min_out = max(dl // 2, 1)  # :710
-        while not finished:
-            if graph is None:
-                graph = self._capture_step(rt, key, use_trie, dl, bl, mql, min_out, tmode,
-                                           'hier' if fmt == 'hier' else 'one', max_length, accept)
-            graph.replay()
+        key = (use_trie, dl, bl, mql, tmode, fmt, akey, id(trie._t))
+        stream = torch.cuda.current_stream()
+        if not finished:
+            ent = self._graph_entry(rt, key, lambda: self._capture_step(
+                rt, trie, use_trie, dl, bl, mql, min_out, tmode, 'hier' if fmt == 'hier' else 'one', accept))
+            graphs = ent['graphs']
+            # step k+1 is enqueued before the host reads record k: the ~0.25 ms of host work per step (record read,
+            # python bookkeeping, streamer) overlaps the next verify forward; a step that runs after `finished` was
+            # raised changes nothing on the device (pia_accept no-op, zero-length stream_put)
+            events = [torch.cuda.Event(), torch.cuda.Event()]
+            k = 0
+            graphs[0].replay()
+            events[0].record(stream)
             rt.replays += 1
-            torch.cuda.current_stream().synchronize()
-            rec = rt.record_host
-            count, fin, n, status = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])
-            if status != 0:
-                from .. import _lib as L
-                L.check(status)
-            toks = rec[4:4 + count].tolist()
-            new_tokens.extend(toks)
-            decoding_kwargs['dls'].append(n)
-            decoding_kwargs['edls'].append(count)
-            decoding_kwargs['qts'].append(0.0)
-            if streamer is not None:
-                streamer.put(np.array([toks]))
-            if decoding_kwargs.get('debug_lookahead', False):
-                tok = decoding_kwargs.get('tokenizer', None)
-                words = '' if tok is None else tok.decode(toks)
-                print(f'decoding_length:{n} accept_length:{count} accept_token:{toks} accept_word:{words}')
-            finished = bool(fin)
-            te = time.time()
-            decoding_kwargs['fts'].append(te - ts)
-            ts = te
+            while True:
+                graphs[(k + 1) & 1].replay()
+                events[(k + 1) & 1].record(stream)
+                rt.replays += 1
+                events[k & 1].synchronize()
+                rec = rt.record_host[k & 1][0]
+                count, fin, n, status = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])
+                if status != 0:
+                    from .. import _lib as L
+                    L.check(status)
+                toks = rec[4:4 + count].tolist()
+                new_tokens.extend(toks)
+                decoding_kwargs['dls'].append(n)
+                decoding_kwargs['edls'].append(count)
+                decoding_kwargs['qts'].append(0.0)
+                if streamer is not None:
+                    streamer.put(np.array([toks]))
+                if decoding_kwargs.get('debug_lookahead', False):
+                    tok = decoding_kwargs.get('tokenizer', None)
+                    words = '' if tok is None else tok.decode(toks)
+                    print(f'decoding_length:{n} accept_length:{count} accept_token:{toks} accept_word:{words}')
+                te = time.time()
+                decoding_kwargs['fts'].append(te - ts)
+                ts = te
+                k += 1
+                if fin:
+                    break
+            events[k & 1].synchronize()  # the step launched ahead (a no-op on the device) has drained
         if use_trie:  # :1237-1238
             trie.stream_put([], branch_length=bl + 1, final=True, mode='output', idx=0)
         if streamer is not None:
             streamer.end()
         out_ids = torch.cat([input_ids.to(dev), torch.tensor([new_tokens], dtype=input_ids.dtype, device=dev)], dim=1)
         if return_dict_in_generate:
-            kw = {k: decoding_kwargs[k] for k in ('dls', 'edls', 'fts', 'qts')}
+            kw = {k_: decoding_kwargs[k_] for k_ in ('dls', 'edls', 'fts', 'qts')}
             return LookaheadDecoderOnlyOutput(sequences=out_ids, scores=() if output_scores else None, kwargs=kw)
         return out_ids
 
-    def _prefill_kv(self, rt, prompt_len):
-        """prompt tokens rt.seq[:prompt_len] -> KV rows [0, prompt_len); leaves the last prompt row's logits in
-        rt.logits[0].  The prompt goes through the verify kernels as chain drafts (row i attends rows <= i): per pass
-        the GEMMs see up to 256 rows at once, RoPE/KV-append and tree attention run per 64-row chunk."""
+    def _prefill_kv(self, rt, prompt_len, slot=0):
+        """prompt tokens rt.seq[slot, :prompt_len] -> KV rows [0, prompt_len) of that slot's cache; leaves the last
+        prompt row's hidden state in the prefill buffers and its logits in rt.logits[0].  The prompt goes through
+        the verify kernels as chain drafts (row i attends rows <= i): per pass the GEMMs see up to 256 rows at once,
+        RoPE/KV-append and tree attention run once over all 64-row chunks (one table slot per chunk)."""
         R, C = rt.max_nodes, rt.pf_chunks
-        if not hasattr(rt, 'chain'):
-            rt.chain = rt.chain_mask_rows()
         pb = rt.prefill_bufs
+        pb.slots = rt.prefill_slots(slot)
+        pb.kv_slot = slot
+        pad = rt.pad_host
         pos = 0
         while pos < prompt_len:
             m = min(R * C, prompt_len - pos)
-            pb.ids[:m] = rt.seq[pos:pos + m]
+            pb.ids[:m] = rt.seq[slot, pos:pos + m]
             pb.n_total.fill_(m)
             ns = [max(0, min(R, m - R * c)) for c in range(C)]
-            meta = torch.tensor([ns, [pos + R * c for c in range(C)]], dtype=torch.int32).to(rt.device)
-            rt.pf_n.copy_(meta[0])
-            rt.pf_P.copy_(meta[1])
-            masks = [rt.chain] * C
-            if rt.pad_len > pos:  # left padding (:1123-1131): pad columns are invisible, also inside a chain chunk
-                masks = []
+            rt.pf_meta_host.copy_(torch.tensor([ns, [pos + R * c for c in range(C)], [pad] * C], dtype=torch.int32))
+            rt.pf_meta.copy_(rt.pf_meta_host, non_blocking=True)
+            if pad > pos:  # left padding (:1123-1131): pad columns are invisible, also inside a chain chunk
                 for c in range(C):
-                    k = min(max(rt.pad_len - (pos + R * c), 0), R)
-                    masks.append(rt.chain if k == 0 else rt.chain_without_first(k))
-            pb.chunks = [(R * c, R * (c + 1), masks[c], rt.pf_n[c:c + 1], rt.pf_P[c:c + 1]) for c in range(C) if ns[c] > 0]
+                    k = min(max(pad - (pos + R * c), 0), R)
+                    pb.mask[R * c:R * (c + 1)] = rt.chain if k == 0 else rt.chain_without_first(k)
+                rt.pf_mask_dirty = True
+            elif rt.pf_mask_dirty:
+                pb.mask.copy_(rt.chain.repeat(C, 1))
+                rt.pf_mask_dirty = False
             last = pos + m >= prompt_len
             self._verify_layers(rt, bufs=pb, last_only=not last)
+            torch.cuda.current_stream().synchronize()  # pf_meta_host is rewritten by the next pass
             pos += m
         last_row = (prompt_len - 1) % (R * C)
-        torch.mm(pb.y[last_row:last_row + 1], self.lm_head.weight.t(), out=rt.logits[0:1])
-        rt.prefix_len.fill_(prompt_len)
+        return pb.y[last_row:last_row + 1]
+
+    def _prefill_logits(self, rt, prompt_len, slot=0, row=0):
+        """prefill of slot `slot` + the last prompt row's logits into rt.logits[row]"""
+        y = self._prefill_kv(rt, prompt_len, slot)
+        torch.mm(y, self.lm_head.weight.t(), out=rt.logits[row:row + 1])
 
     def _prefill(self, rt, prompt_len, accept):
         """prefill + the first generated token: (penalised) arg-max of the last prompt row's logits (:783-798)"""
-        self._prefill_kv(rt, prompt_len)
-        rt.ids[0, 0:1] = rt.seq[prompt_len - 1:prompt_len]
-        rt.mask[0].copy_(rt.chain)
+        self._prefill_logits(rt, prompt_len)
+        return self._first_token(rt, prompt_len, accept)
+
+    def _first_token(self, rt, prompt_len, accept):
+        rt.ids[0:1] = rt.seq[0, prompt_len - 1:prompt_len]
+        rt.mask.copy_(rt.chain)
         rt.n.fill_(1)
         rt.seq_len.fill_(prompt_len)
-        accept.run(rt.logits, rt.ids[0], rt.mask[0], rt.n, rt.seq, rt.seq_len, rt.pad_len, rt.acc_tokens, rt.acc_count,
-                   rt.acc_nodes, rt.prefix_len, rt.finished)
         rt.prefix_len.fill_(prompt_len)
-        return int(rt.acc_tokens[0].item())
+        accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
+                   rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length)
+        rt.prefix_len.fill_(prompt_len)
+        return int(rt.acc_tokens[0, 0].item())
 
     # ------------------------------------------------------------------ streaming (reference :1323-1350)
     @torch.no_grad()

@@ -94,17 +94,21 @@ __global__ void __launch_bounds__(512) k_rmsnorm(const __nv_bfloat16 *x, const f
   }
 }
 
-// grid = rows; thread = one (head, 8-wide d chunk) of q | k | v
+// grid = batch * rows_per_slot rows (pia_slots_t); thread = one (head, 8-wide d chunk) of q | k | v
 __global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv, const unsigned long long *mask,
-                                                        int mask_words, const int *d_n, const int *d_prefix, int pad_len,
+                                                        int mask_words, pia_slots_t sl,
                                                         int hq, int hkv, int hd, const __nv_bfloat16 *cos_t,
                                                         const __nv_bfloat16 *sin_t, int max_pos, __nv_bfloat16 *q_out,
                                                         __nv_bfloat16 *kc, __nv_bfloat16 *vc, int max_seq) {
   pdl_launch_dependents();
   pdl_wait();
-  const int i = blockIdx.x;
-  const int n = *d_n, P = *d_prefix;
-  if (i >= n) return;
+  const int i = blockIdx.x;                       // activation row
+  const int slot = i / sl.rows_per_slot, node = i % sl.rows_per_slot;
+  const int n = sl.d_n[slot], P = sl.d_prefix_len[slot];
+  const int pad_len = sl.d_pad_len ? sl.d_pad_len[slot] : 0;
+  if (node >= n) return;
+  kc += (long long)slot * sl.kv_slot_stride;
+  vc += (long long)slot * sl.kv_slot_stride;
   int depth = -1;
   for (int w = 0; w < mask_words; ++w) depth += __popcll(mask[(long long)i * mask_words + w]);
   // rowsum(attention_mask) - 1 (modeling_llama.py:587): visible prefix keys [pad_len, P) + visible draft keys - 1
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(256) k_rope_kv_append(const __nv_bfloat16 *qkv
   const int half = hd >> 1, cpr = hd >> 3;  // 16-byte chunks per head row
   const int row_elems = (hq + 2 * hkv) * hd;
   const __nv_bfloat16 *src = qkv + (long long)i * row_elems;
-  const int cache_row = P + i;
+  const int cache_row = P + node;
   const int total = (hq + 2 * hkv) * cpr;
   for (int c = threadIdx.x; c < total; c += blockDim.x) {
     const int head = c / cpr, ch = c % cpr;
@@ -202,19 +206,19 @@ extern "C" int pia_rmsnorm_partials(const float *d_x_parts, int n_parts, int64_t
   return PIA_OK;
 }
 
-extern "C" int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const int32_t *d_n,
-                                  const int32_t *d_prefix_len, int pad_len, int rows, int n_q_heads, int n_kv_heads,
-                                  int head_dim, const void *d_cos, const void *d_sin, int max_pos, void *d_q_out,
-                                  void *d_k_cache_layer, void *d_v_cache_layer, int max_seq, void *stream) {
-  PIA_REQUIRE(d_qkv && d_mask && d_n && d_prefix_len && d_cos && d_sin && d_q_out && d_k_cache_layer && d_v_cache_layer,
-              "null argument");
-  PIA_REQUIRE(head_dim % 16 == 0 && rows > 0 && mask_words >= 1 && mask_words <= 2, "bad rope arguments");
-  PIA_CUDA_CHECK(launch_kernel(k_rope_kv_append, dim3(rows), dim3(256), 0, (cudaStream_t)stream,
-                              (const __nv_bfloat16 *)d_qkv, (const unsigned long long *)d_mask, mask_words,
-                              (const int *)d_n, (const int *)d_prefix_len, pad_len, n_q_heads, n_kv_heads, head_dim,
-                              (const __nv_bfloat16 *)d_cos, (const __nv_bfloat16 *)d_sin, max_pos,
-                              (__nv_bfloat16 *)d_q_out, (__nv_bfloat16 *)d_k_cache_layer,
-                              (__nv_bfloat16 *)d_v_cache_layer, max_seq));
+extern "C" int pia_rope_kv_append(const void *d_qkv, const uint64_t *d_mask, int mask_words, const pia_slots_t *slots,
+                                  int n_q_heads, int n_kv_heads, int head_dim, const void *d_cos, const void *d_sin,
+                                  int max_pos, void *d_q_out, void *d_k_cache_layer, void *d_v_cache_layer, int max_seq,
+                                  void *stream) {
+  PIA_REQUIRE(d_qkv && d_mask && slots && slots->d_n && slots->d_prefix_len && d_cos && d_sin && d_q_out &&
+                  d_k_cache_layer && d_v_cache_layer, "null argument");
+  PIA_REQUIRE(slots->batch >= 1 && slots->rows_per_slot >= 1 && slots->kv_slot_stride >= 0, "bad slot table");
+  PIA_REQUIRE(head_dim % 16 == 0 && mask_words >= 1 && mask_words <= 2, "bad rope arguments");
+  PIA_CUDA_CHECK(launch_kernel(k_rope_kv_append, dim3(slots->batch * slots->rows_per_slot), dim3(256), 0,
+                              (cudaStream_t)stream, (const __nv_bfloat16 *)d_qkv, (const unsigned long long *)d_mask,
+                              mask_words, *slots, n_q_heads, n_kv_heads, head_dim, (const __nv_bfloat16 *)d_cos,
+                              (const __nv_bfloat16 *)d_sin, max_pos, (__nv_bfloat16 *)d_q_out,
+                              (__nv_bfloat16 *)d_k_cache_layer, (__nv_bfloat16 *)d_v_cache_layer, max_seq));
   count_launch();
   return PIA_OK;
 }

@@ -175,8 +175,10 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int b_mn_major) {
 struct Params {
   const __nv_bfloat16 *q;  // [max_nodes, Hq, HD]
   const unsigned long long *mask;
-  const int *d_n, *d_prefix;
-  int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, pad_len, max_seq, n_split, tiles_per_cta;
+  pia_slots_t sl;          // request slots: blockIdx.z = slot (rows, n, P, pad and KV planes of that slot)
+  int slot_planes;         // KV planes between consecutive slots' caches (0: shared cache)
+  int plane0;              // first plane of the cache slot 0 addresses
+  int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, max_seq, n_split, tiles_per_cta;
   float scale_log2;
   __nv_bfloat16 *out;            // [max_nodes, Hq, HD]
   unsigned long long *dbg;       // optional per-CTA phase timestamps (pia_attn_plan_set_debug)
@@ -187,7 +189,7 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define DBG(slot) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); } while (0)
+#define DBG(ev) do { if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (ev)] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v, Params p) {
@@ -205,7 +207,11 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   pdl_launch_dependents();
   pdl_wait();  // the split decision below already reads device state written by the step's earlier kernels
   const int split = blockIdx.x, group = blockIdx.y;
-  const int n = *p.d_n, P = *p.d_prefix;
+  const int slot = blockIdx.z;
+  const int n = p.sl.d_n[slot], P = p.sl.d_prefix_len[slot];
+  const int pad_len = p.sl.d_pad_len ? p.sl.d_pad_len[slot] : 0;
+  if (n <= 0) return;      // idle slot: every CTA of its clusters takes this exit
+  const long long row0 = (long long)slot * p.sl.rows_per_slot;  // first activation / mask row of the slot
   const int L = P + n;
   const int hq0 = group * p.heads_per_cta;
   const int hkv = hq0 / (p.n_q_heads / p.n_kv_heads);
@@ -265,7 +271,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0 && ntile > 0) {
-      const int plane = p.layer * p.n_kv_heads + hkv;
+      const int plane = p.plane0 + slot * p.slot_planes + p.layer * p.n_kv_heads + hkv;
       for (int i = 0; i < ntile; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
@@ -328,7 +334,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     {
       uint4 qv[8];  // Q row -> shared memory (UMMA K-major SWIZZLE_128B); each half loads one 64-wide d sub-tile
       const bool have = hs < p.heads_per_cta && node < n;
-      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((long long)node * p.n_q_heads + hq0 + hs) * HD) + half * 8;
+      const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((row0 + node) * p.n_q_heads + hq0 + hs) * HD) + half * 8;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) qv[ch] = have ? src[ch] : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -342,8 +348,8 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     const int pair_bar = 1 + (warp & 3);  // named barrier shared by the two warps of this lane quadrant
     unsigned long long mrow[2] = {0ull, 0ull};
     if (row_live) {
-      mrow[0] = p.mask[(long long)node * p.mask_words];
-      if (p.mask_words > 1) mrow[1] = p.mask[(long long)node * p.mask_words + 1];
+      mrow[0] = p.mask[(row0 + node) * p.mask_words];
+      if (p.mask_words > 1) mrow[1] = p.mask[(row0 + node) * p.mask_words + 1];
     }
     float acc[64];
 #pragma unroll
@@ -361,11 +367,11 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       tmem_ld_wait();
       // 32-bit visibility word of keys [kb, kb+32): prefix keys [pad_len, P) are visible to every row, the n draft
       // keys follow the row's ancestor bits (bits beyond the live nodes are never set in the trie's mask rows)
-      const bool all_visible = ((t0 + i) * BN >= p.pad_len) && ((t0 + i) * BN + BN <= P);
+      const bool all_visible = ((t0 + i) * BN >= pad_len) && ((t0 + i) * BN + BN <= P);
       auto vis32 = [&](int kb) -> uint32_t {
         if (all_visible) return 0xffffffffu;
         uint32_t m = 0;
-        const int lo = kb < p.pad_len ? p.pad_len : kb;
+        const int lo = kb < pad_len ? pad_len : kb;
         const int hi = kb + 32 < P ? kb + 32 : P;
         if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << (lo - kb);
         const int j0 = kb - P;
@@ -460,7 +466,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       // single split: normalise and write this half of the final bf16 row
       if (row_live) {
         const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((long long)node * p.n_q_heads + hq0 + hs) * HD + half * 64);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.out + ((row0 + node) * p.n_q_heads + hq0 + hs) * HD + half * 64);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
@@ -521,7 +527,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
       __nv_bfloat162 b0 = __floats2bfloat162_rn(o4.x * inv, o4.y * inv), b1 = __floats2bfloat162_rn(o4.z * inv, o4.w * inv);
-      reinterpret_cast<uint2 *>(p.out + ((long long)rn * p.n_q_heads + hq0 + rh) * HD)[c4] =
+      reinterpret_cast<uint2 *>(p.out + ((row0 + rn) * p.n_q_heads + hq0 + rh) * HD)[c4] =
           make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
     }
   }
@@ -563,7 +569,8 @@ static int encode_kv_map(CUtensorMap *m, void *base, const pia_attn_config_t &c)
     fn = (EncodeTiledFn)ptr;
   }
   // cache viewed as [planes = n_layers * n_kv_heads][max_seq][head_dim] bf16, box = 64 d x 128 keys x 1 plane
-  cuuint64_t dims[3] = {(cuuint64_t)c.head_dim, (cuuint64_t)c.max_seq, (cuuint64_t)c.n_layers * c.n_kv_heads};
+  cuuint64_t dims[3] = {(cuuint64_t)c.head_dim, (cuuint64_t)c.max_seq,
+                        (cuuint64_t)(c.n_slots > 0 ? c.n_slots : 1) * c.n_layers * c.n_kv_heads};
   cuuint64_t strides[2] = {(cuuint64_t)c.head_dim * 2, (cuuint64_t)c.max_seq * c.head_dim * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -629,21 +636,30 @@ extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) {
 }
 
 extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask,
-                                 const int32_t *d_n, const int32_t *d_prefix_len, int pad_len, float scale_mul,
-                                 void *d_out, void *stream) {
-  PIA_REQUIRE(p && d_q && d_mask && d_n && d_prefix_len && d_out, "null argument");
+                                 const pia_slots_t *slots, float scale_mul, void *d_out, void *stream) {
+  PIA_REQUIRE(p && d_q && d_mask && slots && slots->d_n && slots->d_prefix_len && d_out, "null argument");
   PIA_REQUIRE(layer >= 0 && layer < p->cfg.n_layers, "layer %d outside [0,%d)", layer, p->cfg.n_layers);
+  PIA_REQUIRE(slots->batch >= 1 && slots->batch <= 65535 && slots->rows_per_slot >= 1 &&
+                  slots->rows_per_slot <= p->cfg.max_nodes, "bad slot table");
+  const long long cache_elems = (long long)p->cfg.n_layers * p->cfg.n_kv_heads * p->cfg.max_seq * p->cfg.head_dim;
+  const int plan_slots = p->cfg.n_slots > 0 ? p->cfg.n_slots : 1;
+  PIA_REQUIRE(slots->kv_first_slot >= 0 && slots->kv_first_slot < plan_slots, "kv_first_slot outside the plan's caches");
+  PIA_REQUIRE(slots->kv_slot_stride == 0 || (slots->kv_slot_stride == cache_elems &&
+                                              slots->kv_first_slot + slots->batch <= plan_slots),
+              "kv_slot_stride must be 0 or one whole cache, and the plan must span `batch` caches");
   Params a;
   a.q = (const __nv_bfloat16 *)d_q;
   a.mask = (const unsigned long long *)d_mask;
-  a.d_n = d_n; a.d_prefix = d_prefix_len;
+  a.sl = *slots;
+  a.slot_planes = slots->kv_slot_stride ? p->cfg.n_layers * p->cfg.n_kv_heads : 0;
+  a.plane0 = slots->kv_first_slot * p->cfg.n_layers * p->cfg.n_kv_heads;
   a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
-  a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.pad_len = pad_len; a.max_seq = p->cfg.max_seq;
+  a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.max_seq = p->cfg.max_seq;
   a.n_split = p->n_split; a.tiles_per_cta = p->tiles_per_cta;
   a.out = (__nv_bfloat16 *)d_out; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
-  PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(p->n_split, p->n_groups), dim3(NTHREADS), SMEM_TOTAL, s,
+  PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(p->n_split, p->n_groups, slots->batch), dim3(NTHREADS), SMEM_TOTAL, s,
                                        (unsigned)p->n_split, p->map_k, p->map_v, a));
   count_launch();
   return PIA_OK;

@@ -113,10 +113,16 @@ __device__ int find_child(const Dev &D, const Node &p, int token) {
 // ---------------------------------------------------------------------------------------------------
 // put / stream_put
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int live_slot(const Dev &D, int slot, const int *d_slot) {
+  if (d_slot != nullptr) { slot = *d_slot; if (slot < 0 || slot >= D.n_slots) slot = 0; }
+  return slot;
+}
+
 __global__ void __launch_bounds__(NT) k_put_prepare(Dev D, const int *tokens, int n, const int *d_n, int B,
-                                                    int is_stream, int final, int slot) {
+                                                    int is_stream, int final, int slot, const int *d_slot) {
   __shared__ int s_cut;
   const int tid = threadIdx.x;
+  slot = live_slot(D, slot, d_slot);
   int n_in = n;
   if (d_n != nullptr) { int v = *d_n; n_in = v < n ? v : n; }
   if (n_in < 0) n_in = 0;
@@ -266,8 +272,9 @@ __device__ void add_update(const Dev &D, int key, int flag, int *list, int *coun
 // in list order (child insertion order is observable), so the first occurrence of a key is the "leader"
 // and replays every later occurrence itself; distinct keys own disjoint trees and run concurrently.
 __global__ void __launch_bounds__(NT) k_put_insert(Dev D, const int *tokens, int B, int mode, int idx, int is_stream,
-                                                   int slot) {
+                                                   int slot, const int *d_slot) {
   const int lane = lane_id();
+  slot = live_slot(D, slot, d_slot);
   const int p = blockIdx.x * (NT / 32) + warp_id();
   const int npos = D.hdr->put_npos, len = D.hdr->put_len;
   if (p >= npos) return;
@@ -308,7 +315,8 @@ __global__ void k_tree_put(Dev D, int key, const int *tokens, int n, int mode, i
   if (n > 0) warp_insert(D, key, tokens, n, mode == PIA_MODE_OUTPUT, idx);
 }
 
-__global__ void k_put_finish(Dev D, int B, int final, int slot) {
+__global__ void k_put_finish(Dev D, int B, int final, int slot, const int *d_slot) {
+  slot = live_slot(D, slot, d_slot);
   // stream_put tail: keep the last B tokens as carry (:401-402) or clear on final (:404)
   __shared__ int tmp[128];
   const int tid = threadIdx.x;
@@ -464,7 +472,7 @@ __device__ void hist_kth(const Hist *h, long long rank, unsigned long long *resu
 }
 
 struct GetParams {
-  const int *queries, *qlen, *d_idx;
+  const int *queries, *qlen, *d_idx, *d_max_seq;
   int batch, q_stride, max_query, idx, dl, bl, min_in, min_out, mode, kind, flags, max_seq;
   int *out_ids; unsigned long long *out_mask; int *out_n, *out_sizes, *out_nsizes, *status;
 };
@@ -890,7 +898,8 @@ __global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
     if (P.flags & PIA_GET_TAIL) {
       nq = len < P.max_query ? len : P.max_query;
       qsrc = P.queries + (long long)b * P.q_stride + (len - nq);
-      if (P.max_seq > 0) { int lim = P.max_seq - len - 1; if (lim < 0) lim = 0; if (bl > lim) bl = lim; }
+      const int max_seq = P.d_max_seq ? *P.d_max_seq : P.max_seq;
+      if (max_seq > 0) { int lim = max_seq - len - 1; if (lim < 0) lim = 0; if (bl > lim) bl = lim; }
     } else {
       nq = len < P.q_stride ? len : P.q_stride;
       qsrc = P.queries + (long long)b * P.q_stride;
@@ -1231,7 +1240,7 @@ static int launch_squeeze(pia_trie *t, cudaStream_t s) {
 }
 
 static int put_common(pia_trie *t, const int32_t *d_tokens, int n, const int32_t *d_n, int B, int mode, int idx,
-                      int final, int is_stream, cudaStream_t s) {
+                      int final, int is_stream, cudaStream_t s, const int32_t *d_slot = nullptr) {
   PIA_REQUIRE(t, "null trie");
   PIA_REQUIRE(n >= 0 && n <= t->cfg.max_put_tokens, "token list of %d exceeds max_put_tokens=%d", n, t->cfg.max_put_tokens);
   PIA_REQUIRE(n == 0 || d_tokens, "null tokens");
@@ -1239,17 +1248,18 @@ static int put_common(pia_trie *t, const int32_t *d_tokens, int n, const int32_t
   PIA_REQUIRE(mode == PIA_MODE_INPUT || mode == PIA_MODE_OUTPUT, "put mode must be input or output");
   if (mode == PIA_MODE_INPUT) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
   const int slot = is_stream ? idx : 0;
-  if (is_stream) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "stream idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
-  k_put_prepare<<<1, NT, 0, s>>>(t->dev, d_tokens, n, d_n, B, is_stream, final, slot);
+  if (is_stream && !d_slot) PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "stream idx %d outside [0,%d)", idx, t->cfg.n_input_slots);
+  PIA_REQUIRE(!(d_slot && final), "a final stream_put needs the request idx on the host");
+  k_put_prepare<<<1, NT, 0, s>>>(t->dev, d_tokens, n, d_n, B, is_stream, final, slot, d_slot);
   PIA_LAUNCH_CHECK();
   const int max_pos = is_stream ? n + 64 : n;
   if (max_pos > 0) {
     const int grid = (max_pos + (NT / 32) - 1) / (NT / 32);
-    k_put_insert<<<grid, NT, 0, s>>>(t->dev, d_tokens, B, mode, idx, is_stream, slot);
+    k_put_insert<<<grid, NT, 0, s>>>(t->dev, d_tokens, B, mode, idx, is_stream, slot, d_slot);
     PIA_LAUNCH_CHECK();
   }
   if (is_stream) {
-    k_put_finish<<<1, 128, 0, s>>>(t->dev, B, final, slot);
+    k_put_finish<<<1, 128, 0, s>>>(t->dev, B, final, slot, d_slot);
     PIA_LAUNCH_CHECK();
   }
   if (final) {
@@ -1276,15 +1286,16 @@ extern "C" int pia_trie_tree_put(pia_trie_t *t, int tree_token, const int32_t *d
   return PIA_OK;
 }
 extern "C" int pia_trie_stream_put(pia_trie_t *t, const int32_t *d_tokens, int n, const int32_t *d_n,
-                                   int branch_length, int idx, int final, void *stream) {
-  return put_common(t, d_tokens, n, d_n, branch_length, PIA_MODE_OUTPUT, idx, final, 1, (cudaStream_t)stream);
+                                   int branch_length, int idx, const int32_t *d_idx, int final, void *stream) {
+  return put_common(t, d_tokens, n, d_n, branch_length, PIA_MODE_OUTPUT, idx, final, 1, (cudaStream_t)stream, d_idx);
 }
 
 extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32_t *d_qlen, int batch, int q_stride,
                             int max_query_length, const int32_t *d_idx, int idx, int decoding_length,
                             int branch_length, int min_input_size, int min_output_size, int mode, int kind, int flags,
-                            int max_seq_length, int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n,
-                            int32_t *d_out_sizes, int32_t *d_out_nsizes, int32_t *d_status, void *stream) {
+                            int max_seq_length, const int32_t *d_max_seq_length, int32_t *d_out_ids,
+                            uint64_t *d_out_mask, int32_t *d_out_n, int32_t *d_out_sizes, int32_t *d_out_nsizes,
+                            int32_t *d_status, void *stream) {
   PIA_REQUIRE(t, "null trie");
   PIA_REQUIRE(batch >= 1 && d_queries && d_qlen, "bad query batch");
   PIA_REQUIRE(decoding_length >= 1 && decoding_length <= 128, "decoding_length %d outside [1,128]", decoding_length);
@@ -1297,7 +1308,7 @@ extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32
   P.queries = d_queries; P.qlen = d_qlen; P.d_idx = d_idx; P.batch = batch; P.q_stride = q_stride;
   P.max_query = max_query_length > 0 ? max_query_length : q_stride; P.idx = idx; P.dl = decoding_length;
   P.bl = branch_length; P.min_in = min_input_size; P.min_out = min_output_size; P.mode = mode; P.kind = kind;
-  P.flags = flags; P.max_seq = max_seq_length;
+  P.flags = flags; P.max_seq = max_seq_length; P.d_max_seq = d_max_seq_length;
   P.out_ids = d_out_ids; P.out_mask = (unsigned long long *)d_out_mask; P.out_n = d_out_n; P.out_sizes = d_out_sizes;
   P.out_nsizes = d_out_nsizes; P.status = d_status;
   const int grid = batch < t->dev.max_resident ? batch : t->dev.max_resident;

@@ -211,11 +211,16 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=sk)
         return plans
 
-    @staticmethod
-    def _mk_gemm(w, x, split_k=1):
-        """HBM-tiled copy of the weight when its row count allows it (N % 128 == 0), else the row-major tensor"""
+    def _mk_gemm(self, w, x, split_k=1):
+        """HBM-tiled copy of the weight when its row count allows it (N % 128 == 0), else the row-major tensor.
+        The tiled copies belong to the model (one per weight), not to a runtime: rebuilding the runtime for a longer
+        max_seq or another slot count must not duplicate 9 GB of weights"""
         if w.shape[0] % 128 == 0:
-            return ops.Gemm(ops.tile_weight(w), x, split_k=split_k, tiled=True)
+            cache = self.__dict__.setdefault('_tiled_weights', {})
+            key = (w.data_ptr(), tuple(w.shape))
+            if key not in cache:
+                cache[key] = ops.tile_weight(w)
+            return ops.Gemm(cache[key], x, split_k=split_k, tiled=True)
         return ops.Gemm(w.contiguous(), x, split_k=split_k)
 
     # ------------------------------------------------------------------ weight prefetch beside the small kernels
@@ -278,9 +283,10 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
 
     def _verify_layers(self, rt, bufs=None, last_only=False):
         """embed -> decoder layers -> final norm -> lm_head over the rows described by `bufs` (default: the decode
-        buffers = one draft of <= max_nodes tree nodes in rt.ids / rt.mask / rt.n on top of rt.prefix_len cached
-        tokens).  A prefill pass uses wider buffers holding several 64-row chain chunks: the GEMMs run once over all
-        rows, RoPE/KV-append and tree attention run per chunk.  Writes bufs.logits (skipped when last_only)."""
+        buffers = the drafts of the request slots in rt.ids / rt.mask / rt.n on top of rt.prefix_len cached tokens;
+        bufs.slots says which slot owns which rows).  A prefill pass uses wider buffers holding several 64-row chain
+        chunks (one table slot each): the GEMMs run once over all rows.  Writes bufs.logits (skipped when
+        last_only)."""
         self.fuse()
         b = bufs if bufs is not None else rt.decode_bufs
         g = rt.g
@@ -308,12 +314,10 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
                 gw = lp['gate_up'].weight
                 self._prefetch(pf, [(a.o_proj.weight, pf['o'], 0),
                                     (gw, pf['gate_up'], gw.shape[1] * gw.shape[2] * gw.shape[3] * 2 if gw.dim() == 4 else 0)])
-            for (r0, r1, mask, n, P) in b.chunks:
-                ops.rope_kv_append(b.qkv[r0:r1], mask, n, P, rt.pad_len, g['n_q_heads'], g['n_kv_heads'],
-                                   g['head_dim'], rt.rope_cos, rt.rope_sin, b.q[r0:r1], rt.k_cache[li], rt.v_cache[li],
-                                   rt.max_seq)
-            for (r0, r1, mask, n, P) in b.chunks:
-                rt.plan.forward(li, b.q[r0:r1], mask, n, P, rt.pad_len, b.attn[r0:r1])
+            # every request slot / prefill chunk of the table in one launch each (pia_slots_t)
+            ops.rope_kv_append(b.qkv, b.mask, b.slots, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], rt.rope_cos,
+                               rt.rope_sin, b.q, rt.k_layer(li, b.kv_slot), rt.v_layer(li, b.kv_slot), rt.max_seq)
+            rt.plan.forward(li, b.q, b.mask, b.slots, b.attn)
             if lp and 'o' in lp:
                 o = lp['o'].run(64)
                 x, parts, resid_in = (o, None, b.resid) if lp['o'].splits == 1 else (None, o, b.resid)
@@ -352,22 +356,19 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             pad_len = int(nz[0]) if len(nz) else P
         tree = am[:, P:]
         need = P + n + 1
-        rt = self._runtime(need if self._rt is not None and self._rt.max_seq >= need else max(need, 256),
-                           64 if n <= 64 else 128)
+        have = self._rt
+        rt = self._runtime(need if have is not None and have.max_seq >= need else max(need, 256),
+                           64 if n <= 64 else 128, keep_cache=P > 0)
         assert n <= rt.max_nodes, 'at most 128 tree nodes per forward; prefill goes through generate()'
-        rows = torch.zeros((rt.max_nodes, rt.max_nodes // 64), dtype=torch.int64)
         import numpy as np
-        bits = np.zeros((rt.max_nodes, rt.max_nodes // 64), dtype=np.uint64)
-        for i in range(n):
-            for j in np.flatnonzero(tree[i]):
-                bits[i, j >> 6] |= np.uint64(1) << np.uint64(j & 63)
-        rows = torch.from_numpy(bits.view(np.int64))
-        rt.mask[0].copy_(rows.to(rt.device))
-        rt.ids[0, :n] = input_ids[0].to(device=rt.device, dtype=torch.int32)
-        rt.decode_bufs.set_chunk_rows(n)
+        packed = np.packbits(np.pad(tree.astype(np.uint8), ((0, rt.max_nodes - n), (0, rt.max_nodes - n))), axis=1,
+                             bitorder='little')
+        rows = torch.from_numpy(packed.view(np.int64).reshape(rt.max_nodes, rt.max_nodes // 64))
+        rt.mask.copy_(rows.to(rt.device))
+        rt.ids[:n] = input_ids[0].to(device=rt.device, dtype=torch.int32)
         rt.n.fill_(n)
         rt.prefix_len.fill_(P)
-        rt.pad_len = pad_len
+        rt.set_request(0, pad_len, 1 << 30)
         self._verify_layers(rt)
         logits = rt.logits[:n].clone()[None]
         return logits, P + n

@@ -35,8 +35,9 @@ rows = np.array([(1 << (i + 1)) - 1 for i in range(R)], dtype=np.uint64)
 mask[:, 0] = torch.from_numpy(rows.view(np.int64)).to(dev)
 dn = torch.tensor([a.n], dtype=torch.int32, device=dev)
 dP = torch.tensor([a.P], dtype=torch.int32, device=dev)
+slots = ops.Slots(dn, dP, None, 64)
 for li in range(a.layers):
-    plan.forward(li, q, mask, dn, dP, 0, out)
+    plan.forward(li, q, mask, slots, out)
 torch.cuda.synchronize()
 dbg = torch.zeros((ns.value * ng.value, 16), dtype=torch.int64, device=dev)
 L.check(plan.lib.pia_attn_plan_set_debug(plan.h, dbg.data_ptr()))
@@ -46,7 +47,7 @@ for trial in range(3):
     dbg.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    plan.forward(trial + 3, q, mask, dn, dP, 0, out)
+    plan.forward(trial + 3, q, mask, slots, out)
     e1.record()
     torch.cuda.synchronize()
     t = dbg.cpu().numpy().astype(np.int64)

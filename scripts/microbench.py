@@ -26,8 +26,9 @@ cfg, _ = bench.make_config(a.model)
 model = LlamaForCausalLM(cfg, device=dev).init_weights(seed=0).requires_grad_(False)
 model.fuse()
 rt = model._runtime(a.max_seq, 64)
-rt.mask[0].copy_(rt.chain_mask_rows())
+rt.mask.copy_(rt.chain)
 rt.n.fill_(a.n)
+draft = dict(ids=rt.ids, mask=rt.mask, n=rt.n, sizes=rt.sizes, nsizes=rt.nsizes, status=rt.status)
 rt.prefix_len.fill_(a.P)
 g = rt.g
 L0 = model.model.layers[0]
@@ -61,9 +62,9 @@ if a.forward_only:
     sys.exit(0)
 L = a.P + a.n
 kv_bytes = 2 * L * g['n_kv_heads'] * g['head_dim'] * 2 + 2 * a.n * g['n_q_heads'] * g['head_dim'] * 2
-timeit('tree_attn+combine (32 layers)', lambda: [rt.plan.forward(li, rt.q, rt.mask[0], rt.n, rt.prefix_len, 0, rt.attn) for li in range(NL)], NL, bytes_per=kv_bytes)
+timeit('tree_attn+combine (32 layers)', lambda: [rt.plan.forward(li, rt.q, rt.mask, rt.decode_bufs.slots, rt.attn) for li in range(NL)], NL, bytes_per=kv_bytes)
 timeit('rmsnorm', lambda: [ops.rmsnorm(rt.h, rt.resid, layers[li].input_layernorm.weight, 1e-5, rt.resid, rt.y) for li in range(NL)], NL)
-timeit('rope_kv_append', lambda: [ops.rope_kv_append(rt.qkv, rt.mask[0], rt.n, rt.prefix_len, 0, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], rt.rope_cos, rt.rope_sin, rt.q, rt.k_cache[li], rt.v_cache[li], rt.max_seq) for li in range(NL)], NL)
+timeit('rope_kv_append', lambda: [ops.rope_kv_append(rt.qkv, rt.mask, rt.decode_bufs.slots, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], rt.rope_cos, rt.rope_sin, rt.q, rt.k_layer(li), rt.v_layer(li), rt.max_seq) for li in range(NL)], NL)
 gu = torch.zeros((64, 2 * g['inter']), dtype=torch.bfloat16, device=dev)
 act = torch.zeros((64, g['inter']), dtype=torch.bfloat16, device=dev)
 timeit('silu_mul', lambda: [ops.silu_mul(gu, act) for _ in range(NL)], NL)
@@ -80,9 +81,9 @@ trie = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
 docs = bench.phrase_bank_prompts(64, cfg.vocab_size, seed=3)
 for d in docs:
     trie.put(d, branch_length=9, mode='output', idx=-1)
-rt.seq[:256] = torch.tensor(docs[0], dtype=torch.int32, device=dev)
+rt.seq[0, :256] = torch.tensor(docs[0], dtype=torch.int32, device=dev)
 rt.seq_len.fill_(200)
-timeit('trie get (1 query, tail mode)', lambda: trie.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=rt.draft), 1)
+timeit('trie get (1 query, tail mode)', lambda: trie.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=draft), 1)
 print('draft n =', int(rt.n))
 
 import sys; sys.exit(0) if __import__("os").environ.get("PIA_ATTN_TILES_PER_CTA") else None
@@ -93,9 +94,9 @@ for d in docs:
     big.put(d, branch_length=9, mode='output', idx=-1)
 st0 = big.stats()
 for name, q in (('hot (3,3)', [3, 3]), ('doc pair', docs[5][100:102]), ('rare', docs[7][40:42])):
-    rt.seq[:2] = torch.tensor(q, dtype=torch.int32, device=dev)
+    rt.seq[0, :2] = torch.tensor(q, dtype=torch.int32, device=dev)
     rt.seq_len.fill_(2)
     s0 = big.stats()
-    us = timeit(f'trie get 1M-node forest, {name}', lambda: big.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=rt.draft), 1)
+    us = timeit(f'trie get 1M-node forest, {name}', lambda: big.get_device(rt.seq, rt.seq_len, 64, 8, min_output_size=32, out=draft), 1)
     s1 = big.stats()
     print('   draft n =', int(rt.n), ' nodes visited per call ~', (s1['nodes_visited'] - s0['nodes_visited']) // 22)

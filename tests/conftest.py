@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    config.addinivalue_line('markers', 'big: gpu tests at the BASELINE model shapes (tens of GB, about a minute each); '
+                                       'part of -m gpu, deselect with -m "gpu and not big" while iterating')
 
 
 def pytest_collection_modifyitems(config, items):

@@ -22,7 +22,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from tests.golden.ref_loop import import_reference, make_driver, run_reference_request  # noqa: E402
+from tests.golden.ref_loop import (import_reference, make_batch_driver, make_driver, run_reference_batch,  # noqa: E402
+                                   run_reference_request)
 from tests.tiny_models import prompts, tiny_hf_model  # noqa: E402
 
 
@@ -76,8 +77,54 @@ def scenario(name, family, dtype, seed, vocab, requests, dl=64, bl=8, reps=2, **
           f'{os.path.getsize(path) // 1024} KB')
 
 
+def batch_scenario(name, family, dtype, seed, vocab, batches, dl=64, bl=8, reps=2, **gen):
+    """batches: list of (LongTensor [bs, L], max_new_tokens).  Runs the reference's BATCHED loop
+    (pretrained_model_batch.py:1002-1330 + bat_get) and records every verify step."""
+    _pm, _pmb, LookaheadCache = import_reference()
+    torch.set_num_threads(4)
+    hf = tiny_hf_model(family, seed=seed, dtype=dtype, vocab=vocab)
+    rec = []
+    drv = make_batch_driver(hf, LookaheadCache(), rec)
+    calls, arrays = [], {}
+    for rep in range(reps):
+        for ids, mnt in batches:
+            s0 = len(rec)
+            r = run_reference_batch(drv, ids, mnt, decoding_length=dl, branch_length=bl, **gen)
+            steps = []
+            for si in range(s0, len(rec)):
+                st = rec[si]
+                key = f'logits_{si}'
+                lg = st['logits'].contiguous()
+                arrays[key] = lg.view(torch.int16).numpy().view(np.uint16).copy() if lg.dtype == torch.bfloat16 \
+                    else lg.float().numpy().copy()
+                steps.append(dict(prefill=st['prefill'], before=st['before'], logits=key, tokens=st['tokens'],
+                                  dls=st['dls'], edls=st['edls']))
+            calls.append(dict(input_ids=ids.tolist(), max_new_tokens=mnt, sequences=r['sequences'], dls=r['dls'],
+                              edls=r['edls'], steps=steps))
+    meta = dict(name=name, family=family, dtype=str(dtype).split('.')[-1], model_seed=seed, vocab=vocab,
+                decoding_length=dl, branch_length=bl, gen=gen, calls=calls)
+    arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(HERE, f'batchloop_{name}.npz')
+    np.savez_compressed(path, **arrays)
+    edl = [e for c in calls for e in c['edls'][len(c['input_ids']):]]
+    print(f'{name}: {len(calls)} batches, {len(rec)} steps, mean edl {np.mean(edl):.2f}, max edl {max(edl)}, '
+          f'{os.path.getsize(path) // 1024} KB')
+
+
 def main():
     V = 96
+    b3 = torch.cat(prompts(31, 3, 20, V), 0)
+    b2 = torch.cat(prompts(32, 2, 16, V), 0)
+    batch_scenario('llama_bf16_bs3_bs2', 'llama', torch.bfloat16, 2, V, [(b3, 32), (b2, 28)], pad_token_id=0)
+    # an eos that one request meets early (requests leave the batch at different steps, _early_stop :937-980) +
+    # repetition penalty
+    hf = tiny_hf_model('mistral', seed=3, dtype=torch.bfloat16, vocab=V)
+    _pm, _pmb, LookaheadCache = import_reference()
+    b4 = torch.cat(prompts(33, 4, 14, V), 0)
+    probe = run_reference_batch(make_batch_driver(hf, LookaheadCache(), None), b4, 30, repetition_penalty=1.1)
+    eos = probe['sequences'][1][14 + 8]
+    batch_scenario('mistral_bf16_bs4_rp11_eos', 'mistral', torch.bfloat16, 3, V, [(b4, 30)], repetition_penalty=1.1,
+                   eos_token_id=int(eos), pad_token_id=0)
     ps = [dict(prompt=p, max_new_tokens=40) for p in prompts(21, 3, 24, V)]
     scenario('llama_bf16', 'llama', torch.bfloat16, 2, V, ps)
     scenario('mistral_bf16_rp11', 'mistral', torch.bfloat16, 3, V,

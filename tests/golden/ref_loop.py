@@ -144,3 +144,94 @@ def run_reference_request(driver, input_ids, max_new_tokens, eos_token_id=2, rep
                                           eos_token_id=eos_token_id, output_scores=False, return_dict_in_generate=True,
                                           output_attentions=False, output_hidden_states=False, **kw)
     return dict(sequences=out.sequences[0].tolist(), dls=list(out.kwargs['dls']), edls=list(out.kwargs['edls']))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batched loop: /root/reference/lookahead/lookahead/common/pretrained_model_batch.py
+#   lookahead_generation :1002-1330, lookahead_prepare_inputs_for_generation :664-759,
+#   _lookahead_update_model_kwargs_for_generation :767-935, _early_stop :937-980, _update_cache :982-989
+# borrowed unmodified; the driver's own code is the batched patched forward the reference expects from its model
+# (models/llama/modeling_llama_batch.py:355-405: preallocated [bs, H, decoding_max_length, D] caches, request b's draft
+# rows written at its cursor), evaluated request by request with an installed HF model.
+# ----------------------------------------------------------------------------------------------------------------
+def make_batch_driver(hf, trie, record=None):
+    _pm, pmb, _LC = import_reference()
+    P = pmb.LookaheadPreTrainedModel
+
+    class RefBatchDriver(object):
+        lookahead_generation = P.lookahead_generation
+        lookahead_prepare_inputs_for_generation = P.lookahead_prepare_inputs_for_generation
+        _ref_update = P._lookahead_update_model_kwargs_for_generation
+        _early_stop = P._early_stop
+        _update_cache = P._update_cache
+        _update_cache_with_axis_2 = P._update_cache_with_axis_2
+        _get_position_ids = P._get_position_ids
+
+        def __init__(self):
+            self.config = hf.config
+            self.generation_config = hf.generation_config
+            self.lookahead_cache = trie
+
+        def __call__(self, input_ids=None, past_key_values=None, use_cache=None, attention_mask=None, return_dict=True,
+                     output_attentions=None, output_hidden_states=None, position_ids=None, decoding_kwargs=None, **kw):
+            bs, n = input_ids.shape
+            if past_key_values is None:
+                Lmax = decoding_kwargs['decoding_max_length']
+                outs = [_hf_forward(hf, input_ids[b:b + 1], attention_mask[b:b + 1], None) for b in range(bs)]
+                past = []
+                for li in range(len(outs[0][1])):
+                    k = torch.cat([o[1][li][0] for o in outs], 0)
+                    v = torch.cat([o[1][li][1] for o in outs], 0)
+                    z = torch.zeros((bs, k.shape[1], Lmax - n, k.shape[3]), dtype=k.dtype)
+                    past.append((torch.cat([k, z], 2), torch.cat([v, z], 2)))
+                return _Out(logits=torch.cat([o[0] for o in outs], 0), past_key_values=tuple(past))
+            cursors = decoding_kwargs['decoding_cursors']
+            logits = []
+            for b in range(bs):
+                cur = cursors[b]
+                pb = tuple((k[b:b + 1, :, :cur], v[b:b + 1, :, :cur]) for k, v in past_key_values)
+                lg, newp = _hf_forward(hf, input_ids[b:b + 1], attention_mask[b:b + 1, :, :, :cur + n], pb)
+                for (k, v), (nk, nv) in zip(past_key_values, newp):
+                    k[b, :, cur:cur + n] = nk[0, :, cur:cur + n]
+                    v[b, :, cur:cur + n] = nv[0, :, cur:cur + n]
+                logits.append(lg)
+            return _Out(logits=torch.cat(logits, 0), past_key_values=past_key_values)
+
+        def _lookahead_update_model_kwargs_for_generation(self, outputs, model_kwargs, is_encoder_decoder=False,
+                                                          standardize_cache_format=False, logits_processor=None,
+                                                          input_ids=None):
+            dk = model_kwargs['decoding_kwargs']
+            prefill = model_kwargs.get('past_key_values', None) is None
+            before = None if prefill else dict(ids=[list(x) for x in dk['decoding_ids']],
+                                               cursors=list(dk['decoding_cursors']),
+                                               batch_indices=list(dk['batch_indices']))
+            n0 = len(dk['edls'])
+            res = self._ref_update(outputs, model_kwargs, is_encoder_decoder=is_encoder_decoder,
+                                   standardize_cache_format=standardize_cache_format,
+                                   logits_processor=logits_processor, input_ids=input_ids)
+            if record is not None:
+                record.append(dict(prefill=prefill, before=before, logits=outputs.logits.detach().clone(),
+                                   tokens=[list(t) for t in res['next_token_list']],
+                                   dls=list(dk['dls'][n0:]), edls=list(dk['edls'][n0:])))
+            return res
+
+    return RefBatchDriver()
+
+
+def run_reference_batch(driver, input_ids, max_new_tokens, eos_token_id=2, repetition_penalty=1.0,
+                        decoding_length=64, branch_length=8, decoding_mode='hier', pad_token_id=0):
+    """one call of the reference's batched lookahead_generation()"""
+    from transformers import LogitsProcessorList, MaxLengthCriteria, RepetitionPenaltyLogitsProcessor, StoppingCriteriaList
+    max_length = input_ids.shape[1] + max_new_tokens
+    lp = LogitsProcessorList()
+    if repetition_penalty != 1.0:
+        lp.append(RepetitionPenaltyLogitsProcessor(penalty=repetition_penalty))
+    sc = StoppingCriteriaList([MaxLengthCriteria(max_length=max_length)])
+    dk = {'use_lookahead': True, 'decoding_length': decoding_length, 'branch_length': branch_length,
+          'decoding_mode': decoding_mode, 'do_sample': False}
+    with torch.no_grad():
+        out = driver.lookahead_generation(input_ids.clone(), logits_processor=lp, stopping_criteria=sc,
+                                          pad_token_id=pad_token_id, eos_token_id=eos_token_id, output_scores=False,
+                                          return_dict_in_generate=True, output_attentions=False,
+                                          output_hidden_states=False, decoding_kwargs=dk, use_cache=True)
+    return dict(sequences=out.sequences.tolist(), dls=list(out.kwargs['dls']), edls=list(out.kwargs['edls']))

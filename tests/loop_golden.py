@@ -39,3 +39,21 @@ def mask01(step):
     rows = step_mask(step)
     n = len(rows)
     return np.array([[(int(r) >> j) & 1 for j in range(n)] for r in rows], dtype=np.int64)
+
+
+def batch_names():
+    return sorted(os.path.basename(f)[10:-4] for f in glob.glob(os.path.join(GOLD, 'batchloop_*.npz')))
+
+
+def load_batch(name):
+    z = np.load(os.path.join(GOLD, f'batchloop_{name}.npz'))
+    return json.loads(bytes(z['meta']).decode()), z
+
+
+def batch_step_logits(meta, z, step):
+    """[k, n, V] tensor of one recorded batched verify step (k = active requests in batch_indices order)"""
+    import torch
+    a = z[step['logits']]
+    if meta['dtype'] == 'bfloat16':
+        return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+    return torch.from_numpy(a.copy())

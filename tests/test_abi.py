@@ -34,7 +34,7 @@ def test_ctypes_table_matches_header():
     from painlessinferenceacceleration_b200 import _lib
     assert sorted(_lib.SYMBOLS) == _declared()
     L = _lib.load()
-    assert L.pia_abi_version() == 1
+    assert L.pia_abi_version() == 2  # v2: request slots (pia_slots_t), device-resident max_length / idx
     assert L.pia_launch_count() == 0
     assert L.pia_last_error() is not None
 
@@ -64,3 +64,29 @@ def test_no_cpu_fallback_without_cuda():
     from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
     with pytest.raises(RuntimeError):
         LookaheadCache()
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / field offsets of every struct that crosses the ABI by pointer, measured by compiling the header with gcc"""
+    import subprocess
+    from painlessinferenceacceleration_b200 import _lib
+    src = tmp_path / 'layout.c'
+    structs = {'pia_trie_config_t': _lib.TrieConfig, 'pia_trie_stats_t': _lib.TrieStats,
+               'pia_attn_config_t': _lib.AttnConfig, 'pia_accept_config_t': _lib.AcceptConfig,
+               'pia_slots_t': _lib.Slots}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/pia_b200.h"', 'int main(void){']
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for fname, _t in cls._fields_:
+            lines.append(f'printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('printf("\\n");')
+    lines += ['return 0;}']
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-o', str(exe), str(src)])
+    out = subprocess.check_output([str(exe)]).decode().strip().split('\n')
+    for line, (cname, cls) in zip(out, structs.items()):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == ctypes.sizeof(cls), cname
+        assert [int(x) for x in parts[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], cname

@@ -13,6 +13,7 @@ from tests.tiny_models import prompts, tiny_hf_model
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+EPS = 0.35  # fp32 logit margin below which a bf16 implementation may legitimately pick the other candidate
 
 
 def _diag(name, **kw):
@@ -63,7 +64,7 @@ def test_generate_matches_oracle(family, penalty):
     hf, ours = _pair(family, seed=2)
     ours.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
     otrie = OracleLookaheadCache(eos_ids=[2])
-    exact, total, edl_pairs = 0, 0, []
+    exact, total, edl_pairs, agree_tok, all_tok = 0, 0, [], 0, 0
     for rep in range(2):
         for p in prompts(21, 4, 24, 200):
             p = p.to(DEV)
@@ -73,17 +74,23 @@ def test_generate_matches_oracle(family, penalty):
             ref = lookahead_generate(hf, otrie, p, max_new_tokens=48, eos_token_id=[2], repetition_penalty=penalty)
             a, b = out.sequences[0].tolist(), ref['sequences'][0].tolist()
             total += 1
+            all_tok += len(b) - p.shape[1]
             if a == b:
                 exact += 1
+                agree_tok += len(b) - p.shape[1]
                 # identical tokens + parity-exact trie => identical drafts => identical accepted lengths
                 assert out.kwargs['edls'] == ref['edls'], (out.kwargs['edls'], ref['edls'])
                 assert out.kwargs['dls'] == ref['dls']
                 edl_pairs.append(sum(ref['edls'][1:]) / max(len(ref['edls']) - 1, 1))
             else:
                 k = next(i for i in range(min(len(a), len(b))) if a[i] != b[i])
+                agree_tok += k - p.shape[1]
                 ok, gap, noise = _legit_divergence(family, hf, ref['sequences'][:, :k], a[k], b[k], penalty)
                 _diag('generate_matches_oracle', family=family, pos=k, gap=gap, noise=noise)
                 assert ok, f'diverged at {k}: fp32 gap {gap:.3f} vs bf16 noise {noise:.3f}'
+                # stated tolerance: both candidates within EPS of the fp32 optimum (logit std of these models ~1.3-1.8,
+                # the eager bf16 model's own max logit error 0.07-0.3)
+                assert gap < EPS, f'diverged at {k} although the fp32 top-2 margin is {gap:.3f} >= {EPS}'
                 # the tries have diverged with the text: resync both from scratch
                 ours.lookahead_cache.fresh()
                 otrie.fresh()
@@ -91,7 +98,8 @@ def test_generate_matches_oracle(family, penalty):
     # least one bf16 near-tie; what must hold is that EVERY divergence sits on such a tie (asserted above) and
     # that equal text implies equal drafts (dls) and accepted lengths (edls).  The exact-loop-logic statement is
     # test_loop_is_exact_given_the_same_logits below.
-    assert exact >= 1, f'only {exact}/{total} sequences identical'
+    assert 2 * exact >= total, f'only {exact}/{total} sequences identical'
+    assert agree_tok >= 0.75 * all_tok, f'only {agree_tok}/{all_tok} tokens precede the first bf16 near-tie'
 
 
 def test_lookahead_equals_own_greedy_and_respects_limits():
@@ -133,9 +141,9 @@ class OursBackend(object):
         n = ids_in.shape[1]
         if self.P == 0 and self.prefill_like_generate:  # prompt: exactly the prefill generate() runs (last row only)
             rt = self.m._runtime(self.max_seq, 64)
-            rt.pad_len = 0
-            rt.seq[:n] = ids_in[0].to(device=rt.device, dtype=torch.int32)
-            self.m._prefill_kv(rt, n)
+            rt.set_request(0, 0, 1 << 30)
+            rt.seq[0, :n] = ids_in[0].to(device=rt.device, dtype=torch.int32)
+            self.m._prefill_logits(rt, n)
             self.P = n
             return rt.logits[0:1].clone()[None]
         if self.P == 0 and n > 64:  # prompt: chain chunks of 64 through forward()
@@ -151,8 +159,8 @@ class OursBackend(object):
     def compact(self, keep_idx):
         rt = self.m._rt
         L = keep_idx.numel()
-        rt.k_cache[:, :, :L] = rt.k_cache[:, :, keep_idx.to(rt.device)]
-        rt.v_cache[:, :, :L] = rt.v_cache[:, :, keep_idx.to(rt.device)]
+        rt.k_cache[0][:, :, :L] = rt.k_cache[0][:, :, keep_idx.to(rt.device)]
+        rt.v_cache[0][:, :, :L] = rt.v_cache[0][:, :, keep_idx.to(rt.device)]
         self.P = L
 
 
@@ -259,3 +267,62 @@ def test_left_padding_eos_and_streamer():
         assert st.ended
         streamed = [int(t) for c in st.chunks[1:] for t in (c.reshape(-1).tolist())]
         assert streamed == a[padded.shape[1]:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Parity at the BASELINE shapes (BASELINE.json configs 2-4): the same exact-loop statement as above, at full size.
+# Random-init weights of the named shapes (no checkpoints offline), phrase-bank prompts of bench.py; every request
+# runs twice so that the second pass drafts the first pass's answer from the trie (multi-token accepts, non-contiguous
+# KV compaction at the real head counts / cache strides / vocabulary).
+# ---------------------------------------------------------------------------------------------------------------
+def _shape_model(name, layers=None):
+    import bench
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama import LlamaForCausalLM
+    from painlessinferenceacceleration_b200.models.mixtral.modeling_mixtral import MixtralForCausalLM
+    cfg, fam = bench.make_config(name)
+    if layers is not None:
+        cfg.num_hidden_layers = layers
+    cls = MixtralForCausalLM if fam == 'mixtral' else LlamaForCausalLM
+    a = cls(cfg, device=torch.device(DEV)).init_weights(seed=0)
+    b = cls(cfg, device=torch.device(DEV))
+    b.load_state_dict(a.state_dict(), strict=True)
+    return cfg, a, b
+
+
+@pytest.mark.big
+@pytest.mark.parametrize('name,layers,penalty,n_prompts,new', [('llama2-7b', None, 1.0, 4, 128),
+                                                               ('mistral-7b', None, 1.1, 3, 96),
+                                                               ('mixtral-8x7b', 3, 1.0, 3, 64)])
+def test_loop_is_exact_at_baseline_shapes(name, layers, penalty, n_prompts, new):
+    """Llama-2-7B (32 layers, 4096, MHA-32, V=32000; config 2), Mistral-7B (GQA-4) with repetition_penalty=1.1
+    (config 3) and an 8-expert Mixtral-8x7B-shaped slice (3 of the 32 layers; config 4): the oracle loop (reference
+    semantics + C oracle trie on the host) drives one copy of the model through the backend interface, the fused device
+    loop drives the other; 64-token / 8-branch drafts, 256-token phrase-bank prompts.  Tokens, dls and edls must be
+    identical for every request, with the tries carried across requests."""
+    import bench
+    from oracle.loop import lookahead_generate
+    from oracle.trie import OracleLookaheadCache
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    cfg, a, b = _shape_model(name, layers)
+    a.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=cfg.vocab_size)
+    otrie = OracleLookaheadCache(eos_ids=[2])
+    ps = bench.phrase_bank_prompts(n_prompts, cfg.vocab_size)
+    edl_all, moved = [], 0
+    for rep in range(2):
+        for p in ps:
+            p = torch.tensor([p], device=DEV)
+            out = a.generate(input_ids=p, max_new_tokens=new, eos_token_id=2, repetition_penalty=penalty,
+                             decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
+                             return_dict_in_generate=True)
+            ref = lookahead_generate(None, otrie, p, max_new_tokens=new, eos_token_id=[2], repetition_penalty=penalty,
+                                     backend=OursBackend(b, prefill_like_generate=True, max_seq=256 + new + 65),
+                                     trace=True)
+            assert out.sequences[0].tolist() == ref['sequences'][0].tolist(), (name, rep)
+            assert out.kwargs['edls'] == ref['edls'] and out.kwargs['dls'] == ref['dls'], (name, rep)
+            if rep == 1:
+                edl_all += ref['edls'][1:]
+                moved += sum(1 for st in ref['steps'] if len(st['tokens']) > 1 and
+                             st['logit_indices'] != list(range(len(st['tokens']))))
+    _diag('baseline_shape_parity', name=name, mean_edl_second_pass=sum(edl_all) / len(edl_all), max_edl=max(edl_all),
+          non_contiguous_steps=moved)
+    assert max(edl_all) > 2, 'the second pass never accepted a draft: the test did not exercise the accept path'

@@ -39,6 +39,12 @@ def _mask_tensor(rows, R):
     return torch.from_numpy(m.view(np.int64)).to(DEV)
 
 
+def _slots(ns, Ps, pads, rows_per_slot, stride=0, first=0):
+    from painlessinferenceacceleration_b200.common import ops
+    t = [torch.tensor(v, dtype=torch.int32, device=DEV) for v in (ns, Ps, pads)]
+    return ops.Slots(t[0], t[1], t[2], rows_per_slot, stride, kv_first_slot=first)
+
+
 def _ref_attention(q, kc, vc, rows, n, P, pad_len, G):
     """eager attention of the reference with the [n, P+n] lookahead mask; fp32 scores, probabilities rounded to
     bf16 before PV exactly like modeling_llama.py:291-292"""
@@ -78,11 +84,10 @@ def test_tree_attention(Hq, Hkv, P, n, pad):
     mask = _mask_tensor(rows, R)
     plan = ops.AttnPlan(kc, vc, Hq, Hkv, D, R)
     out = torch.zeros((R, Hq, D), dtype=torch.bfloat16, device=DEV)
-    dn = torch.tensor([n], dtype=torch.int32, device=DEV)
-    dP = torch.tensor([P], dtype=torch.int32, device=DEV)
+    slots = _slots([n], [P], [pad], R)
     for layer in (1, 0):
         out.zero_()
-        plan.forward(layer, q, mask, dn, dP, pad, out)
+        plan.forward(layer, q, mask, slots, out)
         torch.cuda.synchronize()
         ref = _ref_attention(q, kc[layer], vc[layer], rows, n, P, pad, Hq // Hkv)
         got = out[:n].float()
@@ -126,9 +131,7 @@ def test_rope_kv_append_and_silu():
     qo = torch.zeros((R, Hq, D), dtype=torch.bfloat16, device=DEV)
     kc = torch.zeros((Hkv, max_seq, D), dtype=torch.bfloat16, device=DEV)
     vc = torch.zeros_like(kc)
-    dn = torch.tensor([n], dtype=torch.int32, device=DEV)
-    dP = torch.tensor([P], dtype=torch.int32, device=DEV)
-    ops.rope_kv_append(qkv, mask, dn, dP, pad, Hq, Hkv, D, cos, sin, qo, kc, vc, max_seq)
+    ops.rope_kv_append(qkv, mask, _slots([n], [P], [pad], R), Hq, Hkv, D, cos, sin, qo, kc, vc, max_seq)
     torch.cuda.synchronize()
     pos = torch.tensor([P - pad + d for d in depth], device=DEV)
     c = torch.cat([cos[pos], cos[pos]], -1)[:, None]  # [n,1,D] bf16  (modeling_llama.py:124-127)
@@ -148,8 +151,7 @@ def test_rope_kv_append_and_silu():
     # key, position = depth (rowsum(mask) - 1, modeling_llama.py:587)
     qo2 = torch.zeros_like(qo)
     kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(vc)
-    P2 = torch.tensor([3], dtype=torch.int32, device=DEV)
-    ops.rope_kv_append(qkv, mask, dn, P2, 9, Hq, Hkv, D, cos, sin, qo2, kc2, vc2, max_seq)
+    ops.rope_kv_append(qkv, mask, _slots([n], [3], [9], R), Hq, Hkv, D, cos, sin, qo2, kc2, vc2, max_seq)
     pos2 = torch.tensor(list(depth), device=DEV)
     c2 = torch.cat([cos[pos2], cos[pos2]], -1)[:, None]
     s2 = torch.cat([sin[pos2], sin[pos2]], -1)[:, None]
@@ -234,7 +236,7 @@ def test_accept_walk_and_kv_compact(penalty):
         kc = torch.arange(2 * 2 * 128 * 16, device=DEV).float().view(2, 2, 128, 16).to(torch.bfloat16).contiguous()
         vc = (kc.float() + 0.5).to(torch.bfloat16).contiguous()
         k0, v0 = kc.clone(), vc.clone()
-        acc.run(logits, d['ids'], mask, d['n'], seq, seq_len, 0, at, ac, an, prefix, fin)
+        acc.run(logits, d['ids'], mask, d['n'], seq, seq_len, at, ac, an, prefix, fin)
         ops.kv_compact(kc, vc, an, ac, prefix)
         torch.cuda.synchronize()
         c = int(ac)
@@ -246,6 +248,160 @@ def test_accept_walk_and_kv_compact(penalty):
         # rows [0, P0] untouched, accepted draft rows moved next to the prefix (:894-907)
         keep = list(range(P0 + 1)) + [P0 + j for j in nodes[1:]]
         assert torch.equal(kc[:, :, :len(keep)], k0[:, :, keep]) and torch.equal(vc[:, :, :len(keep)], v0[:, :, keep])
+
+
+@pytest.mark.parametrize('Hq,Hkv,rps,cases', [
+    (4, 2, 16, [(16, 100, 0), (5, 0, 0), (0, 7, 0), (9, 257, 3)]),        # one idle slot, one empty context, padding
+    (32, 8, 8, [(8, 300, 0), (3, 290, 0), (8, 310, 2), (1, 5, 0), (7, 128, 0), (8, 64, 0), (2, 500, 0), (6, 301, 0)]),
+    (32, 32, 32, [(32, 420, 0), (11, 64, 0)])])
+def test_batched_slots_rope_and_attention(Hq, Hkv, rps, cases):
+    """the request-slot form of RoPE/KV-append and tree attention (pia_slots_t; batched loop,
+    modeling_llama_batch.py:375-405): every slot has its own draft, cursor, padding and KV cache; one launch each must
+    equal the per-slot single launches bit for bit, and rows beyond a slot's draft are never written"""
+    from painlessinferenceacceleration_b200.common import ops
+    rng = np.random.default_rng(rps)
+    torch.manual_seed(rps)
+    D, R, n_layers, B = 128, 64, 2, len(cases)
+    max_seq = max(P + n for n, P, _ in cases) + 70
+    kc = (torch.randn((B, n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    vc = (torch.randn((B, n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    qkv = torch.randn((R, (Hq + 2 * Hkv) * D), device=DEV).to(torch.bfloat16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=DEV).float() / D))
+    ang = torch.arange(max_seq + 8, device=DEV).float()[:, None] * inv[None]
+    cos, sin = ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous()
+    mask = torch.zeros((R, 1), dtype=torch.int64, device=DEV)
+    trees = []
+    for s_, (n, P, pad) in enumerate(cases):
+        rows = _random_tree(rng, n)[2] if n else np.zeros((0,), dtype=np.uint64)
+        trees.append(rows)
+        if n:
+            mask[s_ * rps:s_ * rps + n, 0] = torch.from_numpy(rows.view(np.int64)).to(DEV)
+    ns, Ps, pads = [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases]
+    plan = ops.AttnPlan(kc, vc, Hq, Hkv, D, R)
+    layer = 1
+    # batched: one launch each over all slots
+    kb, vb = kc.clone(), vc.clone()
+    planb = ops.AttnPlan(kb, vb, Hq, Hkv, D, R)
+    qb = torch.full((R, Hq, D), 7.0, dtype=torch.bfloat16, device=DEV)
+    ob = torch.full((R, Hq, D), 9.0, dtype=torch.bfloat16, device=DEV)
+    sl = _slots(ns, Ps, pads, rps, stride=plan.slot_stride)
+    ops.rope_kv_append(qkv, mask, sl, Hq, Hkv, D, cos, sin, qb, kb[0, layer], vb[0, layer], max_seq)
+    planb.forward(layer, qb, mask, sl, ob)
+    torch.cuda.synchronize()
+    # slot by slot: single-slot launches on that slot's own cache / rows, then the fp32 reference
+    for s_, (n, P, pad) in enumerate(cases):
+        r0 = s_ * rps
+        one = _slots([n], [P], [pad], rps, first=s_)
+        q1 = torch.full((R, Hq, D), 7.0, dtype=torch.bfloat16, device=DEV)
+        o1 = torch.full((R, Hq, D), 9.0, dtype=torch.bfloat16, device=DEV)
+        ops.rope_kv_append(qkv[r0:], mask[r0:], one, Hq, Hkv, D, cos, sin, q1, kc[s_, layer], vc[s_, layer], max_seq)
+        plan.forward(layer, q1, mask[r0:], one, o1)
+        torch.cuda.synchronize()
+        assert torch.equal(qb[r0:r0 + rps], q1[:rps]) and torch.equal(ob[r0:r0 + rps], o1[:rps])
+        assert torch.equal(kb[s_], kc[s_]) and torch.equal(vb[s_], vc[s_])
+        assert float((qb[r0 + n:r0 + rps].float() - 7.0).abs().sum()) == 0   # rows beyond the draft: untouched
+        assert float((ob[r0 + n:r0 + rps].float() - 9.0).abs().sum()) == 0
+        if n:
+            ref = _ref_attention(q1, kc[s_, layer], vc[s_, layer], trees[s_], n, P, pad, Hq // Hkv)
+            assert torch.allclose(ob[r0:r0 + n].float(), ref, atol=1.5e-2, rtol=2e-2)
+
+
+def test_prefill_chunks_share_one_cache():
+    """a prefill pass = one table slot per 64-row chain chunk over the SAME cache (kv_slot_stride 0): chunk c must see
+    the rows chunk c-1 appended in the same launch sequence; equals feeding the chunks one after the other"""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(5)
+    Hq, Hkv, D, R, C, n_layers = 8, 2, 128, 64, 3, 1
+    lens = [64, 64, 23]
+    max_seq = 400
+    chain = np.array([(1 << (i + 1)) - 1 if i < 63 else 0xFFFFFFFFFFFFFFFF for i in range(R)], dtype=np.uint64)
+    mask = torch.from_numpy(np.tile(chain, C).view(np.int64)).to(DEV).view(C * R, 1)
+    qkv = torch.randn((C * R, (Hq + 2 * Hkv) * D), device=DEV).to(torch.bfloat16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=DEV).float() / D))
+    ang = torch.arange(max_seq, device=DEV).float()[:, None] * inv[None]
+    cos, sin = ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous()
+    base = 40  # tokens already cached
+    outs = []
+    for batched in (True, False):
+        kc = (torch.randn((n_layers, Hkv, max_seq, D), device=DEV, generator=torch.Generator(DEV).manual_seed(1)) * 0.7).to(torch.bfloat16)
+        vc = (torch.randn((n_layers, Hkv, max_seq, D), device=DEV, generator=torch.Generator(DEV).manual_seed(2)) * 0.7).to(torch.bfloat16)
+        plan = ops.AttnPlan(kc, vc, Hq, Hkv, D, R)
+        q = torch.zeros((C * R, Hq, D), dtype=torch.bfloat16, device=DEV)
+        o = torch.zeros((C * R, Hq, D), dtype=torch.bfloat16, device=DEV)
+        if batched:
+            sl = _slots(lens, [base + R * c for c in range(C)], [0] * C, R)
+            ops.rope_kv_append(qkv, mask, sl, Hq, Hkv, D, cos, sin, q, kc[0], vc[0], max_seq)
+            plan.forward(0, q, mask, sl, o)
+        else:
+            for c in range(C):
+                sl = _slots([lens[c]], [base + R * c], [0], R)
+                ops.rope_kv_append(qkv[R * c:], mask[R * c:], sl, Hq, Hkv, D, cos, sin, q[R * c:], kc[0], vc[0], max_seq)
+            for c in range(C):
+                sl = _slots([lens[c]], [base + R * c], [0], R)
+                plan.forward(0, q[R * c:], mask[R * c:], sl, o[R * c:])
+        torch.cuda.synchronize()
+        outs.append((q.clone(), o.clone(), kc.clone(), vc.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_batched_accept_walk_and_compaction():
+    """pia_accept / pia_kv_compact over several request slots (pretrained_model_batch.py:810-918): each slot equals the
+    single-slot run on its own rows; bound_walk caps the accepted tokens at max_length - len (:862); a slot that already
+    finished and an idle slot accept nothing"""
+    from painlessinferenceacceleration_b200.common import ops
+    rng = np.random.default_rng(23)
+    V, R, B, rps = 500, 64, 4, 16
+    stride = 128
+    ids = torch.zeros((R,), dtype=torch.int32, device=DEV)
+    mask = torch.zeros((R, 1), dtype=torch.int64, device=DEV)
+    logits = torch.randn((R, V), device=DEV).to(torch.bfloat16)
+    seq = torch.zeros((B, stride), dtype=torch.int32, device=DEV)
+    ns, lens, info = [], [], []
+    for s_ in range(B):
+        n = [16, 9, 0, 12][s_]
+        ns.append(n)
+        parent = [-1] + list(range(n - 1))          # one chain: every node's child continues it
+        toks = [int(rng.integers(3, 40))] + rng.choice(np.arange(40, 400), size=max(n - 1, 0), replace=False).tolist()
+        L0 = 20 + s_
+        lens.append(L0)
+        seq[s_, :L0] = torch.tensor(rng.integers(3, 40, size=L0).tolist(), dtype=torch.int32)
+        if n:
+            seq[s_, L0 - 1] = toks[0]
+            ids[s_ * rps:s_ * rps + n] = torch.tensor(toks, dtype=torch.int32)
+            rows = np.array([(1 << (i + 1)) - 1 for i in range(n)], dtype=np.uint64)
+            mask[s_ * rps:s_ * rps + n, 0] = torch.from_numpy(rows.view(np.int64)).to(DEV)
+            for j in range(n - 1):                   # row j votes for its child: the whole chain would be accepted
+                logits[s_ * rps + j, toks[j + 1]] = 40.0
+        info.append(toks)
+    max_length = 30   # slot 0: len 20 -> at most 10 tokens; slot 1: len 21 -> 9 ; slot 3: len 23 -> 7
+    dn = torch.tensor(ns, dtype=torch.int32, device=DEV)
+    seq_len = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    prefix = seq_len - 1
+    fin = torch.zeros((B,), dtype=torch.int32, device=DEV)
+    fin[1] = 1                                       # slot 1 finished earlier: must be left alone
+    at = torch.zeros((B, R), dtype=torch.int32, device=DEV)
+    ac = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+    an = torch.zeros((B, R), dtype=torch.int32, device=DEV)
+    acc = ops.Accept(V, R, 1.0, [2], 10 ** 6, DEV, bound_walk=True)
+    ml = torch.tensor([max_length], dtype=torch.int32, device=DEV)
+    r = torch.arange(stride, device=DEV)
+    kc = torch.zeros((B, 1, 1, stride, 128), dtype=torch.bfloat16, device=DEV)
+    kc[..., 0] = r.to(torch.bfloat16)
+    kc[..., 1] = torch.arange(B, device=DEV).to(torch.bfloat16)[:, None, None, None]
+    vc = kc.clone()
+    k0 = kc.clone()
+    acc.run(logits, ids, mask, dn, seq, seq_len, at, ac, an, prefix, fin, batch=B, rows_per_slot=rps, max_length=ml)
+    ops.kv_compact(kc, vc, an, ac, prefix, batch=B)
+    torch.cuda.synchronize()
+    assert ac.tolist() == [10, 0, 0, 7]
+    assert seq_len.tolist() == [30, 21, 22, 30] and prefix.tolist() == [29, 20, 21, 29]
+    assert fin.tolist() == [1, 1, 0, 1]              # slots 0 and 3 reached max_length
+    for s_ in (0, 3):
+        c = int(ac[s_])
+        assert at[s_, :c].tolist() == info[s_][1:c + 1] and an[s_, :c].tolist() == list(range(c))
+        assert seq[s_, lens[s_]:lens[s_] + c].tolist() == info[s_][1:c + 1]
+    assert torch.equal(kc, k0) and torch.equal(vc, k0)  # chains are contiguous: nothing moves
 
 
 @pytest.mark.parametrize('N,K,split', [(256, 128, 1), (12288, 4096, 1), (4096, 4096, 4), (22016, 4096, 1),

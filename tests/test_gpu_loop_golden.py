@@ -43,7 +43,6 @@ def test_accept_and_compaction_kernels_step_by_step(name):
         max_length = len(req['prompt']) + req['max_new_tokens']
         max_seq = max_length + 80
         acc = ops.Accept(V, 64, pen, [eos], max_length, dev)
-        pad_len = 0 if req['attention_mask'] is None else req['attention_mask'].index(1)
         for si, st in enumerate(req['steps']):
             if st['mask'] is None:
                 continue
@@ -64,7 +63,7 @@ def test_accept_and_compaction_kernels_step_by_step(name):
             kc[0, 0, :, 0], kc[0, 0, :, 1] = (r // 128).to(torch.bfloat16), (r % 128).to(torch.bfloat16)
             vc = kc.clone()
             before = kc.clone()
-            acc.run(logits, ids, mask, dn, seq, seq_len, pad_len, toks, cnt, nodes, prefix, fin)
+            acc.run(logits, ids, mask, dn, seq, seq_len, toks, cnt, nodes, prefix, fin)
             ops.kv_compact(kc, vc, nodes, cnt, prefix)
             torch.cuda.synchronize()
             c = int(cnt)
@@ -114,7 +113,7 @@ def _replay_model(vocab, dev):
 
         def load(self, meta, z, req):
             steps = req['steps']
-            assert len(steps) - 1 <= self.cap
+            assert len(steps) < self.cap  # + the step launched ahead of the stop check
             self.all.zero_()
             for k, st in enumerate(steps[1:]):
                 self.all[k] = _pad_logits(meta, z, st).to(dev)
@@ -122,17 +121,14 @@ def _replay_model(vocab, dev):
             self.step.zero_()
             self.ids_log.zero_()
 
-        def _prefill_kv(self, rt, prompt_len):
-            if not hasattr(rt, 'chain'):
-                rt.chain = rt.chain_mask_rows()
-            rt.logits[0:1] = self.first
-            rt.prefix_len.fill_(prompt_len)
+        def _prefill_logits(self, rt, prompt_len, slot=0, row=0):
+            rt.logits[row:row + 1] = self.first
 
         def _verify_layers(self, rt, bufs=None, last_only=False):
             rt.logits.copy_(self.all.index_select(0, self.step)[0])
-            self.ids_log.index_copy_(0, self.step, rt.ids)
+            self.ids_log.index_copy_(0, self.step, rt.ids[None])
             self.n_log.index_copy_(0, self.step, rt.n)
-            self.mask_log.index_copy_(0, self.step, rt.mask[:, :, 0])
+            self.mask_log.index_copy_(0, self.step, rt.mask[None, :, 0])
             self.step += 1
 
     return Replay()
@@ -167,4 +163,96 @@ def test_device_loop_reproduces_the_reference_loop(name):
             assert int(n_log[k]) == n and ids_log[k, :n].tolist() == st['decoding_ids'], (name, ri, k)
             assert np.array_equal(mask_log[k, :n], G.step_mask(st)), (name, ri, k)
         multi += sum(e > 1 for e in req['edls'])
+    assert multi >= 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# batched device loop (common/pretrained_model_batch.py) against records of the reference's own batched loop
+# ---------------------------------------------------------------------------------------------------------------
+def _batch_replay_model(vocab, dev, dl):
+    from painlessinferenceacceleration_b200.common.pretrained_model_batch import LookaheadPreTrainedModel
+
+    class BatchReplay(LookaheadPreTrainedModel):
+        def __init__(self):
+            super().__init__(types.SimpleNamespace(eos_token_id=2, pad_token_id=0))
+            self.anchor = nn.Parameter(torch.zeros(1, device=dev), requires_grad=False)
+            self.cap = 64
+            self.all = torch.zeros((self.cap, 64, vocab), dtype=torch.bfloat16, device=dev)
+            self.ids_log = torch.zeros((self.cap, 64), dtype=torch.int32, device=dev)
+            self.n_log = torch.zeros((self.cap, 8), dtype=torch.int32, device=dev)
+            self.step = torch.zeros((1,), dtype=torch.int64, device=dev)
+            self.first = None
+
+        def geometry(self):
+            return dict(n_layers=1, hidden=128, n_q_heads=1, n_kv_heads=1, head_dim=128, inter=128, vocab=vocab)
+
+        def rope_tables(self, max_pos):
+            z = torch.zeros((max_pos, 64), dtype=torch.bfloat16, device=dev)
+            return z, z.clone()
+
+        @staticmethod
+        def share(k):
+            return max(dl // k, 1) // k   # decoding_length // active // active (pretrained_model_batch.py:713 + bat_get :534)
+
+        def load(self, meta, z, call):
+            steps = call['steps']
+            assert steps[0]['prefill'] and len(steps) < self.cap
+            self.first = G.batch_step_logits(meta, z, steps[0])[:, -1].to(dev)       # [bs, V]
+            self.all.zero_()
+            for t, st in enumerate(steps[1:]):
+                lg = G.batch_step_logits(meta, z, st)
+                k, n = lg.shape[0], lg.shape[1]
+                sh = self.share(k)
+                assert n <= sh
+                for r in range(k):
+                    self.all[t, r * sh:r * sh + n] = lg[r].to(dev)
+            self.step.zero_()
+            self.ids_log.zero_()
+            self.n_log.zero_()
+
+        def _prefill_logits(self, rt, prompt_len, slot=0, row=0):
+            rt.logits[row:row + 1] = self.first[slot:slot + 1]
+
+        def _verify_layers(self, rt, bufs=None, last_only=False):
+            rt.logits.copy_(self.all.index_select(0, self.step)[0])
+            self.ids_log.index_copy_(0, self.step, rt.ids[None])
+            self.n_log[:, :rt.n.numel()].index_copy_(0, self.step, rt.n[None])
+            self.step += 1
+
+    return BatchReplay()
+
+
+@pytest.mark.parametrize('name', G.batch_names())
+def test_batched_device_loop_reproduces_the_reference_batch_loop(name):
+    """GPU trie batched get (request idx per row) -> [recorded logits] -> per-slot accept (bounded walk) -> per-slot
+    KV compaction -> per-slot stream_put with device-resident idx, slots compacted as requests finish: the drafts,
+    tokens, dls, edls and the padded output equal the reference's batched loop for every call"""
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    meta, z = G.load_batch(name)
+    gen = meta['gen']
+    eos, V, dl = gen.get('eos_token_id', 2), meta['vocab'], meta['decoding_length']
+    dev = torch.device(DEV)
+    model = _batch_replay_model(V, dev, dl)
+    model.lookahead_cache = LookaheadCache(eos_ids=[eos], device=dev, vocab_capacity=1024, node_capacity=1 << 20)
+    multi = 0
+    for ci, call in enumerate(meta['calls']):
+        model.load(meta, z, call)
+        ids = torch.tensor(call['input_ids'], device=dev)
+        out = model.generate(input_ids=ids, max_new_tokens=call['max_new_tokens'], eos_token_id=eos,
+                             pad_token_id=gen.get('pad_token_id', 0),
+                             repetition_penalty=gen.get('repetition_penalty', 1.0),
+                             decoding_kwargs={'use_lookahead': True, 'decoding_length': dl,
+                                              'branch_length': meta['branch_length']},
+                             return_dict_in_generate=True)
+        assert out.sequences.tolist() == call['sequences'], (name, ci)
+        assert out.kwargs['dls'] == call['dls'] and out.kwargs['edls'] == call['edls'], (name, ci)
+        ids_log, n_log = model.ids_log.cpu(), model.n_log.cpu()
+        for t, st in enumerate(call['steps'][1:]):
+            k = len(st['before']['batch_indices'])
+            sh = model.share(k)
+            for r in range(k):
+                n = int(n_log[t, r])
+                want = st['before']['ids'][r]
+                assert ids_log[t, r * sh:r * sh + n].tolist() == want[:n] and all(x == 0 for x in want[n:]), (name, ci, t, r)
+        multi += sum(e > 1 for e in call['edls'])
     assert multi >= 3

@@ -94,3 +94,61 @@ def test_accept_routine_step_by_step(name):
             if st['kv'] is not None:
                 assert [i - 1 + st['context_len'] for i in li[1:]] == st['kv']['kv_idx']
                 assert st['kv']['continuous'] == (li[-1] == len(toks) - 1)
+
+
+class BatchReplayBackend(object):
+    """request `b` of a recorded batched call: returns the recorded logits of its row at every step it is active"""
+
+    def __init__(self, meta, z, call, b):
+        self.meta, self.z, self.call, self.b, self.P, self.t = meta, z, call, b, 0, 0
+
+    def rows(self):
+        return self.P
+
+    def forward(self, ids_in, m01, pos):
+        while True:
+            st = self.call['steps'][self.t]
+            self.t += 1
+            if st['prefill'] or self.b in st['before']['batch_indices']:
+                break
+        lg = G.batch_step_logits(self.meta, self.z, st)
+        if st['prefill']:
+            row = self.b
+        else:
+            row = st['before']['batch_indices'].index(self.b)
+            assert ids_in[0].tolist() == st['before']['ids'][row], (self.b, self.t)
+            assert self.P == st['before']['cursors'][row]
+        self.P += ids_in.shape[1]
+        return lg[row:row + 1]
+
+    def compact(self, keep_idx):
+        self.P = keep_idx.numel()
+
+
+@pytest.mark.parametrize('name', G.batch_names())
+def test_oracle_batch_loop_reproduces_the_reference_batch_loop(name):
+    """oracle/loop_batch.py against records of the reference's own batched loop (pretrained_model_batch.py:664-1330 +
+    bat_get): per-slot trie puts, drafts of decoding_length // active // active nodes padded to the widest, bounded
+    accept walks, requests leaving the batch at different steps, the padded output"""
+    from oracle.loop_batch import lookahead_generate_batch
+    meta, z = G.load_batch(name)
+    gen = meta['gen']
+    eos = gen.get('eos_token_id', 2)
+    trie = OracleLookaheadCache(eos_ids=[eos])
+    multi = 0
+    for call in meta['calls']:
+        ids = torch.tensor(call['input_ids'])
+        out = lookahead_generate_batch(None, trie, ids, max_new_tokens=call['max_new_tokens'], eos_token_id=[eos],
+                                       decoding_length=meta['decoding_length'], branch_length=meta['branch_length'],
+                                       repetition_penalty=gen.get('repetition_penalty', 1.0),
+                                       pad_token_id=gen.get('pad_token_id', 2),
+                                       backend_factory=lambda b: BatchReplayBackend(meta, z, call, b), trace=True)
+        assert out['sequences'].tolist() == call['sequences']
+        assert out['dls'] == call['dls'] and out['edls'] == call['edls']
+        rec = [st for st in call['steps'] if not st['prefill']]
+        assert len(rec) == len(out['steps'])
+        for st, tr in zip(rec, out['steps']):
+            assert tr['active'] == st['before']['batch_indices'] and tr['ids'] == st['before']['ids']
+            assert tr['tokens'] == st['tokens']
+        multi += sum(e > 1 for e in call['edls'])
+    assert multi >= 3
