@@ -5,11 +5,16 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one request through the hot path: a 256-token synthetic prompt -> greedy generation of 256 new tokens
-with 64-token / 8-branch trie drafts (BASELINE config 2).  Weights are random-init of the named shape
-(no checkpoints exist offline), prompts come from the seeded phrase bank of SURVEY.md 8d, the trie is warmed by W
-untimed requests exactly like the reference's benchmark warms it from earlier answers (benchmarks/benchmark.py:159-169).
-One JSON line is printed by rank 0; see the keys below.  N > 1 = independent data-parallel replicas (the loop is per
-request, pretrained_model.py:1152): one NCCL broadcast of the weights, then no collective on the data path.
+with 64-token / 8-branch trie drafts (BASELINE config 2).  No checkpoints exist offline, so the weights
+are synthetic, of the named shape, and IDENTICAL in the GPU arm and the CPU arms (a counter-based hash of the element
+index, synth_fill below): every decoder layer is plain random init (std 0.02); the embedding scale and the lm_head are
+constructed so that greedy decoding is a noisy first-order chain over the vocabulary (next = succ(token) unless the
+random layers' context-dependent contribution flips the arg-max).  Such text re-uses n-grams across requests like
+real text does, so a trie warmed on OTHER prompts (the reference's warm-up, benchmarks/benchmark.py:159-169)
+yields accepted lengths > 1 on prompts it has never seen - the headline is that first pass, not answer replay.
+One JSON line is printed by rank 0; see README.md / DESIGN.md 5 for the keys.  N > 1 = independent data-parallel
+replicas (the loop is per request, pretrained_model.py:1152): one NCCL broadcast of the weights, then no collective on
+the data path; every replica runs the same K requests (identical work per rank, weak scaling).
 """
 import argparse
 import json
@@ -17,6 +22,7 @@ import os
 import sys
 import threading
 import time
+import zlib
 
 import numpy as np
 
@@ -24,18 +30,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MODELS = {
-    # name: (family, hidden, inter, layers, heads, kv_heads, vocab)
-    'llama2-7b': ('llama', 4096, 11008, 32, 32, 32, 32000),
-    'mistral-7b': ('mistral', 4096, 14336, 32, 32, 8, 32000),
-    'mixtral-8x7b': ('mixtral', 4096, 14336, 32, 32, 8, 32000),
-    'tiny': ('llama', 512, 1024, 4, 4, 4, 32000),
+    # name: (family, hidden, inter, layers, heads, kv_heads, vocab, repetition_penalty of its BASELINE config)
+    'llama2-7b': ('llama', 4096, 11008, 32, 32, 32, 32000, 1.0),
+    'mistral-7b': ('mistral', 4096, 14336, 32, 32, 8, 32000, 1.1),
+    'mixtral-8x7b': ('mixtral', 4096, 14336, 32, 32, 8, 32000, 1.0),
+    'tiny': ('llama', 512, 1024, 4, 4, 4, 32000, 1.0),
 }
+METRIC_NAMES = {'llama2-7b': 'Llama-2-7B', 'mistral-7b': 'Mistral-7B', 'mixtral-8x7b': 'Mixtral-8x7B', 'tiny': 'tiny'}
 PROMPT_LEN, NEW_TOKENS, DL, BL = 256, 256, 64, 8
+EMBED_STD = float(os.environ.get('PIA_BENCH_EMBED_STD', '1.0'))   # signal of the successor chain vs the layers' noise
+LM_SCALE = 0.25
+CPU_NEW_TOKENS = 16   # generated tokens per request of the bounded CPU samples (fixed, so the sample is reproducible)
+
+
+def metric_name(model):
+    return f'accepted tokens/sec @ {METRIC_NAMES[model]} {DL}-draft/{BL}-branch; mean accepted len/step'
 
 
 def make_config(name):
     from transformers import LlamaConfig, MistralConfig, MixtralConfig
-    fam, hid, inter, layers, heads, kv, vocab = MODELS[name]
+    fam, hid, inter, layers, heads, kv, vocab, _rp = MODELS[name]
     kw = dict(vocab_size=vocab, hidden_size=hid, intermediate_size=inter, num_hidden_layers=layers,
               num_attention_heads=heads, num_key_value_heads=kv, max_position_embeddings=4096, rms_norm_eps=1e-5,
               bos_token_id=1, eos_token_id=2, pad_token_id=0)
@@ -55,6 +69,80 @@ def phrase_bank_prompts(n, vocab, length=PROMPT_LEN, seed=1234):
             toks.extend(bank[int(rng.integers(0, len(bank)))].tolist())
         out.append(toks[:length])
     return out
+
+
+# ----------------------------------------------------------------------------------------------- synthetic weights
+def _hash32(i, seed):
+    """murmur3 finaliser over int32 tensors (wrap-around arithmetic is identical on CPU and CUDA)"""
+    import torch
+
+    def lsr(x, k):  # logical shift right of an int32
+        return (x >> k) & ((1 << (32 - k)) - 1)
+    x = i ^ seed
+    x = x ^ lsr(x, 16)
+    x = x * torch.tensor(-2048144789, dtype=torch.int32, device=i.device)   # 0x85EBCA6B
+    x = x ^ lsr(x, 13)
+    x = x * torch.tensor(-1028477387, dtype=torch.int32, device=i.device)   # 0xC2B2AE35
+    x = x ^ lsr(x, 16)
+    return x
+
+
+def hashed_normal_(t, seed, std):
+    """fills tensor t (bf16) in place with ~N(0, std^2) values that are a pure function of (seed, element index):
+    the sum of the four bytes of a 32-bit hash (Irwin-Hall, variance 4 * (256^2 - 1) / 12), centred and scaled"""
+    import torch
+    flat = t.view(-1)
+    n = flat.numel()
+    seed = int(seed) & 0x7FFFFFFF
+    chunk = 1 << 24
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        i = torch.arange(s, e, dtype=torch.int64, device=t.device)
+        lo = (i & 0x7FFFFFFF).to(torch.int32) ^ ((i >> 31).to(torch.int32) * 668265263)
+        x = _hash32(lo, torch.tensor(seed, dtype=torch.int32, device=t.device))
+        b = (x & 255) + ((x >> 8) & 255) + ((x >> 16) & 255) + ((x >> 24) & 255)
+        flat[s:e] = ((b.to(torch.float32) - 510.0) * (std / 147.80)).to(t.dtype)
+    return t
+
+
+def successor_map(vocab, seed=99):
+    """succ(t): a fixed pseudo-random function [3, V) -> [3, V) (not injective: chains started from different tokens
+    merge, which is what makes n-grams recur across requests)"""
+    import torch
+    t = torch.arange(vocab, dtype=torch.int32)
+    h = _hash32(t, torch.tensor(seed, dtype=torch.int32)).to(torch.int64) & 0x7FFFFFFF
+    return (3 + h % (vocab - 3)).to(torch.int64)
+
+
+def synth_fill(model, cfg, seed=0, embed_std=None):
+    """the benchmark's weights, identical on every device and in every arm (HF parameter names): norms = 1, decoder
+    weights ~ N(0, 0.02^2), embedding ~ N(0, embed_std^2), lm_head row v = LM_SCALE * sum of the unit embeddings of the
+    tokens t with succ(t) = v (hashed N(0, 0.02^2) for tokens without a predecessor)"""
+    import torch
+    embed_std = EMBED_STD if embed_std is None else embed_std
+    emb = lm = None
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            pseed = zlib.crc32(name.encode()) ^ (seed * 7919)
+            if name.endswith('norm.weight') or name.endswith('layernorm.weight'):
+                p.fill_(1.0)
+            elif name.endswith('embed_tokens.weight'):
+                hashed_normal_(p.data, pseed, embed_std)
+                emb = p
+            else:
+                hashed_normal_(p.data, pseed, 0.02)
+                if name.endswith('lm_head.weight'):
+                    lm = p
+        V = emb.shape[0]
+        succ = successor_map(V).to(emb.device)
+        unit = emb.data.double()
+        unit = unit / unit.norm(dim=1, keepdim=True).clamp_min(1e-30)
+        acc = torch.zeros_like(unit)
+        acc.index_add_(0, succ[3:], unit[3:])          # float64: the order of the (few) addends cannot reach bf16
+        has = torch.zeros((V,), dtype=torch.bool, device=emb.device)
+        has[succ[3:]] = True
+        lm.data[has] = (acc[has] * LM_SCALE).to(lm.dtype)
+    return model
 
 
 class ClockSampler(threading.Thread):
@@ -101,6 +189,12 @@ def peaks():
         return 6650.0, 1400.0, 'fallback'
 
 
+def timed_requests(K, rank=0):
+    """the K timed prompts: the same on every rank (identical work per replica: the aggregate scales with the hardware,
+    not with which shard happens to accept longer drafts) and disjoint from the warm-up prompts"""
+    return [i % 64 for i in range(K)]
+
+
 # ----------------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -117,27 +211,27 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     cfg, fam = make_config(args.model)
+    penalty = MODELS[args.model][7]
     if fam == 'mixtral':
         from painlessinferenceacceleration_b200.models.mixtral.modeling_mixtral import MixtralForCausalLM as Cls
     else:
         Cls = LlamaForCausalLM
     model = Cls(cfg, device=dev)
     if rank == 0:
-        model.init_weights(seed=0)
+        synth_fill(model, cfg)
     if world > 1:  # the one collective of this path: weights from rank 0 over NVLink
         for p in model.parameters():
             dist.broadcast(p.data, src=0)
     model.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
     K, Wm = args.steps, args.warmup
-    allp = phrase_bank_prompts(64 + 8 * Wm, cfg.vocab_size)
-    timed = [allp[(rank * K + i) % 64] for i in range(K)]
-    warm = [allp[64 + (rank * Wm + i) % (8 * Wm)] for i in range(Wm)] if Wm else []
+    allp = phrase_bank_prompts(64 + 8 * max(Wm, 1), cfg.vocab_size)
+    timed = [allp[j] for j in timed_requests(K, rank)]
+    warm = [allp[64 + i % (8 * max(Wm, 1))] for i in range(Wm)]
     dk = {'use_lookahead': True, 'decoding_length': DL, 'branch_length': BL}
-    gen = dict(max_new_tokens=NEW_TOKENS, eos_token_id=2, decoding_kwargs=dk, return_dict_in_generate=True)
-    warm_outputs = []
-    for p in warm:  # untimed: CUDA graph capture, cuBLAS heuristics, trie warm-up
-        o = model.generate(input_ids=torch.tensor([p], device=dev), **gen)
-        warm_outputs.append(o.sequences[0, PROMPT_LEN:].tolist())
+    gen = dict(max_new_tokens=NEW_TOKENS, eos_token_id=2, decoding_kwargs=dk, return_dict_in_generate=True,
+               repetition_penalty=penalty)
+    for p in warm:  # untimed: CUDA graph capture, trie warm-up on a disjoint prompt set (benchmark.py:159-169)
+        model.generate(input_ids=torch.tensor([p], device=dev), **gen)
 
     def barrier():
         if world > 1:
@@ -160,63 +254,103 @@ def run_ours(args):
             edls += o.kwargs['edls'][1:]
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms_rank = e0.elapsed_time(e1)
+        ms = ms_rank
         launches = (ops.launch_count() - l0) + (model._rt.replays - r0) * model._rt.kernels_per_graph
+        per_rank = [ms_rank]
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
+            allms = [torch.zeros((1,), device=dev) for _ in range(world)]
+            dist.all_gather(allms, torch.tensor([ms_rank], device=dev))
+            per_rank = [float(t) for t in allms]
+            ms = max(per_rank)
             agg = torch.tensor([float(toks), float(sum(edls)), float(len(edls)), float(launches)], device=dev)
             dist.all_reduce(agg)
             toks, s_e, n_e, launches = (float(v) for v in agg)
         else:
             s_e, n_e = float(sum(edls)), float(len(edls))
-        return dict(ms=ms, tokens=toks, mean_edl=s_e / max(n_e, 1), steps=n_e, launches=int(launches), outs=outs)
+        return dict(ms=ms, tokens=toks, mean_edl=s_e / max(n_e, 1), steps=n_e, launches=int(launches), outs=outs,
+                    per_rank_ms=per_rank)
 
+    trie = model.lookahead_cache
+    snap = trie.snapshot()              # the trie after the disjoint warm-up: both timed passes start from it
     sampler = ClockSampler(local)
     sampler.start()
-    first = timed_pass(host_io=False)   # epoch 1: the trie has never seen these prompts' answers
-    res = timed_pass(host_io=False)     # epoch 2 (headline): the trie saw each answer once (examples/llama_example.py:39)
-    e2e = timed_pass(host_io=True)      # epoch 3, through host buffers
+    res = timed_pass(host_io=False)     # headline: first pass over prompts the trie has never seen
+    trie.restore(snap)
+    e2e = timed_pass(host_io=True)      # the same pass through host buffers, from the same trie state
+    second = timed_pass(host_io=False)  # second pass: the trie has seen every answer once (the round-1 headline regime)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    roof = attention_roofline(model, dev) if rank == 0 else None
-    trie_roof = trie_roofline(dev) if rank == 0 else None
-    roof_long = attention_roofline_long(dev) if rank == 0 else None
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args, warm_outputs, timed[0])
+    same_tokens = all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(res['outs'], e2e['outs']))
+    extra = {}
+    if rank == 0:
+        extra['roofline'] = gemm_roofline(model, dev)
+        extra['roofline_attention'] = attention_roofline(model, dev)
+        extra['roofline_attention_long_context'] = attention_roofline_long(dev)
+        extra['roofline_trie_get'] = trie_roofline(dev)
+        extra['trie_counters'] = trie_counters(dev)
+        if world == 1 and fam != 'mixtral' and not args.no_batched:
+            extra['batched'] = batched_line(args, cfg, model, dev, allp)
+        if world == 1 and not args.no_cpu_baseline:
+            extra['cpu_baseline'] = cpu_baseline(args, cfg, model, dev, allp)
     if rank == 0:
         hbm, _tf, src = peaks()
+        step_ms = res['ms'] / max(res['steps'] / world, 1)
+        wbytes = weight_bytes_per_step(model)
         line = {
-            'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
+            'metric': metric_name(args.model),
             'value': res['tokens'] / (res['ms'] / 1e3), 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': res['ms'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16', 'data': 'synthetic (phrase-bank prompts, random-init weights of the named shape)',
+            'dtype': 'bf16', 'data': 'synthetic (phrase-bank prompts; hashed weights of the named shape whose greedy '
+                                     'decoding is a noisy first-order chain, identical in the GPU and CPU arms)',
             'mean_accepted_len_per_step': res['mean_edl'], 'verify_steps': res['steps'],
-            'first_epoch': {'value': first['tokens'] / (first['ms'] / 1e3), 'unit': 'tokens/s',
-                            'mean_accepted_len_per_step': first['mean_edl'], 'verify_steps': first['steps'],
-                            'ms_per_verify_step': first['ms'] / max(first['steps'] / world, 1)},
-            'ms_per_verify_step': res['ms'] / max(res['steps'] / world, 1),
-            'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft, '
-                                   f'{PROMPT_LEN}-token prompt -> {NEW_TOKENS} new tokens, 1 request per step per GPU',
-                       'l2': 'inputs larger than L2: every verify step streams the full weight set (>= 13 GB) and the '
-                             'KV cache of all layers',
-                       'trie': f'warmed by {Wm} untimed requests on other prompts, then by one earlier epoch over the timed '
-                               'prompts (value = epoch 2; first_epoch = epoch 1, cold for these prompts)',
-                       'parallelism': f'{world} independent replicas' if world > 1 else 'single GPU',
-                       'peaks': src},
+            'ms_per_verify_step': step_ms,
+            'second_epoch': {'value': second['tokens'] / (second['ms'] / 1e3), 'unit': 'tokens/s',
+                             'mean_accepted_len_per_step': second['mean_edl'], 'verify_steps': second['steps'],
+                             'ms_per_verify_step': second['ms'] / max(second['steps'] / world, 1)},
+            'config': workload_config(args, world, src),
             'clocks': sampler.summary(),
+            'per_rank_ms': res['per_rank_ms'],
             'e2e': {'value': e2e['tokens'] / (e2e['ms'] / 1e3), 'unit': 'tokens/s',
                     'h2d_bytes_per_step': PROMPT_LEN * 8,
                     'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (4 + DL)),
-                    'mean_accepted_len_per_step': e2e['mean_edl']},
+                    'mean_accepted_len_per_step': e2e['mean_edl'], 'verify_steps': e2e['steps'],
+                    'ms_per_verify_step': e2e['ms'] / max(e2e['steps'] / world, 1),
+                    'same_trie_state_as_value': True, 'same_tokens_as_value': bool(same_tokens)},
             'gpu_launches': res['launches'],
-            'roofline': roof, 'roofline_long_context': roof_long, 'roofline_trie_get': trie_roof, 'cpu_baseline': cpu,
+            'roofline_step': {'bound': 'hbm', 'bytes_per_step': wbytes, 'ms_per_step': step_ms,
+                              'achieved': wbytes / (step_ms * 1e-3) / 1e9, 'peak': hbm, 'unit': 'GB/s',
+                              'frac': wbytes / (step_ms * 1e-3) / 1e9 / hbm,
+                              'note': 'decoder + lm_head weight bytes streamed by one verify step / measured time per '
+                                      'verify step (host gaps, prefill and trie work included)'},
         }
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_config(args, world, peaks_src):
+    penalty = MODELS[args.model][7]
+    return {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft, {PROMPT_LEN}-token prompt -> '
+                        f'{NEW_TOKENS} new tokens, repetition_penalty {penalty}, 1 request per step per GPU',
+            'l2': 'inputs larger than L2: every verify step streams the full weight set (>= 13 GB) and the KV cache of '
+                  'all layers',
+            'trie': 'warmed by the untimed warm-up requests on OTHER prompts only; value and e2e both start from that '
+                    'trie state (snapshot / restore), second_epoch = a later pass that has seen each answer once',
+            'weights': f'synth_fill: decoder N(0,0.02^2) hashed, embedding std {EMBED_STD}, successor lm_head x{LM_SCALE}',
+            'parallelism': f'{world} independent replicas, identical requests on every replica' if world > 1 else 'single GPU',
+            'peaks': peaks_src}
+
+
+def weight_bytes_per_step(model):
+    """algorithmic HBM bytes of one verify step: every decoder / lm_head weight once (the embedding is gathered)"""
+    n = 0
+    for name, p in model.named_parameters():
+        if 'embed_tokens' in name:
+            continue
+        n += p.numel() * p.element_size()
+    return n
 
 
 def ncu_traffic(prefix, kernel):
@@ -224,8 +358,7 @@ def ncu_traffic(prefix, kernel):
     capture name starts with `prefix` (profiles/*_traffic.json, written by scripts/summarize_profiles.py); None when
     there is no such capture"""
     import glob
-    for f in sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', '*_traffic.json')),
-                    reverse=True):
+    for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
         try:
             for k, v in json.load(open(f)).items():
                 name, _, kern = k.partition(':')
@@ -236,29 +369,14 @@ def ncu_traffic(prefix, kernel):
     return None
 
 
-def attention_roofline(model, dev):
-    """k_tree_attn alone at the benchmark shape: 64 draft rows, prefix ~ mid-generation, all layers in turn (the
-    layers' KV planes together exceed L2, so every launch reads cold HBM).  CUDA events on the launch stream."""
+def _graph_time(fn, reps=20):
+    """microseconds per replay of fn captured as a CUDA graph (so that the host launch path does not bound it)"""
     import torch
-    rt = model._rt
-    g = rt.g
-    P, n = PROMPT_LEN + NEW_TOKENS // 2, DL
-    rt.n.fill_(n)
-    rt.prefix_len.fill_(P)
-    rt.pad.zero_()
-    rt.mask.copy_(rt.chain)
-    L = P + n
-    reps = 20
-
-    def sweep():
-        for li in range(g['n_layers']):
-            rt.plan.forward(li, rt.q, rt.mask, rt.decode_bufs.slots, rt.attn)
-
-    sweep()
+    fn()
     torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()  # a graph, so that the host launch path does not bound the measurement
+    graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        sweep()
+        fn()
     graph.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -267,14 +385,63 @@ def attention_roofline(model, dev):
         graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * g['n_layers'])
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def gemm_roofline(model, dev):
+    """the step's dominant kernel by the committed launch list (profiles/*_launches.md): k_gemm_ws on the fused
+    gate/up projection.  All layers' plans in turn (their weights together exceed L2, so every launch streams cold
+    HBM), CUDA events around graph replays; algorithmic bytes = the weight once + the 64 activation rows + the output"""
+    rt = model._rt
+    plans = getattr(rt, 'gemm_plans', None)
+    if not plans:
+        return None
+    lp = [p for p in plans['layers'] if 'gate_up' in p]
+    if not lp:
+        return None
+    b = rt.decode_bufs
+
+    def sweep():
+        for p in lp:
+            p['gate_up'].run(64, out=b.gu)
+
+    us = _graph_time(sweep) / len(lp)
+    N, Kd = lp[0]['gate_up'].N, b.y.shape[1]
+    by = N * Kd * 2 + 64 * Kd * 2 + 64 * N * 2
+    hbm, _tf, src = peaks()
+    ach = by / (us * 1e-6) / 1e9
+    return {'kernel': 'k_gemm_ws<4> (gate_up projection, one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
+            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_gemm_ws', 'k_gemm_ws'),
+            'bytes_per_launch': by, 'us_per_launch': us, 'shape': f'Y[64,{N}] = X[64,{Kd}] W[{N},{Kd}]^T',
+            'peak_source': src}
+
+
+def attention_roofline(model, dev):
+    """k_tree_attn alone at the benchmark shape: 64 draft rows, prefix ~ mid-generation, all layers in turn (the
+    layers' KV planes together exceed L2, so every launch reads cold HBM).  CUDA events on the launch stream."""
+    rt = model._rt
+    g = rt.g
+    P, n = PROMPT_LEN + NEW_TOKENS // 2, DL
+    rt.n.fill_(n)
+    rt.prefix_len.fill_(P)
+    rt.pad.zero_()
+    rt.mask.copy_(rt.chain)
+    L = P + n
+
+    def sweep():
+        for li in range(g['n_layers']):
+            rt.plan.forward(li, rt.q, rt.mask, rt.decode_bufs.slots, rt.attn)
+
+    us = _graph_time(sweep) / g['n_layers']
     # algorithmic bytes per launch (SURVEY.md 8d): K,V rows of every KV head + Q read + O write
     by = 2 * L * g['n_kv_heads'] * g['head_dim'] * 2 + 2 * n * g['n_q_heads'] * g['head_dim'] * 2
-    hbm, _tf, src = peaks()
+    fl = 4.0 * n * L * g['head_dim'] * g['n_q_heads']
+    hbm, tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
     return {'kernel': 'k_tree_attn (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
             'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_attn_short', 'k_tree_attn'),
-            'bytes_per_launch': by, 'us_per_launch': us,
+            'bytes_per_launch': by, 'us_per_launch': us, 'tensor_tflops': fl / (us * 1e-6) / 1e12,
+            'tensor_frac': fl / (us * 1e-6) / 1e12 / tf,
             'shape': f'n={n} P={P} Hq={g["n_q_heads"]} Hkv={g["n_kv_heads"]} D={g["head_dim"]}', 'peak_source': src}
 
 
@@ -299,21 +466,7 @@ def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
         for li in range(layers):
             plan.forward(li, q, mask, slots, out)
 
-    sweep()
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        sweep()
-    graph.replay()
-    reps = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        graph.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * layers)
+    us = _graph_time(sweep) / layers
     L = P + n
     by = 2 * L * hkv * D * 2 + 2 * n * hq * D * 2
     hbm, _tf, src = peaks()
@@ -324,16 +477,21 @@ def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
             'shape': f'n={n} P={P} Hq={hq} Hkv={hkv} D={D}', 'peak_source': src}
 
 
-def trie_roofline(dev, n_docs=1500, n_queries=4096):
-    """batched synthetic scan of SURVEY.md 8d: forest grown from phrase-bank documents, 4096 concurrent hier_get
-    queries; bytes = node records (32 B) + child entries (8 B) actually visited, counted by the kernel."""
-    import torch
-    from painlessinferenceacceleration_b200 import _lib as L
+def _forest(dev, n_docs):
     from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
     c = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=32000, node_capacity=1 << 23, max_resident_queries=592)
     docs = phrase_bank_prompts(n_docs, 32000, length=256, seed=7)
     for d in docs:
         c.put(d, branch_length=9, mode='output', idx=-1)
+    return c, docs
+
+
+def trie_roofline(dev, n_docs=1500, n_queries=4096):
+    """batched synthetic scan of SURVEY.md 8d: forest grown from phrase-bank documents, 4096 concurrent hier_get
+    queries; bytes = node records (32 B) + child entries (8 B) actually visited, counted by the kernel."""
+    import torch
+    from painlessinferenceacceleration_b200 import _lib as L
+    c, docs = _forest(dev, n_docs)
     rng = np.random.default_rng(8)
     qs = []
     for _ in range(n_queries):
@@ -374,9 +532,95 @@ def trie_roofline(dev, n_docs=1500, n_queries=4096):
             'forest_nodes': s1['nodes_used'], 'mean_draft': float(o['n'].float().mean()), 'peak_source': src}
 
 
+def trie_counters(dev, n_docs=200, n_ops=200):
+    """perf_check_trie-style counters (benchmarks/benchmark.py:353-395): microseconds per get / stream_put / prompt put
+    through the LookaheadCache API (host call, kernel, result back on the host), next to the same ops on the CPU trie
+    restatement (oracle, 1 thread)"""
+    import torch
+    c, docs = _forest(dev, n_docs)
+    rng = np.random.default_rng(9)
+    qs = [docs[int(rng.integers(0, n_docs))][j:j + 2] for j in rng.integers(0, 250, size=n_ops).tolist()]
+    out = {}
+
+    def timeit(fn, n):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(n):
+            fn(i)
+        torch.cuda.synchronize()
+        return (time.time() - t0) / n * 1e6
+
+    c.hier_get(qs[0], decoding_length=DL, branch_length=BL, min_output_size=DL // 2)
+    out['gpu_us_per_hier_get'] = timeit(lambda i: c.hier_get(qs[i], decoding_length=DL, branch_length=BL,
+                                                             min_output_size=DL // 2), n_ops)
+    out['gpu_us_per_stream_put_4'] = timeit(lambda i: c.stream_put(docs[i % n_docs][8:12], branch_length=BL + 1), n_ops)
+    out['gpu_us_per_prompt_put_256'] = timeit(lambda i: c.put(docs[i % n_docs], branch_length=BL + 1, mode='input', idx=0), 50)
+    out['forest_nodes'] = c.stats()['nodes_used']
+    try:
+        from oracle.trie import OracleLookaheadCache
+        o = OracleLookaheadCache(eos_ids=[2])
+        for d in docs:
+            o.put(d, branch_length=9, mode='output', idx=-1)
+
+        def cput(fn, n):
+            t0 = time.time()
+            for i in range(n):
+                fn(i)
+            return (time.time() - t0) / n * 1e6
+
+        out['cpu_port_us_per_hier_get'] = cput(lambda i: o.hier_get(qs[i], decoding_length=DL, branch_length=BL,
+                                                                    min_output_size=DL // 2), n_ops)
+        out['cpu_port_us_per_stream_put_4'] = cput(lambda i: o.stream_put(docs[i % n_docs][8:12], branch_length=BL + 1), n_ops)
+        out['cpu_port_us_per_prompt_put_256'] = cput(lambda i: o.put(docs[i % n_docs], branch_length=BL + 1, mode='input', idx=0), 50)
+        out['cpu_kind'] = 'port (oracle/trie_oracle.c, 1 thread); the Python reference measured 1.5-12 ms per get (BASELINE.md 2)'
+    except Exception as e:  # pragma: no cover
+        out['cpu_port_error'] = f'{type(e).__name__}: {e}'
+    return out
+
+
+def batched_line(args, cfg, model, dev, allp, bs=8):
+    """BASELINE config 5's "batch=8/GPU" served as a true batch (common/pretrained_model_batch.py): 8 requests share
+    the 64 draft rows of one verify step.  Two draft shares: 'reference' = decoding_length // active // active (what the
+    reference's bat_get computes: 1 node per request at 8 requests, i.e. batched plain decoding) and 'rows' =
+    decoding_length // active.  Same weights (the batch class shares the parameters), fresh trie warmed like the
+    headline run."""
+    import torch
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    from painlessinferenceacceleration_b200.models.llama.modeling_llama_batch import LlamaForCausalLM as BatchCls
+    bm = BatchCls(cfg, device=dev)
+    for (n1, p1), (n2, p2) in zip(bm.named_parameters(), model.named_parameters()):
+        assert n1 == n2
+        p1.data = p2.data
+    bm._tiled_weights = getattr(model, '_tiled_weights', {})
+    penalty = MODELS[args.model][7]
+    out = {}
+    for mode in ('rows', 'reference'):
+        bm.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size, n_input_slots=bs)
+        dk = {'use_lookahead': True, 'decoding_length': DL, 'branch_length': BL, 'batch_share': mode}
+        gen = dict(max_new_tokens=NEW_TOKENS, eos_token_id=2, decoding_kwargs=dk, return_dict_in_generate=True,
+                   repetition_penalty=penalty)
+        warm = torch.tensor(allp[64:64 + bs], device=dev)
+        bm.generate(input_ids=warm, **gen)                     # untimed: graphs + trie warm-up on other prompts
+        ids = torch.tensor(allp[:bs], device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        o = bm.generate(input_ids=ids, **gen)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        toks = sum(o.kwargs['lengths']) - bs * PROMPT_LEN
+        edls = o.kwargs['edls'][bs:]
+        out[mode] = {'value': toks / (ms / 1e3), 'unit': 'tokens/s', 'batch': bs, 'tokens': toks, 'ms': ms,
+                     'mean_accepted_len_per_request_step': float(np.mean(edls)) if edls else None}
+    bm._rt = None
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- CPU arms
 def build_cpu_model(name):
-    """HF model of the named shape on the host, bf16, weights tiled from one random block (timing only)"""
+    """HF eager model of the named shape on the host, bf16, the SAME synthetic weights as the GPU arm"""
     import torch
     from transformers import AutoModelForCausalLM
     cfg, _ = make_config(name)
@@ -384,17 +628,8 @@ def build_cpu_model(name):
     with torch.device('meta'):
         m = AutoModelForCausalLM.from_config(cfg, attn_implementation='eager', dtype=torch.bfloat16)
     m = m.to_empty(device='cpu')
-    g = torch.Generator().manual_seed(0)
-    block = (torch.randn((1 << 22,), generator=g) * 0.02).to(torch.bfloat16)
+    synth_fill(m, cfg)
     with torch.no_grad():
-        for n_, p in m.named_parameters():
-            flat = p.data.view(-1)
-            if 'norm' in n_:
-                flat.fill_(1.0)
-                continue
-            for i in range(0, flat.numel(), block.numel()):
-                k = min(block.numel(), flat.numel() - i)
-                flat[i:i + k] = block[:k]
         for n_, b in m.named_buffers():
             if 'inv_freq' in n_:
                 hd = cfg.hidden_size // cfg.num_attention_heads
@@ -402,106 +637,80 @@ def build_cpu_model(name):
     return m.eval()
 
 
-def cpu_probe(model, n_tok=16):
-    """seconds of one eager forward over n_tok tokens on the host (second call, after thread-pool warm-up)"""
-    import torch
-    x = torch.randint(3, 1000, (1, n_tok))
-    with torch.no_grad():
-        model(input_ids=x)
-        t0 = time.time()
-        model(input_ids=x)
-    return time.time() - t0
-
-
-def cpu_sample(model, trie, prompt, budget_s, max_new=NEW_TOKENS):
-    """one request through the oracle loop (oracle/loop.py = the reference's CPU path restated), cut off at the first
-    step boundary after `budget_s` seconds (never before its first verify step); returns (new tokens, seconds, edls,
-    per-forward seconds)"""
-    import torch
-    from oracle.loop import lookahead_generate
-    t0 = time.time()
-    r = lookahead_generate(model, trie, torch.tensor([prompt]), max_new_tokens=max_new, eos_token_id=[2],
-                           decoding_length=DL, branch_length=BL, time_budget_s=budget_s)
-    return r['sequences'].shape[1] - len(prompt), time.time() - t0, r['edls'], r['fts']
-
-
-def cpu_epoch2_sample(model, trie, prompt, step_budget_s):
-    """the bench's regime (second epoch: the trie has seen this prompt's answer once) as a bounded CPU sample:
-    an UNTIMED cold run of the request, cut at the first step boundary after 35 % of the step budget, produces g
-    tokens; the TIMED run then regenerates those g tokens (prefill + verify steps that now draft from the trie), itself
-    cut at the first step boundary after 50 % of the budget."""
-    g, _, _, _ = cpu_sample(model, trie, prompt, 0.35 * step_budget_s)
-    return cpu_sample(model, trie, prompt, 0.5 * step_budget_s, max_new=max(g, 1))
-
-
 def cpu_threads():
     """host threads for the CPU arms: small-row GEMMs stop scaling (and then degrade) beyond a few dozen threads"""
     return max(1, min(os.cpu_count() or 1, 32))
 
 
-def cpu_plan(model, step_budget_s):
-    """how much of the 256-token prompt a CPU sample may use: a 16-token probe forward gives the host's speed
-    (forwards scale ~linearly in rows at these sizes); the prefill may take at most 15 % of a step's budget.
-    returns (S, probe seconds)"""
-    f16 = cpu_probe(model, 16)
-    per_tok = f16 / 16.0
-    S = PROMPT_LEN
-    while S > 16 and S * per_tok > 0.15 * step_budget_s:
-        S //= 2
-    return S, f16
+def cpu_request(model, trie, prompt, penalty, new_tokens=CPU_NEW_TOKENS):
+    """one request of the fixed CPU sample through the oracle loop (oracle/loop.py = the reference's CPU path restated):
+    the full 256-token prompt, `new_tokens` generated tokens"""
+    import torch
+    from oracle.loop import lookahead_generate
+    t0 = time.time()
+    r = lookahead_generate(model, trie, torch.tensor([prompt]), max_new_tokens=new_tokens, eos_token_id=[2],
+                           decoding_length=DL, branch_length=BL, repetition_penalty=penalty)
+    return dict(tokens=r['sequences'][0, len(prompt):].tolist(), seconds=time.time() - t0, edls=r['edls'], dls=r['dls'],
+                fts=r['fts'])
 
 
-def cpu_summary(S, samples):
-    """tokens/s of the bounded samples + what the same per-forward times give for a full 256 -> 256 request (prefill
-    scaled to the full prompt, verify-step time and accepted length as measured)"""
-    toks = sum(n for n, _, _, _ in samples)
-    secs = sum(s_ for _, s_, _, _ in samples)
-    edls = [e for _, _, ed, _ in samples for e in ed[1:]]
-    pre = float(np.mean([ft[0] for _, _, _, ft in samples]))
-    ver = [t for _, _, _, ft in samples for t in ft[1:]]
-    full = None
-    if edls and ver:
-        edl, step = float(np.mean(edls)), float(np.mean(ver))
-        full = NEW_TOKENS / (pre * PROMPT_LEN / S + NEW_TOKENS / edl * step)
-    return toks, secs, edls, {'prefill_s': pre, 'verify_step_s': float(np.mean(ver)) if ver else None,
-                              'full_request_tokens_per_s_extrapolated': full}
+CPU_SAMPLE = ('{n} requests of the SAME workload cut to a fixed size: the full {p}-token prompt (prefill included) + '
+              '{g} generated tokens each, 64/8 drafts, same synthetic weights and prompts as the GPU arm, trie warmed by '
+              '{w} such requests on other prompts; oracle/loop.py + the C restatement of the trie over the installed HF '
+              'eager bf16 model, {t} host threads')
 
 
-SAMPLE_NOTE = ('1 request = prefill of the first {S} of the {p} prompt tokens + the verify steps that regenerate the g tokens an '
-               'untimed cold run of the same request produced (cold run cut at the first step boundary after 35 % of the '
-               "step's {b:.0f}s budget, timed run after 50 %; second-epoch regime of the GPU arm; a 16-token probe forward "
-               'took {f:.2f}s on this host with {t} threads; the prefill is amortised over g, not {n}, tokens - see '
-               'full_request_tokens_per_s_extrapolated)')
-
-
-def cpu_baseline(args, warm_outputs, prompt, total_budget_s=45.0):
+def cpu_baseline(args, cfg, model, dev, allp, n_req=2):
+    """rank 0, N=1: the CPU port on a bounded, fixed sample, and the cross-check BASELINE.md 3 promised: the same
+    requests through the GPU path from the same (fresh) trie state must give the same tokens and the same accepted
+    lengths (identical weights; bf16 near-ties are reported, not hidden)"""
     import torch
     from oracle.trie import OracleLookaheadCache
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    penalty = MODELS[args.model][7]
     threads = cpu_threads()
     torch.set_num_threads(threads)
     t0 = time.time()
-    model = build_cpu_model(args.model)
-    trie = OracleLookaheadCache(eos_ids=[2])
-    for w in warm_outputs:  # same warm-up text as the GPU run (benchmark.py:159-169)
-        trie.put(w, branch_length=BL + 1, mode='output', idx=-1)
+    cpu_model = build_cpu_model(args.model)
     build_s = time.time() - t0
-    S, f16 = cpu_plan(model, total_budget_s)
-    smp = cpu_epoch2_sample(model, trie, prompt[:S], total_budget_s)
-    ntok, secs, edls, extra = cpu_summary(S, [smp])
-    out = {'value': ntok / secs, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
-           'sample': f'oracle/loop.py + oracle trie, {args.model} bf16 weights on host: '
-                     + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads, b=total_budget_s)
-                     + f'; {ntok} tokens in {secs:.1f}s over {len(smp[2])} forwards (model build {build_s:.0f}s untimed)',
-           'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None}
-    out.update(extra)
-    return out
+    ctrie = OracleLookaheadCache(eos_ids=[2])
+    saved = model.lookahead_cache
+    model.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size)
+    rows, secs, toks, edls = [], 0.0, 0, []
+    try:
+        for rep in range(2):   # the second pass drafts the first pass's answers: multi-token accepts on both sides
+            for i in range(n_req):
+                c = cpu_request(cpu_model, ctrie, allp[i], penalty)
+                g = model.generate(input_ids=torch.tensor([allp[i]], device=dev), max_new_tokens=CPU_NEW_TOKENS,
+                                   eos_token_id=2, repetition_penalty=penalty, return_dict_in_generate=True,
+                                   decoding_kwargs={'use_lookahead': True, 'decoding_length': DL, 'branch_length': BL})
+                gt = g.sequences[0, PROMPT_LEN:].tolist()
+                same = gt == c['tokens']
+                rows.append({'request': i, 'pass': rep, 'tokens_equal': same,
+                             'edls_equal': bool(same and g.kwargs['edls'] == c['edls']),
+                             'cpu_edl': float(np.mean(c['edls'][1:])) if len(c['edls']) > 1 else None,
+                             'gpu_edl': float(np.mean(g.kwargs['edls'][1:])) if len(g.kwargs['edls']) > 1 else None})
+                secs += c['seconds']
+                toks += len(c['tokens'])
+                edls += c['edls'][1:]
+                if not same:  # a bf16 near-tie: the texts (and so the tries) part ways, resync both
+                    ctrie.fresh()
+                    model.lookahead_cache.fresh()
+    finally:
+        model.lookahead_cache = saved
+    return {'value': toks / secs, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
+            'sample': CPU_SAMPLE.format(n=2 * n_req, p=PROMPT_LEN, g=CPU_NEW_TOKENS, w=0, t=threads)
+            + f' (2 passes over {n_req} prompts from a fresh trie); {toks} tokens in {secs:.1f}s, model build {build_s:.0f}s untimed',
+            'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None,
+            'cross_check_vs_gpu': {'requests': rows, 'all_tokens_equal': all(r['tokens_equal'] for r in rows),
+                                   'edl_equal_where_tokens_equal': all(r['edls_equal'] for r in rows if r['tokens_equal'])}}
 
 
-def run_reference(args, total_budget_s=150.0):
+def run_reference(args):
     """--impl reference: the reference's own CPU path (restated: oracle/loop.py over the installed HF eager model +
-    the C restatement of its trie) on the host cores; rank 0 only.  The whole run is time-boxed (~total_budget_s of
-    forwards + the model build) whatever --steps/--warmup are: every step gets total_budget_s / steps seconds, and when
-    the host is too slow for that, fewer steps are executed and the sample text says how many."""
+    the C restatement of its trie) on the host cores; rank 0 only.  FIXED sample, independent of the host's speed:
+    every step = one request with the full 256-token prompt and CPU_NEW_TOKENS generated tokens; warm-up = the same on
+    the warm-up prompts.  Same metric / config / weights / prompts as the GPU arm."""
     import torch
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -510,38 +719,33 @@ def run_reference(args, total_budget_s=150.0):
     threads = cpu_threads()
     torch.set_num_threads(threads)
     cfg, _ = make_config(args.model)
+    penalty = MODELS[args.model][7]
     model = build_cpu_model(args.model)
     trie = OracleLookaheadCache(eos_ids=[2])
-    allp = phrase_bank_prompts(64 + 8 * max(args.warmup, 1), cfg.vocab_size)
     K, Wm = args.steps, args.warmup
-    B = total_budget_s / max(K, 1)
-    S, f16 = cpu_plan(model, B)
-    t_start = time.time()
-    for i in range(Wm):  # warm-up: one prefill + one verify step each, only while it stays cheap
-        if time.time() - t_start > 0.1 * total_budget_s:
-            break
-        cpu_sample(model, trie, allp[64 + i][:S], 0.0, max_new=2)
-    t_start = time.time()
-    samples, last = [], 0.0
-    for i in range(K):
-        if samples and time.time() - t_start + last > total_budget_s:
-            break
-        t0 = time.time()
-        samples.append(cpu_epoch2_sample(model, trie, allp[i % 64][:S], B))
-        last = time.time() - t0
-    toks, secs, edls, extra = cpu_summary(S, samples)
+    allp = phrase_bank_prompts(64 + 8 * max(Wm, 1), cfg.vocab_size)
+    for i in range(Wm):
+        cpu_request(model, trie, allp[64 + i % (8 * max(Wm, 1))], penalty)
+    samples = [cpu_request(model, trie, allp[j], penalty) for j in timed_requests(K)]
+    toks = sum(len(s['tokens']) for s in samples)
+    secs = sum(s['seconds'] for s in samples)
+    edls = [e for s in samples for e in s['edls'][1:]]
+    pre = float(np.mean([s['fts'][0] for s in samples]))
+    ver = [t for s in samples for t in s['fts'][1:]]
     v = toks / secs
-    sample = ('per step: ' + SAMPLE_NOTE.format(S=S, p=PROMPT_LEN, f=f16, n=NEW_TOKENS, t=threads, b=B)
-              + f'; {args.model} bf16; {len(samples)} of the {K} requested steps executed: {toks} tokens in {secs:.0f}s')
-    cpu = {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample}
-    cpu.update(extra)
+    sample = CPU_SAMPLE.format(n=K, p=PROMPT_LEN, g=CPU_NEW_TOKENS, w=Wm, t=threads) + f'; {toks} tokens in {secs:.0f}s'
+    cpu = {'value': v, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+           'prefill_s': pre, 'verify_step_s': float(np.mean(ver)) if ver else None,
+           'full_request_tokens_per_s_extrapolated':
+               (NEW_TOKENS / (pre + NEW_TOKENS / float(np.mean(edls)) * float(np.mean(ver)))) if ver and edls else None}
     print(json.dumps({
-        'impl': 'reference', 'metric': 'accepted tokens/sec @ Llama-2-7B 64-draft/8-branch; mean accepted len/step',
+        'impl': 'reference', 'metric': metric_name(args.model),
         'value': v, 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': K, 'warmup': Wm,
         'ms_per_step': secs / len(samples) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic',
+        'dtype': 'bf16', 'data': 'synthetic (phrase-bank prompts; hashed weights of the named shape whose greedy '
+                                 'decoding is a noisy first-order chain, identical in the GPU and CPU arms)',
         'mean_accepted_len_per_step': float(np.mean(edls)) if edls else None,
-        'config': {'workload': f'{args.model} bf16, greedy, {DL}-token/{BL}-branch trie draft', 'sample': sample},
+        'config': workload_config(args, args.gpus, peaks()[2]),
         'cpu_baseline': cpu,
         'e2e': {'value': v, 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
@@ -554,6 +758,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--model', default='llama2-7b', choices=sorted(MODELS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-batched', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

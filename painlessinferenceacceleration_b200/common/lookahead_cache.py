@@ -352,6 +352,20 @@ class LookaheadCache(object):
                                           root_of.ctypes.data, n_node.ctypes.data, n_out.ctypes.data, t.stream()))
         return nodes[:nn.value], edges[:ne.value], root_of, n_node, n_out
 
+    def snapshot(self):
+        """the forest as raw host arrays (pia_trie_export); restore() puts it back.  Pending stream_put carries and
+        the touched-tree lists are not part of it: take it between requests."""
+        return self._export_arrays()
+
+    def restore(self, snap):
+        nodes, edges, root_of, n_node, n_out = snap
+        nodes = np.ascontiguousarray(nodes) if len(nodes) else np.zeros((1,), dtype=_NODE_DTYPE)
+        edges = np.ascontiguousarray(edges) if len(edges) else np.zeros((1, 2), dtype=np.int32)
+        t = self._t
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_import(t.h, nodes.ctypes.data, len(snap[0]), edges.ctypes.data, len(snap[1]),
+                                          root_of.ctypes.data, n_node.ctypes.data, n_out.ctypes.data, t.stream()))
+
     def to_reference_mem(self):
         """the forest as the reference's `mem` structure: {token: Tree} of nested Node dicts"""
         nodes, edges, root_of, n_node, n_out = self._export_arrays()
