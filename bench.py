@@ -88,20 +88,26 @@ def _hash32(i, seed):
 
 
 def hashed_normal_(t, seed, std):
-    """fills tensor t (bf16) in place with ~N(0, std^2) values that are a pure function of (seed, element index):
-    the sum of the four bytes of a 32-bit hash (Irwin-Hall, variance 4 * (256^2 - 1) / 12), centred and scaled"""
+    """fills tensor t (bf16) in place with zero-mean values of standard deviation std that are a pure function of
+    (seed, element index) and identical on CPU and CUDA: a 24-bit uniform drawn from a two-round multiply/xorshift hash
+    of the index (int32 wrap-around arithmetic), centred and scaled to the requested std"""
     import torch
     flat = t.view(-1)
     n = flat.numel()
-    seed = int(seed) & 0x7FFFFFFF
     chunk = 1 << 24
-    for s in range(0, n, chunk):
+    dev = t.device
+    base = torch.arange(chunk, dtype=torch.int32, device=dev)
+    c1 = torch.tensor(-1640531535, dtype=torch.int32, device=dev)   # 0x9E3779B1
+    c2 = torch.tensor(-2048144789, dtype=torch.int32, device=dev)   # 0x85EBCA6B
+    scale = std * (12.0 ** 0.5) / 16777216.0
+    for k, s in enumerate(range(0, n, chunk)):
         e = min(n, s + chunk)
-        i = torch.arange(s, e, dtype=torch.int64, device=t.device)
-        lo = (i & 0x7FFFFFFF).to(torch.int32) ^ ((i >> 31).to(torch.int32) * 668265263)
-        x = _hash32(lo, torch.tensor(seed, dtype=torch.int32, device=t.device))
-        b = (x & 255) + ((x >> 8) & 255) + ((x >> 16) & 255) + ((x >> 24) & 255)
-        flat[s:e] = ((b.to(torch.float32) - 510.0) * (std / 147.80)).to(t.dtype)
+        salt = (int(seed) * 2654435761 + (k + 1) * 40503) & 0x7FFFFFFF
+        x = (base[:e - s] ^ salt) * c1
+        x = x ^ ((x >> 15) & 0x1FFFF)
+        x = x * c2
+        x = x ^ ((x >> 13) & 0x7FFFF)
+        flat[s:e] = (((x & 0xFFFFFF).to(torch.float32) - 8388607.5) * scale).to(t.dtype)
     return t
 
 
@@ -116,7 +122,7 @@ def successor_map(vocab, seed=99):
 
 def synth_fill(model, cfg, seed=0, embed_std=None):
     """the benchmark's weights, identical on every device and in every arm (HF parameter names): norms = 1, decoder
-    weights ~ N(0, 0.02^2), embedding ~ N(0, embed_std^2), lm_head row v = LM_SCALE * sum of the unit embeddings of the
+    weights ~ U(std 0.02), embedding ~ U(std embed_std), lm_head row v = LM_SCALE * sum of the unit embeddings of the
     tokens t with succ(t) = v (hashed N(0, 0.02^2) for tokens without a predecessor)"""
     import torch
     embed_std = EMBED_STD if embed_std is None else embed_std

@@ -292,6 +292,9 @@ typedef struct {
  *   d_seq : [batch, seq_stride] int32 token sequences (prompt + generated), d_seq_len [batch] their lengths; the
  *           accepted tokens are appended and d_seq_len advanced.
  *   d_max_length : device int overriding cfg->max_length, or NULL
+ *   d_rng : NULL = greedy arg-max (:839).  Else multinomial accept (do_sample, :835-837): {seed, step counter} in
+ *           device memory; every node draws from softmax(its penalised logits) by the Gumbel-max construction and the
+ *           counter is advanced once per call.  The draws are not torch.multinomial's stream: parity is distributional.
  *   d_accept_tokens [batch, cfg->max_nodes] accepted tokens (draft matches + bonus); d_accept_count [batch] (edl)
  *   d_accept_nodes  [batch, cfg->max_nodes] draft node index (slot relative) whose logits produced each token
  *                   (logit_indices :845)
@@ -300,7 +303,8 @@ typedef struct {
  * batch * rows_per_slot <= cfg->max_nodes.  A slot with d_n == 0 is idle (count 0). */
 int pia_accept(const pia_accept_config_t *cfg, const void *d_logits, const int32_t *d_ids, const uint64_t *d_mask,
                int mask_words, int batch, int rows_per_slot, const int32_t *d_n, int32_t *d_seq, int32_t *d_seq_len,
-               int seq_stride, const int32_t *d_max_length, int32_t *d_accept_tokens, int32_t *d_accept_count,
+               int seq_stride, const int32_t *d_max_length, uint32_t *d_rng, int32_t *d_accept_tokens,
+               int32_t *d_accept_count,
                int32_t *d_accept_nodes, int32_t *d_prefix_len, int32_t *d_finished, void *d_workspace, void *stream);
 int64_t pia_accept_workspace_bytes(const pia_accept_config_t *cfg);
 
@@ -311,6 +315,35 @@ int64_t pia_accept_workspace_bytes(const pia_accept_config_t *cfg);
 int pia_kv_compact(void *d_k_cache, void *d_v_cache, int n_layers, int n_kv_heads, int max_seq, int head_dim, int batch,
                    int64_t kv_slot_stride, const int32_t *d_accept_nodes, int nodes_stride,
                    const int32_t *d_accept_count, const int32_t *d_prefix_len, void *stream);
+
+/* ============================================================================================
+ * FLOOD `Spec` integration: the hash-table lookahead draft of flood/flood/utils/speculative.py:23-124
+ * (class Lookahead) whose Triton kernels live in flood/flood/ops/draft.py.  Tables are FLOOD's own: freq_table
+ * float32 [table_size], draft_table int32 [table_size, branch_length]; a 2-token context (p0, p1) owns the
+ * branch_count slots from bucket (p0 * vocab + p1) % (table_size - branch_count).
+ * ============================================================================================ */
+/* update_draft_table (draft.py:168-204, kernel :92-165): every position p of d_tokens[token_count] with p + 4 <=
+ * token_count inserts / reinforces the branch tokens[p+2 : p+2+branch_length] under context (tokens[p], tokens[p+1]);
+ * all slots of the bucket decay by 1/2 per update.  Positions are applied in order. */
+int pia_flood_update_draft_table(const int32_t *d_tokens, int token_count, float *d_freq_table, int32_t *d_draft_table,
+                                 int64_t table_size, int branch_length, int branch_count, int vocab, void *stream);
+/* retrieve_draft_table (draft.py:352-402, kernel :278-349): d_queries [batch, 2] -> d_out_tokens
+ * [batch, retrieve_count * branch_length + 1] (zero-filled by the caller): [p1, branch 0, branch 1, ...], the
+ * retrieve_count most established branches by the 64, 32, ..., 0.5 frequency ladder. */
+int pia_flood_retrieve_draft_table(const int32_t *d_queries, int batch, const float *d_freq_table,
+                                   const int32_t *d_draft_table, int64_t table_size, int vocab, int branch_length,
+                                   int branch_count, int retrieve_count, int32_t *d_out_tokens, void *stream);
+/* verify_draft (draft.py:491-543, kernel :406-488): d_input_ids / d_next_ids [batch, branch_count * branch_length] (the
+ * flattened draft layout of retrieve_draft_table and the model's next token at each of its positions) -> the longest
+ * accepted branch: d_output_ids [batch, branch_length + 1], d_cache_src / d_cache_dst [batch * branch_length]
+ * (all three filled with -1 by the caller); d_cache_offsets [batch] = first cache row of each request's draft. */
+int pia_flood_verify_draft(const int32_t *d_input_ids, const int32_t *d_next_ids, const int32_t *d_cache_offsets, int batch,
+                           int branch_count, int branch_length, int32_t *d_output_ids, int32_t *d_cache_src,
+                           int32_t *d_cache_dst, void *stream);
+/* update_draft_cache (draft.py:562-570, kernel :547-559): cache row d_src[i] -> row d_dst[i] for every i with
+ * d_src[i] >= 0 and d_src[i] != d_dst[i]; d_cache is [rows, row_bytes]. */
+int pia_flood_update_draft_cache(void *d_cache, int64_t row_bytes, const int32_t *d_src, const int32_t *d_dst, int count,
+                                 void *stream);
 
 #ifdef __cplusplus
 }

@@ -90,10 +90,15 @@ SYMBOLS = {
     'pia_moe_combine': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     'pia_l2_prefetch': (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, vp]),
     'pia_accept': (C.c_int, [C.POINTER(AcceptConfig), vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp,
-                             vp, vp, vp, vp, vp, vp, vp]),
+                             vp, vp, vp, vp, vp, vp, vp, vp]),
     'pia_accept_workspace_bytes': (C.c_int64, [C.POINTER(AcceptConfig)]),
     'pia_kv_compact': (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, vp, C.c_int, vp, vp,
                                  vp]),
+    'pia_flood_update_draft_table': (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]),
+    'pia_flood_retrieve_draft_table': (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                                                 vp]),
+    'pia_flood_verify_draft': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+    'pia_flood_update_draft_cache': (C.c_int, [vp, C.c_int64, vp, vp, C.c_int, vp]),
 }
 
 

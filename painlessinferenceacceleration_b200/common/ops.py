@@ -212,14 +212,15 @@ class Accept(object):
                                      dtype=torch.int32, device=device)
 
     def run(self, logits, ids, mask, n, seq, seq_len, acc_tokens, acc_count, acc_nodes, prefix_len, finished,
-            batch=1, rows_per_slot=None, max_length=None):
+            batch=1, rows_per_slot=None, max_length=None, rng=None):
         """ids [batch * rows_per_slot], mask [batch * rows_per_slot, W], n / seq_len / prefix_len / finished /
         acc_count [batch], seq [batch, stride] (or 1-D for one slot), acc_tokens / acc_nodes [batch, max_nodes];
-        max_length: optional int32 device scalar overriding the config's"""
+        max_length: optional int32 device scalar overriding the config's; rng: None (greedy) or an int32 device
+        tensor {seed, counter} -> multinomial accept (do_sample)"""
         rps = int(rows_per_slot if rows_per_slot is not None else self.max_nodes // batch)
         stride = seq.shape[-1] if seq.dim() == 2 else seq.numel()
         L.check(self.lib.pia_accept(C.byref(self.cfg), _p(logits), _p(ids), _p(mask), mask.shape[-1], int(batch), rps,
-                                    _p(n), _p(seq), _p(seq_len), int(stride), _p(max_length), _p(acc_tokens),
+                                    _p(n), _p(seq), _p(seq_len), int(stride), _p(max_length), _p(rng), _p(acc_tokens),
                                     _p(acc_count), _p(acc_nodes), _p(prefix_len), _p(finished), _p(self.workspace), _s()))
 
 

@@ -86,6 +86,7 @@ class _Runtime(object):
         self.pad = torch.zeros((S,), **i32)            # left-pad columns (pretrained_model.py:1123-1131)
         self.trie_idx = torch.arange(S, **i32)         # slot -> request idx of the trie (batched loop)
         self.max_length = torch.zeros((1,), **i32)     # MaxLengthCriteria, read on the device
+        self.rng = torch.zeros((2,), **i32)            # {seed, step counter} of the multinomial accept (do_sample)
         self.acc_tokens = torch.zeros((S, R), **i32)
         self.acc_count = torch.zeros((S,), **i32)
         self.acc_nodes = torch.zeros((S, R), **i32)
@@ -255,8 +256,8 @@ class LookaheadPreTrainedModel(nn.Module):
         eos = opt('eos_token_id', getattr(self.config, 'eos_token_id', None))
         pad = opt('pad_token_id', getattr(self.config, 'pad_token_id', None))
         mode = self._get_generation_mode(do_sample, use_cache, decoding_kwargs)
-        if mode == GenerationMode.SAMPLE or do_sample:
-            raise NotImplementedError('multinomial accept (pretrained_model.py:835-837) is SURVEY 8f-3, not built yet')
+        if do_sample and mode != GenerationMode.LOOKAHEAD_GENERATION:
+            decoding_kwargs = dict(decoding_kwargs, use_lookahead=False)  # plain sampling = a draft of the root alone
         # the reference mutates the caller's dict (:362-372)
         decoding_kwargs['generation_mode'] = mode
         decoding_kwargs['do_sample'] = do_sample
@@ -287,7 +288,7 @@ class LookaheadPreTrainedModel(nn.Module):
             rt.graphs.move_to_end(key)
         return ent
 
-    def _capture_step(self, rt, trie, use_trie, dl, bl, mql, min_out, tmode, kind, accept):
+    def _capture_step(self, rt, trie, use_trie, dl, bl, mql, min_out, tmode, kind, accept, sample=False):
         """one decode step of the per-request loop as a CUDA graph over the static buffers (slot 0)"""
         draft = dict(ids=rt.ids, mask=rt.mask, n=rt.n, sizes=rt.sizes, nsizes=rt.nsizes, status=rt.status)
 
@@ -304,7 +305,8 @@ class LookaheadPreTrainedModel(nn.Module):
                 rt.mask[0, 0:1].fill_(1)
             self._verify_layers(rt)
             accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
-                       rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length)
+                       rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length,
+                       rng=rt.rng if sample else None)
             ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len, batch=1)
             if use_trie:  # :1203
                 trie.stream_put_device(rt.acc_tokens, rt.max_nodes, rt.acc_count, branch_length=self._put_bl,
@@ -347,7 +349,11 @@ class LookaheadPreTrainedModel(nn.Module):
             dmode = dmode + '_mix'  # :712-713
         fmt, tmode = dmode.split('_')
         if fmt == 'par':
-            raise NotImplementedError('par_get drafts are host-composed (lookahead_cache.py:441-488); SURVEY 8f-3')
+            # the reference dies here as well: par_get returns a float64 mask (lookahead_cache.py:481), and its accept
+            # routine then slices a list with float indices (pretrained_model.py:817-819: TypeError on the first
+            # non-empty draft; tests/golden/gen_loop_golden.py).  LookaheadCache.par_get itself is built (host API).
+            raise TypeError('slice indices must be integers or None or have an __index__ method '
+                            "(decoding_mode 'par' never worked inside the reference's loop, pretrained_model.py:819)")
         assert dl <= 128 and bl <= 32, 'decoding_length <= 128 and branch_length <= 32 are built'
         if max_length is None:
             max_length = int(decoding_kwargs.get('max_length', 2048))
@@ -376,6 +382,10 @@ class LookaheadPreTrainedModel(nn.Module):
                 nz = torch.nonzero(am.to('cpu') != 0)
                 pad_len = int(nz[0]) if nz.numel() else 0
         rt.set_request(0, pad_len, max_length)
+        # multinomial accept (:787-789, :835-837): softmax of the processed scores, no warpers on this path (:430-441)
+        sample = bool(decoding_kwargs.get('do_sample', False))
+        if sample:
+            rt.rng.copy_(torch.tensor([torch.initial_seed() & 0x7FFFFFFF, rt.replays & 0x7FFFFFFF], dtype=torch.int32))
 
         ts = time.time()
         prompt = input_ids[0].to(device=dev, dtype=torch.int32)
@@ -389,7 +399,7 @@ class LookaheadPreTrainedModel(nn.Module):
         if accept is None:  # referenced by captured graphs: lives as long as the runtime
             accept = ops.Accept(self.geometry()['vocab'], max_nodes, repetition_penalty, eos_token_id, max_length, dev)
             rt.accepts[akey] = accept
-        first = self._prefill(rt, prompt_len, accept)
+        first = self._prefill(rt, prompt_len, accept, sample)
         new_tokens = [first]
         decoding_kwargs['dls'].append(1)  # the prefill step counts as one fed token (:797-798)
         decoding_kwargs['edls'].append(1)
@@ -404,11 +414,11 @@ class LookaheadPreTrainedModel(nn.Module):
         ts = te
 
         min_out = max(dl // 2, 1)  # :710
-        key = (use_trie, dl, bl, mql, tmode, fmt, akey, id(trie._t))
+        key = (use_trie, dl, bl, mql, tmode, fmt, akey, id(trie._t), sample)
         stream = torch.cuda.current_stream()
         if not finished:
             ent = self._graph_entry(rt, key, lambda: self._capture_step(
-                rt, trie, use_trie, dl, bl, mql, min_out, tmode, 'hier' if fmt == 'hier' else 'one', accept))
+                rt, trie, use_trie, dl, bl, mql, min_out, tmode, 'hier' if fmt == 'hier' else 'one', accept, sample))
             graphs = ent['graphs']
             # step k+1 is enqueued before the host reads record k: the ~0.25 ms of host work per step (record read,
             # python bookkeeping, streamer) overlaps the next verify forward; a step that runs after `finished` was
@@ -494,19 +504,20 @@ class LookaheadPreTrainedModel(nn.Module):
         y = self._prefill_kv(rt, prompt_len, slot)
         torch.mm(y, self.lm_head.weight.t(), out=rt.logits[row:row + 1])
 
-    def _prefill(self, rt, prompt_len, accept):
-        """prefill + the first generated token: (penalised) arg-max of the last prompt row's logits (:783-798)"""
+    def _prefill(self, rt, prompt_len, accept, sample=False):
+        """prefill + the first generated token: (penalised) arg-max / draw of the last prompt row's logits (:783-798)"""
         self._prefill_logits(rt, prompt_len)
-        return self._first_token(rt, prompt_len, accept)
+        return self._first_token(rt, prompt_len, accept, sample)
 
-    def _first_token(self, rt, prompt_len, accept):
+    def _first_token(self, rt, prompt_len, accept, sample=False):
         rt.ids[0:1] = rt.seq[0, prompt_len - 1:prompt_len]
         rt.mask.copy_(rt.chain)
         rt.n.fill_(1)
         rt.seq_len.fill_(prompt_len)
         rt.prefix_len.fill_(prompt_len)
         accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
-                   rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length)
+                   rt.prefix_len, rt.finished, batch=1, rows_per_slot=rt.max_nodes, max_length=rt.max_length,
+                   rng=rt.rng if sample else None)
         rt.prefix_len.fill_(prompt_len)
         return int(rt.acc_tokens[0, 0].item())
 

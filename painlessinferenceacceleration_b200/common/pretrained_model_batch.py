@@ -35,7 +35,7 @@ from .pretrained_model import LookaheadPreTrainedModel as _Base
 class LookaheadPreTrainedModel(_Base):
     _batch_generation = True
 
-    def _capture_batch_step(self, rt, trie, k, share, bl, mql, tmode, kind, accept):
+    def _capture_batch_step(self, rt, trie, k, share, bl, mql, tmode, kind, accept, sample=False):
         """one decode step over the k active slots (dense: slots 0..k-1), `share` draft rows each"""
         W = rt.max_nodes // 64
         rows = k * share
@@ -57,7 +57,8 @@ class LookaheadPreTrainedModel(_Base):
             finally:
                 db.slots, db.n_total = saved
             accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
-                       rt.prefix_len, rt.finished, batch=k, rows_per_slot=share, max_length=rt.max_length)
+                       rt.prefix_len, rt.finished, batch=k, rows_per_slot=share, max_length=rt.max_length,
+                       rng=rt.rng if sample else None)
             ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len, batch=k)
             for s in range(k):  # :1243-1248; the request idx of a slot is read on the device
                 trie.stream_put_device(rt.acc_tokens[s], rt.max_nodes, rt.acc_count[s:s + 1],
@@ -146,6 +147,9 @@ class LookaheadPreTrainedModel(_Base):
 
         # prefill (:781-808): every request through the chain-chunk prefill into its own cache, then one batched
         # arg-max of the last prompt rows
+        sample = bool(decoding_kwargs.get('do_sample', False))  # :796-798, :821-823, :871-873
+        if sample:
+            rt.rng.copy_(torch.tensor([torch.initial_seed() & 0x7FFFFFFF, rt.replays & 0x7FFFFFFF], dtype=torch.int32))
         share_mode = decoding_kwargs.get('batch_share', 'reference')
         assert share_mode in ('reference', 'rows')
 
@@ -166,7 +170,8 @@ class LookaheadPreTrainedModel(_Base):
         rt.seq_len[:bs].fill_(prompt_len)
         rt.prefix_len[:bs].fill_(prompt_len)
         accept.run(rt.logits, rt.ids, rt.mask, rt.n, rt.seq, rt.seq_len, rt.acc_tokens, rt.acc_count, rt.acc_nodes,
-                   rt.prefix_len, rt.finished, batch=bs, rows_per_slot=share, max_length=rt.max_length)
+                   rt.prefix_len, rt.finished, batch=bs, rows_per_slot=share, max_length=rt.max_length,
+                   rng=rt.rng if sample else None)
         rt.prefix_len[:bs].fill_(prompt_len)
         first = rt.acc_tokens[:bs, 0].tolist()
         fin = rt.finished[:bs].tolist()
@@ -189,9 +194,9 @@ class LookaheadPreTrainedModel(_Base):
         while active:
             k = len(active)
             share = rows_of(k)
-            key = ('batch', k, share, bl, tmode, kind, akey, id(trie._t))
+            key = ('batch', k, share, bl, tmode, kind, akey, id(trie._t), sample)
             ent = self._graph_entry(rt, key, lambda: self._capture_batch_step(rt, trie, k, share, bl, 2, tmode, kind,
-                                                                             accept))
+                                                                             accept, sample))
             ent['graphs'][0].replay()
             rt.replays += 1
             stream.synchronize()

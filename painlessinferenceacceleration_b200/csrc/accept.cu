@@ -19,6 +19,17 @@ namespace accept {
 
 __device__ __forceinline__ float bf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Gumbel noise for multinomial accept (pretrained_model.py:835-837: probs = softmax(scores); multinomial(probs, 1)):
+// arg-max_v (score_v + G_v) with independent standard Gumbel G_v is a draw from softmax(scores).  G_v is a pure function
+// of (seed, step counter, activation row, token), so every draft node of a step draws independently and a replayed
+// CUDA graph draws fresh numbers every step (the walk advances the counter).
+__device__ __forceinline__ float gumbel(unsigned seed, unsigned counter, unsigned row, unsigned tok) {
+  unsigned x = seed ^ (counter * 0x9E3779B1u) ^ (row * 0x85EBCA6Bu) ^ (tok * 0xC2B2AE35u);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  const float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+  return -__logf(-__logf(u));
+}
+
 constexpr int NT = 1024;
 
 // grid = batch * rows_per_slot activation rows (rows >= n of their slot idle).  dynamic smem: vocab bits (only when
@@ -26,7 +37,8 @@ constexpr int NT = 1024;
 __global__ void __launch_bounds__(NT) k_row_argmax(const __nv_bfloat16 *logits, int vocab, const int *ids,
                                                    const unsigned long long *mask, int mask_words, const int *d_n,
                                                    int rows_per_slot, const int *seq, int seq_stride,
-                                                   const int *d_seq_len, float penalty, int *row_tok) {
+                                                   const int *d_seq_len, float penalty, const unsigned *rng,
+                                                   int *row_tok) {
   extern __shared__ unsigned bits[];
   __shared__ float s_val[NT / 32];
   __shared__ int s_idx[NT / 32];
@@ -53,6 +65,8 @@ __global__ void __launch_bounds__(NT) k_row_argmax(const __nv_bfloat16 *logits, 
     __syncthreads();
   }
   const __nv_bfloat16 *lr = logits + (long long)row * vocab;
+  const bool sample = rng != nullptr;
+  const unsigned seed = sample ? rng[0] : 0u, counter = sample ? rng[1] : 0u;
   float best = -INFINITY;
   int best_i = 0x7fffffff;
   for (int v0 = tid * 8; v0 < vocab; v0 += NT * 8) {
@@ -68,6 +82,7 @@ __global__ void __launch_bounds__(NT) k_row_argmax(const __nv_bfloat16 *logits, 
       if (t >= vocab) break;
       float x = __bfloat162float(h[j]);
       if (pen && ((bits[t >> 5] >> (t & 31)) & 1u)) x = x < 0.f ? bf(x * penalty) : bf(x / penalty);
+      if (sample) x += gumbel(seed, counter, (unsigned)row, (unsigned)t);
       if (x > best) { best = x; best_i = t; }  // ascending t inside a thread keeps the first maximum
     }
   }
@@ -96,11 +111,12 @@ __global__ void __launch_bounds__(NT) k_row_argmax(const __nv_bfloat16 *logits, 
 __global__ void __launch_bounds__(128) k_accept_walk(pia_accept_config_t cfg, const int *row_tok, const int *ids,
                                                      const unsigned long long *mask, int mask_words, const int *d_n,
                                                      int rows_per_slot, int *seq, int seq_stride, int *d_seq_len,
-                                                     const int *d_max_length, int *acc_tokens, int *acc_count,
-                                                     int *acc_nodes, int *d_prefix, int *d_finished) {
+                                                     const int *d_max_length, unsigned *rng, int *acc_tokens,
+                                                     int *acc_count, int *acc_nodes, int *d_prefix, int *d_finished) {
   __shared__ int s_parent[128], s_ids[128], s_next;
   const int j = threadIdx.x, slot = blockIdx.x;
   const int n = d_n[slot];
+  if (rng != nullptr && slot == 0 && j == 0) rng[1] = rng[1] + 1u;  // k_row_argmax of this step has drawn its noise
   // idle slot, or a request that already finished (a step launched ahead of the host's stop check is a no-op)
   if (n <= 0 || d_finished[slot] != 0) { if (j == 0) acc_count[slot] = 0; return; }
   const long long r0 = (long long)slot * rows_per_slot;
@@ -188,7 +204,7 @@ extern "C" int64_t pia_accept_workspace_bytes(const pia_accept_config_t *cfg) {
 extern "C" int pia_accept(const pia_accept_config_t *cfg, const void *d_logits, const int32_t *d_ids,
                           const uint64_t *d_mask, int mask_words, int batch, int rows_per_slot, const int32_t *d_n,
                           int32_t *d_seq, int32_t *d_seq_len, int seq_stride, const int32_t *d_max_length,
-                          int32_t *d_accept_tokens, int32_t *d_accept_count, int32_t *d_accept_nodes,
+                          uint32_t *d_rng, int32_t *d_accept_tokens, int32_t *d_accept_count, int32_t *d_accept_nodes,
                           int32_t *d_prefix_len, int32_t *d_finished, void *d_workspace, void *stream) {
   PIA_REQUIRE(cfg && d_logits && d_ids && d_mask && d_n && d_seq && d_seq_len && d_accept_tokens && d_accept_count &&
                   d_accept_nodes && d_prefix_len && d_finished && d_workspace, "null argument");
@@ -209,10 +225,10 @@ extern "C" int pia_accept(const pia_accept_config_t *cfg, const void *d_logits, 
   k_row_argmax<<<batch * rows_per_slot, accept::NT, smem, s>>>((const __nv_bfloat16 *)d_logits, cfg->vocab, d_ids,
                                                               (const unsigned long long *)d_mask, mask_words, d_n,
                                                               rows_per_slot, d_seq, seq_stride, d_seq_len,
-                                                              cfg->repetition_penalty, row_tok);
+                                                              cfg->repetition_penalty, d_rng, row_tok);
   PIA_LAUNCH_CHECK();
   k_accept_walk<<<batch, 128, 0, s>>>(*cfg, row_tok, d_ids, (const unsigned long long *)d_mask, mask_words, d_n,
-                                      rows_per_slot, d_seq, seq_stride, d_seq_len, d_max_length, d_accept_tokens,
+                                      rows_per_slot, d_seq, seq_stride, d_seq_len, d_max_length, d_rng, d_accept_tokens,
                                       d_accept_count, d_accept_nodes, d_prefix_len, d_finished);
   PIA_LAUNCH_CHECK();
   return PIA_OK;

@@ -655,12 +655,16 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   a.plane0 = slots->kv_first_slot * p->cfg.n_layers * p->cfg.n_kv_heads;
   a.layer = layer; a.n_q_heads = p->cfg.n_q_heads; a.n_kv_heads = p->cfg.n_kv_heads; a.np = p->cfg.max_nodes;
   a.mask_words = p->mask_words; a.heads_per_cta = p->heads_per_cta; a.max_seq = p->cfg.max_seq;
-  a.n_split = p->n_split; a.tiles_per_cta = p->tiles_per_cta;
+  // KV splits per (slot, head group): one wave of CTAs over ALL slots - a batch of requests brings its own parallelism,
+  // so each cluster shrinks (8 slots x 32 head groups already cover the SMs without any split)
+  int ns = p->n_split / slots->batch;
+  if (ns < 1) ns = 1;
+  a.n_split = ns; a.tiles_per_cta = p->tiles_per_cta;
   a.out = (__nv_bfloat16 *)d_out; a.dbg = p->dbg;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
-  PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(p->n_split, p->n_groups, slots->batch), dim3(NTHREADS), SMEM_TOTAL, s,
-                                       (unsigned)p->n_split, p->map_k, p->map_v, a));
+  PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(ns, p->n_groups, slots->batch), dim3(NTHREADS), SMEM_TOTAL, s,
+                                       (unsigned)ns, p->map_k, p->map_v, a));
   count_launch();
   return PIA_OK;
 }

@@ -329,6 +329,6 @@ def test_loop_is_exact_at_baseline_shapes(name, layers, penalty, n_prompts, new)
                 edl_all += ref['edls'][1:]
                 moved += sum(1 for st in ref['steps'] if len(st['tokens']) > 1 and
                              st['logit_indices'] != list(range(len(st['tokens']))))
-    _diag('baseline_shape_parity', name=name, mean_edl_second_pass=sum(edl_all) / len(edl_all), max_edl=max(edl_all),
+    _diag('baseline_shape_parity', model=name, mean_edl_second_pass=sum(edl_all) / len(edl_all), max_edl=max(edl_all),
           non_contiguous_steps=moved)
     assert max(edl_all) > 2, 'the second pass never accepted a draft: the test did not exercise the accept path'

@@ -404,6 +404,48 @@ def test_batched_accept_walk_and_compaction():
     assert torch.equal(kc, k0) and torch.equal(vc, k0)  # chains are contiguous: nothing moves
 
 
+def test_multinomial_accept_draws_from_softmax():
+    """do_sample (pretrained_model.py:835-837: softmax of the processed scores, then multinomial): the Gumbel-max
+    draws of k_row_argmax must follow softmax(penalised logits) - chi-square over 6400 draws (64 rows x 100 steps, the
+    step counter advancing on the device), and differ from step to step"""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(3)
+    V, R = 24, 64
+    base = (torch.randn((V,), device=DEV) * 1.5).to(torch.bfloat16)
+    logits = base[None].repeat(R, 1).contiguous()
+    for penalty in (1.0, 1.3):
+        acc = ops.Accept(V, R, penalty, [2], 10 ** 6, DEV)
+        ids = torch.full((R,), 5, dtype=torch.int32, device=DEV)
+        mask = _mask_tensor(np.array([1 << i for i in range(R)], dtype=np.uint64) | np.uint64(1), R)  # stars: no paths
+        seq = torch.zeros((512,), dtype=torch.int32, device=DEV)
+        seq[:4] = torch.tensor([5, 7, 9, 5], dtype=torch.int32)
+        rng = torch.tensor([1234, 0], dtype=torch.int32, device=DEV)
+        counts = torch.zeros((V,), dtype=torch.float64)
+        draws = []
+        for step in range(100):
+            seq_len = torch.tensor([4], dtype=torch.int32, device=DEV)
+            prefix = torch.tensor([3], dtype=torch.int32, device=DEV)
+            fin = torch.zeros((1,), dtype=torch.int32, device=DEV)
+            at, ac, an = (torch.zeros((R,), dtype=torch.int32, device=DEV), torch.zeros((1,), dtype=torch.int32, device=DEV),
+                          torch.zeros((R,), dtype=torch.int32, device=DEV))
+            acc.run(logits, ids, mask, torch.tensor([R], dtype=torch.int32, device=DEV), seq, seq_len, at, ac, an,
+                    prefix, fin, rng=rng)
+            rt = acc.workspace[:R].cpu()
+            draws.append(rt.tolist())
+            counts += torch.bincount(rt.long(), minlength=V).double()
+        assert int(rng[1]) == 100 and draws[0] != draws[1]
+        sc = base.float().cpu()
+        if penalty != 1.0:  # RepetitionPenaltyLogitsProcessor on the context {5, 7, 9} (+ the path token 5)
+            for t in (5, 7, 9):
+                v = sc[t].to(torch.bfloat16).float()
+                sc[t] = (v * penalty if v < 0 else v / penalty).to(torch.bfloat16).float()
+        p = torch.softmax(sc.double(), 0)
+        exp = p * counts.sum()
+        keep = exp > 5
+        chi2 = float((((counts - exp) ** 2) / exp)[keep].sum())
+        assert chi2 < 2.0 * int(keep.sum()) + 20, (penalty, chi2, int(keep.sum()))
+
+
 @pytest.mark.parametrize('N,K,split', [(256, 128, 1), (12288, 4096, 1), (4096, 4096, 4), (22016, 4096, 1),
                                        (4096, 11008, 4), (32000, 4096, 1), (4096, 4096, 1), (1024, 14336, 7)])
 def test_gemm_weight_streaming(N, K, split):
