@@ -319,7 +319,7 @@ def run_ours(args):
             'per_rank_ms': res['per_rank_ms'],
             'e2e': {'value': e2e['tokens'] / (e2e['ms'] / 1e3), 'unit': 'tokens/s',
                     'h2d_bytes_per_step': PROMPT_LEN * 8,
-                    'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (4 + DL)),
+                    'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (5 + DL)),
                     'mean_accepted_len_per_step': e2e['mean_edl'], 'verify_steps': e2e['steps'],
                     'ms_per_verify_step': e2e['ms'] / max(e2e['steps'] / world, 1),
                     'same_trie_state_as_value': True, 'same_tokens_as_value': bool(same_tokens)},

@@ -117,12 +117,20 @@ int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32_t *d_qlen,
                  const int32_t *d_max_seq_length, int32_t *d_out_ids, uint64_t *d_out_mask, int32_t *d_out_n,
                  int32_t *d_out_sizes, int32_t *d_out_nsizes, int32_t *d_status, void *stream);
 
+/* Tree.squeeze :295-301 and Tree.reset_input_freq :320-333 of the single tree keyed by `token` (no touched-tree
+ * bookkeeping, no 1024-trees threshold: the per-tree methods callers may invoke directly) */
+int pia_trie_tree_squeeze(pia_trie_t *t, int token, void *stream);
+int pia_trie_tree_reset_input_freq(pia_trie_t *t, int token, int idx, void *stream);
 /* reset_input_freqs :566-570 ; squeeze_branch_counts :572-576 ; fresh :563-564 */
 int pia_trie_reset_input_freqs(pia_trie_t *t, int idx, void *stream);
 int pia_trie_squeeze_branch_counts(pia_trie_t *t, void *stream);
 int pia_trie_fresh(pia_trie_t *t, void *stream);
 /* Synchronises `stream`. */
 int pia_trie_stats(pia_trie_t *t, pia_trie_stats_t *h_out, void *stream);
+/* the sticky error bits (pia_trie_stats_t.error_flags: node / edge pool exhausted, carry buffer overflow, ...) copied to
+ * *d_out on the stream, capturable: the generation loops put it into their per-step record so that a trie that stopped
+ * learning (inserts dropped, lookahead_cache.py has no such failure mode) is reported instead of going unnoticed. */
+int pia_trie_copy_error_flags(pia_trie_t *t, int32_t *d_out, void *stream);
 /* per-tree counters Tree.n_node / n_output_node (lookahead_cache.py:29-30); -1 when the tree is absent. Synchronous. */
 int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_node, int64_t *h_n_output_node, void *stream);
 

@@ -62,10 +62,13 @@ SYMBOLS = {
     'pia_trie_stream_put': (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp]),
     'pia_trie_get': (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
+    'pia_trie_tree_squeeze': (C.c_int, [vp, C.c_int, vp]),
+    'pia_trie_tree_reset_input_freq': (C.c_int, [vp, C.c_int, C.c_int, vp]),
     'pia_trie_reset_input_freqs': (C.c_int, [vp, C.c_int, vp]),
     'pia_trie_squeeze_branch_counts': (C.c_int, [vp, vp]),
     'pia_trie_fresh': (C.c_int, [vp, vp]),
     'pia_trie_stats': (C.c_int, [vp, C.POINTER(TrieStats), vp]),
+    'pia_trie_copy_error_flags': (C.c_int, [vp, vp, vp]),
     'pia_trie_tree_counters': (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     'pia_trie_export_sizes': (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     'pia_trie_export': (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),

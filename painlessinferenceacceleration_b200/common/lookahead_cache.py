@@ -320,6 +320,10 @@ class LookaheadCache(object):
         with torch.cuda.device(self._t.device):
             L.check(self._t.lib.pia_trie_squeeze_branch_counts(self._t.h, self._t.stream()))
 
+    def copy_error_flags_device(self, d_out):
+        """sticky pool-exhaustion bits -> int32 device scalar, on the current stream (capturable)"""
+        L.check(self._t.lib.pia_trie_copy_error_flags(self._t.h, d_out.data_ptr(), self._t.stream()))
+
     def stats(self):
         s = L.TrieStats()
         with torch.cuda.device(self._t.device):
@@ -542,10 +546,17 @@ class Tree(object):
                                   L.GET_ONE, flags=L.GET_FIRST_ONLY)[0]
 
     def squeeze(self):
-        raise NotImplementedError('use LookaheadCache.squeeze_branch_counts()')
+        """reference :295-301"""
+        t = self._c._t
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_set_limits(t.h, int(self.max_node), int(self.max_output_node)))
+            L.check(t.lib.pia_trie_tree_squeeze(t.h, int(self.token_id), t.stream()))
 
     def reset_input_freq(self, idx):
-        raise NotImplementedError('use LookaheadCache.reset_input_freqs()')
+        """reference :320-333"""
+        t = self._c._t
+        with torch.cuda.device(t.device):
+            L.check(t.lib.pia_trie_tree_reset_input_freq(t.h, int(self.token_id), int(idx), t.stream()))
 
     @property
     def n_node(self):

@@ -31,6 +31,16 @@ from .lookahead_cache import LookaheadCache
 from .lookahead_generation_utils import GenerationMode, LookaheadDecoderOnlyOutput
 
 MAX_GRAPHS = 8  # captured step graphs kept per runtime (LRU)
+REC = 5         # header words of a step record: count, finished, n, status, trie error bits
+
+
+def warn_trie_errors(bits):
+    """the trie's sticky pool-exhaustion bits arrived with a step record: generation stays lossless, but inserts are
+    being dropped, i.e. the draft cache has stopped learning (the reference's Python dicts cannot run out)"""
+    import warnings
+    warnings.warn(f'LookaheadCache pools exhausted (error bits {bits:#x}: 1 nodes, 2 edges, 4 frontier, 8 stream buffer, '
+                  '16 histogram, 32 token id): new n-grams are no longer stored; call lookahead_cache.fresh() or build '
+                  'the cache with a larger node_capacity', RuntimeWarning, stacklevel=3)
 
 
 class _Bufs(object):
@@ -90,10 +100,11 @@ class _Runtime(object):
         self.acc_tokens = torch.zeros((S, R), **i32)
         self.acc_count = torch.zeros((S,), **i32)
         self.acc_nodes = torch.zeros((S, R), **i32)
-        # host-visible step record per slot: [count, finished, n, status, tokens...]; two pinned copies so that the
-        # step launched ahead does not overwrite the record the host is still reading
-        self.record = torch.zeros((S, 4 + R), **i32)
-        self.record_host = [torch.zeros((S, 4 + R), dtype=torch.int32).pin_memory() for _ in range(2)]
+        # host-visible step record per slot: [count, finished, n, status, trie error bits, tokens...]; two pinned copies
+        # so that the step launched ahead does not overwrite the record the host is still reading
+        self.record = torch.zeros((S, REC + R), **i32)
+        self.record_host = [torch.zeros((S, REC + R), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.trie_err = torch.zeros((1,), **i32)
         # activations of a decode step
         db = _Bufs(g, R, dev, with_logits=True)
         db.ids = self.ids
@@ -229,9 +240,8 @@ class LookaheadPreTrainedModel(nn.Module):
         if unknown:  # reference :1309-1317
             raise ValueError(f'The following `model_kwargs` are not used by the model: {unknown} (note: typos in the'
                              ' generate arguments will also show up in this list)')
-        if logits_processor or prefix_allowed_tokens_fn or assistant_model is not None:
-            raise NotImplementedError('custom logits processors / assistant models are outside the B200 hot path; '
-                                      'repetition_penalty is built in')
+        if prefix_allowed_tokens_fn or assistant_model is not None:
+            raise NotImplementedError('prefix_allowed_tokens_fn / assistant models are not on the lookahead path')
         if kwargs.get('num_beams', 1) != 1:
             raise NotImplementedError('beam search is not on the lookahead path')
         input_ids = kwargs.get('input_ids', inputs)
@@ -267,7 +277,11 @@ class LookaheadPreTrainedModel(nn.Module):
         crit_max = getattr(stopping_criteria, 'max_length', None) if stopping_criteria is not None else None
         if crit_max is not None:
             max_length = min(max_length, int(crit_max))
-        return self.lookahead_generation(input_ids, logits_processor=None, stopping_criteria=None, max_length=max_length,
+        # caller-supplied processors / criteria (reference :349-360): MaxLengthCriteria is the device-side max_length;
+        # anything else runs on the host path of the loop, one processor call per accepted token like the reference
+        extra_criteria = [c for c in (stopping_criteria or []) if type(c).__name__ != 'MaxLengthCriteria']
+        return self.lookahead_generation(input_ids, logits_processor=list(logits_processor or []) or None,
+                                         stopping_criteria=extra_criteria or None, max_length=max_length,
                                          pad_token_id=pad, eos_token_id=eos,
                                          output_scores=opt('output_scores', False),
                                          return_dict_in_generate=opt('return_dict_in_generate', False),
@@ -311,11 +325,13 @@ class LookaheadPreTrainedModel(nn.Module):
             if use_trie:  # :1203
                 trie.stream_put_device(rt.acc_tokens, rt.max_nodes, rt.acc_count, branch_length=self._put_bl,
                                        final=False, idx=0)
+                trie.copy_error_flags_device(rt.trie_err)
             rt.record[0, 0:1] = rt.acc_count
             rt.record[0, 1:2] = rt.finished
             rt.record[0, 2:3] = rt.n
             rt.record[0, 3:4] = rt.status
-            rt.record[0, 4:] = rt.acc_tokens[0]
+            rt.record[0, 4:5] = rt.trie_err
+            rt.record[0, REC:] = rt.acc_tokens[0]
 
         graphs = []
         l0 = ops.launch_count()
@@ -399,7 +415,14 @@ class LookaheadPreTrainedModel(nn.Module):
         if accept is None:  # referenced by captured graphs: lives as long as the runtime
             accept = ops.Accept(self.geometry()['vocab'], max_nodes, repetition_penalty, eos_token_id, max_length, dev)
             rt.accepts[akey] = accept
-        first = self._prefill(rt, prompt_len, accept, sample)
+        if logits_processor:   # the processors also see the prefill logits (:786)
+            self._prefill_logits(rt, prompt_len)
+            first = self._host_pick(logits_processor, input_ids.to(dev), rt.logits[0:1], sample)
+            rt.seq[0, prompt_len] = first
+            rt.seq_len.fill_(prompt_len + 1)
+            rt.prefix_len.fill_(prompt_len)
+        else:
+            first = self._prefill(rt, prompt_len, accept, sample)
         new_tokens = [first]
         decoding_kwargs['dls'].append(1)  # the prefill step counts as one fed token (:797-798)
         decoding_kwargs['edls'].append(1)
@@ -416,6 +439,11 @@ class LookaheadPreTrainedModel(nn.Module):
         min_out = max(dl // 2, 1)  # :710
         key = (use_trie, dl, bl, mql, tmode, fmt, akey, id(trie._t), sample)
         stream = torch.cuda.current_stream()
+        if (logits_processor or stopping_criteria) and not finished:
+            finished = self._host_accept_loop(rt, trie, use_trie, dl, bl, mql, min_out, tmode,
+                                              'hier' if fmt == 'hier' else 'one', logits_processor or [],
+                                              stopping_criteria or [], sample, eos_token_id, max_length, new_tokens,
+                                              decoding_kwargs, streamer, input_ids)
         if not finished:
             ent = self._graph_entry(rt, key, lambda: self._capture_step(
                 rt, trie, use_trie, dl, bl, mql, min_out, tmode, 'hier' if fmt == 'hier' else 'one', accept, sample))
@@ -438,7 +466,10 @@ class LookaheadPreTrainedModel(nn.Module):
                 if status != 0:
                     from .. import _lib as L
                     L.check(status)
-                toks = rec[4:4 + count].tolist()
+                if int(rec[4]) != 0 and not getattr(trie, '_warned_pool', False):
+                    trie._warned_pool = True
+                    warn_trie_errors(int(rec[4]))
+                toks = rec[REC:REC + count].tolist()
                 new_tokens.extend(toks)
                 decoding_kwargs['dls'].append(n)
                 decoding_kwargs['edls'].append(count)
@@ -465,6 +496,84 @@ class LookaheadPreTrainedModel(nn.Module):
             kw = {k_: decoding_kwargs[k_] for k_ in ('dls', 'edls', 'fts', 'qts')}
             return LookaheadDecoderOnlyOutput(sequences=out_ids, scores=() if output_scores else None, kwargs=kw)
         return out_ids
+
+    # ------------------------------------------------------------------ host accept path (custom processors / criteria)
+    @staticmethod
+    def _host_pick(processors, ids, logits_row, sample):
+        """next_tokens_scores = logits_processor(update_input_ids, next_token_logits); arg-max / multinomial (:834-839)"""
+        scores = logits_row
+        for proc in processors:
+            scores = proc(ids, scores)
+        if sample:
+            return int(torch.multinomial(torch.softmax(scores, dim=-1), num_samples=1)[0, 0])
+        return int(torch.argmax(scores, dim=-1)[0])
+
+    def _host_accept_loop(self, rt, trie, use_trie, dl, bl, mql, min_out, tmode, kind, processors, criteria, sample,
+                          eos_token_id, max_length, new_tokens, decoding_kwargs, streamer, input_ids):
+        """The loop for caller-supplied logits processors / stopping criteria (reference :349-360, :786, :834, :1225):
+        arbitrary Python callables cannot run inside the captured step, so the accept walk runs on the host exactly like
+        the reference's (:827-860: one processor call + one device->host sync per accepted token) while draft, verify
+        forward, KV compaction and trie update stay the device kernels.  Returns True (the request finished here)."""
+        dev = rt.device
+        draft = dict(ids=rt.ids, mask=rt.mask, n=rt.n, sizes=rt.sizes, nsizes=rt.nsizes, status=rt.status)
+        seq = input_ids[0].tolist() + list(new_tokens)
+        ts = time.time()
+        while True:
+            if use_trie:
+                trie.get_device(rt.seq, rt.seq_len, dl, bl, max_query_length=mql, min_input_size=0,
+                                min_output_size=min_out, mode=tmode, idx=0, kind=kind, max_seq_length=1,
+                                d_max_seq_length=rt.max_length, out=draft)
+            else:
+                rt.ids[0:1] = rt.seq[0].gather(0, (rt.seq_len - 1).long())
+                rt.n.fill_(1)
+                rt.mask[0, 0:1].fill_(1)
+            self._verify_layers(rt)
+            n = int(rt.n[0])
+            ids = rt.ids[:n].tolist()
+            rows = rt.mask[:n].cpu().numpy().view(np.uint64)
+            parent = [-1] * n
+            for j in range(1, n):   # nearest ancestor = highest set bit below j (DFS pre-order)
+                below = [k for k in range(j) if (int(rows[j, k >> 6]) >> (k & 63)) & 1]
+                parent[j] = below[-1] if below else -1
+            cur, toks, nodes = 0, [], []
+            ctx = torch.tensor([seq], dtype=torch.long, device=dev)
+            while True:
+                t = self._host_pick(processors, ctx, rt.logits[cur:cur + 1], sample)
+                toks.append(t)
+                nodes.append(cur)
+                ctx = torch.cat([ctx, torch.tensor([[t]], dtype=torch.long, device=dev)], dim=1)
+                nxt = [j for j in range(1, n) if parent[j] == cur and ids[j] == t]
+                if not nxt or len(toks) >= n:
+                    break
+                cur = nxt[0]
+            count = len(toks)
+            L0 = len(seq)
+            seq.extend(toks)
+            rt.seq[0, L0:L0 + count] = torch.tensor(toks, dtype=torch.int32, device=dev)
+            rt.seq_len.fill_(L0 + count)
+            rt.acc_tokens[0, :count] = torch.tensor(toks, dtype=torch.int32, device=dev)
+            rt.acc_nodes[0, :count] = torch.tensor(nodes, dtype=torch.int32, device=dev)
+            rt.acc_count.fill_(count)
+            rt.prefix_len.fill_(L0 - 1 + count)
+            ops.kv_compact(rt.k_cache, rt.v_cache, rt.acc_nodes, rt.acc_count, rt.prefix_len, batch=1)
+            if use_trie:
+                trie.stream_put_device(rt.acc_tokens, rt.max_nodes, rt.acc_count, branch_length=self._put_bl,
+                                       final=False, idx=0)
+            new_tokens.extend(toks)
+            decoding_kwargs['dls'].append(n)
+            decoding_kwargs['edls'].append(count)
+            decoding_kwargs['qts'].append(0.0)
+            if streamer is not None:
+                streamer.put(np.array([toks]))
+            fin = len(seq) >= max_length or (eos_token_id is not None and any(e in toks for e in eos_token_id))
+            full = torch.tensor([seq], dtype=torch.long, device=dev)
+            for crit in criteria:   # StoppingCriteriaList semantics: any criterion may stop (:1225)
+                fin = fin or bool(torch.as_tensor(crit(full, None)).any())
+            te = time.time()
+            decoding_kwargs['fts'].append(te - ts)
+            ts = te
+            if fin:
+                return True
 
     def _prefill_kv(self, rt, prompt_len, slot=0):
         """prompt tokens rt.seq[slot, :prompt_len] -> KV rows [0, prompt_len) of that slot's cache; leaves the last

@@ -29,6 +29,7 @@ import torch
 from . import ops
 from .lookahead_cache import LookaheadCache
 from .lookahead_generation_utils import GenerationMode, LookaheadDecoderOnlyOutput
+from .pretrained_model import REC, warn_trie_errors
 from .pretrained_model import LookaheadPreTrainedModel as _Base
 
 
@@ -63,11 +64,13 @@ class LookaheadPreTrainedModel(_Base):
             for s in range(k):  # :1243-1248; the request idx of a slot is read on the device
                 trie.stream_put_device(rt.acc_tokens[s], rt.max_nodes, rt.acc_count[s:s + 1],
                                        branch_length=self._put_bl, final=False, idx=0, d_idx=rt.trie_idx[s:s + 1])
+            trie.copy_error_flags_device(rt.trie_err)
             rt.record[:k, 0] = rt.acc_count[:k]
             rt.record[:k, 1] = rt.finished[:k]
             rt.record[:k, 2] = rt.n[:k]
             rt.record[:k, 3] = rt.status[:k]
-            rt.record[:k, 4:] = rt.acc_tokens[:k]
+            rt.record[:k, 4] = rt.trie_err
+            rt.record[:k, REC:] = rt.acc_tokens[:k]
             rt.record_host[0].copy_(rt.record, non_blocking=True)
 
         g = torch.cuda.CUDAGraph()
@@ -208,7 +211,10 @@ class LookaheadPreTrainedModel(_Base):
                 if status != 0:
                     from .. import _lib as L
                     L.check(status)
-                toks = rec[s, 4:4 + count].tolist()
+                if int(rec[s, 4]) != 0 and not getattr(trie, '_warned_pool', False):
+                    trie._warned_pool = True
+                    warn_trie_errors(int(rec[s, 4]))
+                toks = rec[s, REC:REC + count].tolist()
                 seqs[active[s]].extend(toks)
                 decoding_kwargs['dls'].append(widest)
                 decoding_kwargs['edls'].append(count)

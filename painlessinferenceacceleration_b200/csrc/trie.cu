@@ -978,16 +978,17 @@ __global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
 // ---------------------------------------------------------------------------------------------------
 // reset_input_freqs (:320-333, :566-570)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx) {
+// single_key >= 0: Tree.reset_input_freq(idx) of that one tree (:320-333), the touched-tree list is left alone
+__global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx, int single_key) {
   __shared__ BfsShared sh;
   int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
   int *fr1 = fr0 + D.fr_cap;
   unsigned long long nv = 0, ne = 0;
-  const int n = D.hdr->n_updin;
+  const int n = single_key >= 0 ? 1 : D.hdr->n_updin;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    const int key = D.updin_list[i];
+    const int key = single_key >= 0 ? single_key : D.updin_list[i];
     const int root = D.root_of[key];
-    if (threadIdx.x == 0) { sh.err = 0; D.tree_flags[key] &= ~FLAG_UPDIN; }
+    if (threadIdx.x == 0) { sh.err = 0; if (single_key < 0) D.tree_flags[key] &= ~FLAG_UPDIN; }
     __syncthreads();
     if (root < 0) continue;
     auto visit = [&](int id, const Node &nd) -> bool {
@@ -1006,18 +1007,19 @@ __global__ void k_reset_finish(Dev D) { D.hdr->n_updin = 0; }
 // ---------------------------------------------------------------------------------------------------
 // squeeze_branch_counts (:295-318, :572-576): one CTA per touched tree, one warp per surviving parent
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_squeeze(Dev D) {
+// single_key >= 0: Tree.squeeze() of that one tree (:295-301), no 1024-trees threshold, lists left alone
+__global__ void __launch_bounds__(NT) k_squeeze(Dev D, int single_key) {
   __shared__ int s_next, s_count, s_err;
   const int tid = threadIdx.x, lane = lane_id(), wid = warp_id();
   int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
   int *fr1 = fr0 + D.fr_cap;
-  const int n_listed = D.hdr->n_upd;
-  if (n_listed + D.hdr->n_upd_stale < 1024) return;
+  const int n_listed = single_key >= 0 ? 1 : D.hdr->n_upd;
+  if (single_key < 0 && n_listed + D.hdr->n_upd_stale < 1024) return;
   for (int i = blockIdx.x; i < n_listed; i += gridDim.x) {
-    const int key = D.upd_list[i];
+    const int key = single_key >= 0 ? single_key : D.upd_list[i];
     const int root = D.root_of[key];
     __syncthreads();
-    if (tid == 0) { s_next = 0; s_count = 0; s_err = 0; D.tree_flags[key] &= ~FLAG_UPD; }
+    if (tid == 0) { s_next = 0; s_count = 0; s_err = 0; if (single_key < 0) D.tree_flags[key] &= ~FLAG_UPD; }
     __syncthreads();
     if (root < 0) continue;
     if (!(D.tree_n_node[key] > D.hdr->max_node || D.tree_n_out[key] > D.hdr->max_out)) continue;
@@ -1224,7 +1226,7 @@ extern "C" int pia_trie_set_limits(pia_trie_t *t, int max_node, int max_output_n
 
 static int launch_reset(pia_trie *t, int idx, cudaStream_t s) {
   const int grid = t->dev.max_resident < 4 * t->n_sm ? t->dev.max_resident : 4 * t->n_sm;
-  k_reset_input<<<grid, NT, 0, s>>>(t->dev, idx);
+  k_reset_input<<<grid, NT, 0, s>>>(t->dev, idx, -1);
   PIA_LAUNCH_CHECK();
   k_reset_finish<<<1, 1, 0, s>>>(t->dev);
   PIA_LAUNCH_CHECK();
@@ -1232,7 +1234,7 @@ static int launch_reset(pia_trie *t, int idx, cudaStream_t s) {
 }
 static int launch_squeeze(pia_trie *t, cudaStream_t s) {
   const int grid = t->dev.max_resident < 4 * t->n_sm ? t->dev.max_resident : 4 * t->n_sm;
-  k_squeeze<<<grid, NT, 0, s>>>(t->dev);
+  k_squeeze<<<grid, NT, 0, s>>>(t->dev, -1);
   PIA_LAUNCH_CHECK();
   k_squeeze_finish<<<1, 1, 0, s>>>(t->dev);
   PIA_LAUNCH_CHECK();
@@ -1315,6 +1317,30 @@ extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32
   cudaStream_t s = (cudaStream_t)stream;
   if (decoding_length <= 64 && branch_length <= 16) k_get<64, 16><<<grid, NT, sizeof(GetSmem<64, 16>), s>>>(t->dev, P);
   else k_get<128, 32><<<grid, NT, sizeof(GetSmem<128, 32>), s>>>(t->dev, P);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+__global__ void k_copy_err(pia::trie::Dev D, int *out) { *out = D.hdr->err; }
+
+extern "C" int pia_trie_copy_error_flags(pia_trie_t *t, int32_t *d_out, void *stream) {
+  PIA_REQUIRE(t && d_out, "null argument");
+  k_copy_err<<<1, 1, 0, (cudaStream_t)stream>>>(t->dev, d_out);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+
+// Tree.squeeze (:295-301) / Tree.reset_input_freq (:320-333) of the one tree keyed by `token`
+extern "C" int pia_trie_tree_squeeze(pia_trie_t *t, int token, void *stream) {
+  PIA_REQUIRE(t && token >= 0 && token < t->cfg.vocab_capacity, "bad tree token");
+  k_squeeze<<<1, NT, 0, (cudaStream_t)stream>>>(t->dev, token);
+  PIA_LAUNCH_CHECK();
+  return PIA_OK;
+}
+extern "C" int pia_trie_tree_reset_input_freq(pia_trie_t *t, int token, int idx, void *stream) {
+  PIA_REQUIRE(t && token >= 0 && token < t->cfg.vocab_capacity, "bad tree token");
+  PIA_REQUIRE(idx >= 0 && idx < t->cfg.n_input_slots, "bad idx");
+  k_reset_input<<<1, NT, 0, (cudaStream_t)stream>>>(t->dev, idx, token);
   PIA_LAUNCH_CHECK();
   return PIA_OK;
 }

@@ -112,7 +112,7 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             shards = (torch.load(f, map_location='cpu') for f in sorted(glob.glob(os.path.join(path, 'pytorch_model*.bin'))))
         with torch.no_grad():
             for sd in shards:
-                for k, v in sd.items():
+                for k, v in model._convert_checkpoint_keys(sd).items():
                     if k in own:
                         own[k].copy_(v.to(torch_dtype))
                         seen.add(k)
@@ -124,6 +124,10 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         if missing:
             raise RuntimeError(f'checkpoint is missing {len(missing)} tensors, e.g. {missing[:4]}')
         return model
+
+    def _convert_checkpoint_keys(self, sd):
+        """checkpoint tensor names -> this module tree's names (identity for Llama / Mistral)"""
+        return sd
 
     def fuse(self):
         """QKV and gate/up weights into single GEMM operands; the HF-named parameters become views of them"""
@@ -158,10 +162,31 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         then cast to the model dtype"""
         c = self.config
         hd = c.hidden_size // c.num_attention_heads
-        theta = float(getattr(c, 'rope_theta', None) or (getattr(c, 'rope_parameters', None) or {}).get('rope_theta', 10000.0))
+        rp = getattr(c, 'rope_parameters', None) or {}
+        theta = float(getattr(c, 'rope_theta', None) or rp.get('rope_theta', 10000.0))
+        scaling = getattr(c, 'rope_scaling', None) or ({k: v for k, v in rp.items() if k != 'rope_theta'} if rp else None)
+        rtype = (scaling or {}).get('rope_type', (scaling or {}).get('type', 'default')) if scaling else 'default'
         dev = self.device
         inv_freq = 1.0 / (theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float().to(dev) / hd))
         pos = torch.arange(max_pos, device=dev).float()
+        if rtype in (None, 'default'):
+            pass
+        elif rtype == 'linear':      # LlamaLinearScalingRotaryEmbedding (reference :130-146): t / factor
+            pos = pos / float(scaling['factor'])
+        elif rtype == 'dynamic':     # LlamaDynamicNTKScalingRotaryEmbedding (reference :149-169): base grows with seq_len
+            factor, mpe = float(scaling['factor']), int(c.max_position_embeddings)
+            if max_pos > mpe:
+                base = theta * ((factor * max_pos / mpe) - (factor - 1)) ** (hd / (hd - 2))
+                inv_freq = 1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.int64).float().to(dev) / hd))
+        else:                        # the reference raises on unknown types as well (:241 `Unknown RoPE scaling type`)
+            raise ValueError(f'Unknown RoPE scaling type {rtype}')
+        window = getattr(c, 'sliding_window', None)
+        if window is not None and max_pos > int(window) + 8:
+            # the reference ignores the window on the lookahead branch (mistral/modeling_mistral.py:979-982, SURVEY A.2-15);
+            # so does this kernel - say so instead of silently diverging from sliding-window checkpoints
+            import warnings
+            warnings.warn(f'sliding_window={window} is ignored on the lookahead path (as in the reference); contexts '
+                          f'beyond it attend to the full prefix')
         freqs = pos[:, None] * inv_freq[None, :]
         return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
 

@@ -54,6 +54,33 @@ class MixtralForCausalLM(LlamaForCausalLM):
     def _fuse_mlp(self, layer):
         pass  # experts are stored fused ([E, 2I, H]) already
 
+    def _convert_checkpoint_keys(self, sd):
+        """published Mixtral checkpoints (and the reference, mixtral/modeling_mixtral.py:692-759) name the MoE block
+        `block_sparse_moe` with per-expert `experts.N.w1 / w3 / w2` Linear weights; this module tree keeps the experts
+        stacked: gate_up_proj[e] = [w1; w3] ([2I, H]), down_proj[e] = w2 ([H, I]), router = `mlp.gate.weight`.  Tensors
+        of one layer's experts may arrive in different shards: partial stacks are kept until complete."""
+        import re
+        out = {}
+        pend = self.__dict__.setdefault('_pending_experts', {})
+        E = self.config.num_local_experts
+        pat = re.compile(r'^(model\.layers\.\d+)\.block_sparse_moe\.experts\.(\d+)\.(w1|w2|w3)\.weight$')
+        for k, v in sd.items():
+            m = pat.match(k)
+            if m:
+                pend.setdefault(m.group(1), {})[(int(m.group(2)), m.group(3))] = v
+            elif '.block_sparse_moe.gate.weight' in k:
+                out[k.replace('.block_sparse_moe.gate.weight', '.mlp.gate.weight')] = v
+            else:
+                out[k] = v
+        for layer in list(pend):
+            parts = pend[layer]
+            if len(parts) == 3 * E:
+                out[layer + '.mlp.experts.gate_up_proj'] = torch.stack(
+                    [torch.cat([parts[(e, 'w1')], parts[(e, 'w3')]], dim=0) for e in range(E)], dim=0)
+                out[layer + '.mlp.experts.down_proj'] = torch.stack([parts[(e, 'w2')] for e in range(E)], dim=0)
+                del pend[layer]
+        return out
+
     def geometry(self):
         g = super().geometry()
         g['n_experts'] = self.config.num_local_experts

@@ -76,3 +76,33 @@ def replay(cache, ops, stats_fn=None, tag=''):
         else:
             raise ValueError(name)
     return checked
+
+
+def replay_tree_methods(make_tree):
+    """tests/golden/trie_tree_methods.json (recorded from the live reference Tree) against `make_tree(token, max_node,
+    max_output_node)`; returns the number of checked results"""
+    checked = 0
+    for case in load('trie_tree_methods.json'):
+        t = make_tree(case['token'], case['max_node'], case['max_output_node'])
+        for k, op in enumerate(case['ops']):
+            if op[0] == 'put':
+                t.put(list(op[1]), mode=op[2], idx=op[3])
+            elif op[0] == 'get':
+                _, q, mode, idx, want = op
+                try:
+                    ids, m, sizes = t.get(list(q), max_size=16, max_length=6, min_input_size=0, min_output_size=4, mode=mode,
+                                          idx=idx)
+                    got = {'ids': [int(x) for x in ids], 'mask': mask_rows(m), 'sizes': [int(x) for x in sizes]}
+                except IndexError:
+                    got = {'err': 'IndexError'}
+                assert got == want, f'op#{k} {op[:4]}\n got={got}\nwant={want}'
+                checked += 1
+            elif op[0] == 'squeeze':
+                t.squeeze()
+                assert (int(t.n_node), int(t.n_output_node)) == (op[1], op[2]), f'op#{k} squeeze counters'
+                checked += 1
+            elif op[0] == 'reset_input_freq':
+                t.reset_input_freq(op[1])
+            elif op[0] == 'counters':
+                assert (int(t.n_node), int(t.n_output_node)) == (op[1], op[2]), f'op#{k} counters'
+    return checked

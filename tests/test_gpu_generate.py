@@ -332,3 +332,46 @@ def test_loop_is_exact_at_baseline_shapes(name, layers, penalty, n_prompts, new)
     _diag('baseline_shape_parity', model=name, mean_edl_second_pass=sum(edl_all) / len(edl_all), max_edl=max(edl_all),
           non_contiguous_steps=moved)
     assert max(edl_all) > 2, 'the second pass never accepted a draft: the test did not exercise the accept path'
+
+
+def test_caller_supplied_logits_processor_and_stopping_criteria():
+    """generate(logits_processor=..., stopping_criteria=...) (reference :349-360, :786, :834, :1225): the processors
+    run on the host path of the loop.  An explicit RepetitionPenaltyLogitsProcessor must reproduce the built-in
+    repetition_penalty run token for token (same kernels, same logits; dls / edls too), and a custom criterion stops the
+    request at the step where it first fires."""
+    from transformers import RepetitionPenaltyLogitsProcessor, StoppingCriteria
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    hf, ours = _pair('mistral', seed=14)
+    ps = [p.to(DEV) for p in prompts(93, 2, 40, 200)]
+    dk = {'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8}
+    runs = {}
+    for mode in ('builtin', 'processor'):
+        ours.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
+        outs = []
+        for rep in range(2):
+            for p in ps:
+                kw = dict(repetition_penalty=1.1) if mode == 'builtin' else \
+                    dict(logits_processor=[RepetitionPenaltyLogitsProcessor(1.1)])
+                o = ours.generate(input_ids=p, max_new_tokens=40, eos_token_id=2, decoding_kwargs=dict(dk),
+                                  return_dict_in_generate=True, **kw)
+                outs.append((o.sequences[0].tolist(), o.kwargs['dls'], o.kwargs['edls']))
+        runs[mode] = outs
+    assert runs['builtin'] == runs['processor']
+    assert max(e for _, _, ed in runs['processor'] for e in ed) > 1
+
+    class StopOnToken(StoppingCriteria):
+        def __init__(self, tok):
+            self.tok = tok
+
+        def __call__(self, input_ids, scores, **kw):
+            return torch.tensor([bool((input_ids[0, 40:] == self.tok).any())])
+
+    full = runs['builtin'][0][0]
+    tok = full[40 + 9]
+    ours.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
+    o = ours.generate(input_ids=ps[0], max_new_tokens=40, eos_token_id=2, repetition_penalty=1.1,
+                      stopping_criteria=[StopOnToken(tok)], decoding_kwargs=dict(dk), return_dict_in_generate=True)
+    got = o.sequences[0].tolist()
+    assert got == full[:len(got)] and tok in got[40:] and len(got) < len(full)
+    first = 40 + full[40:].index(tok)
+    assert len(got) > first and sum(o.kwargs['edls']) == len(got) - 40

@@ -153,3 +153,11 @@ def test_load_mem_of_a_reference_file_and_save_roundtrip(tmp_path):
         b = d.hier_get(g['q'], decoding_length=64, branch_length=8, min_output_size=32)
         assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2]
     assert c.stats()['n_trees'] == d.stats()['n_trees']
+
+
+def test_tree_methods_against_the_reference_tree():
+    """the product's Tree (one-tree device trie): put / get / squeeze / reset_input_freq / n_node / n_output_node against
+    the op stream recorded from the live reference Tree (tests/golden/gen_tree_methods_golden.py)"""
+    from painlessinferenceacceleration_b200.common.lookahead_cache import Tree
+    from tests.replay import replay_tree_methods
+    assert replay_tree_methods(lambda tok, mn, mo: Tree(tok, max_node=mn, max_output_node=mo)) > 40

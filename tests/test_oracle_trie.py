@@ -53,3 +53,10 @@ def test_recorded_streams(name):
     cache = R.make_cache(OracleLookaheadCache, fx['ctor'])
     n = R.replay(cache, fx['ops'], stats_fn=_stats, tag=name)
     assert n > 0
+
+
+def test_tree_methods_against_the_reference_tree():
+    """Tree.put / get / squeeze / reset_input_freq / counters (lookahead_cache.py:24-333) recorded from the live reference"""
+    from oracle.trie import OracleTree
+    from tests.replay import replay_tree_methods
+    assert replay_tree_methods(lambda tok, mn, mo: OracleTree(tok, max_node=mn, max_output_node=mo)) > 40
