@@ -38,7 +38,7 @@ MODELS = {
 }
 METRIC_NAMES = {'llama2-7b': 'Llama-2-7B', 'mistral-7b': 'Mistral-7B', 'mixtral-8x7b': 'Mixtral-8x7B', 'tiny': 'tiny'}
 PROMPT_LEN, NEW_TOKENS, DL, BL = 256, 256, 64, 8
-EMBED_STD = float(os.environ.get('PIA_BENCH_EMBED_STD', '1.0'))   # signal of the successor chain vs the layers' noise
+EMBED_STD = float(os.environ.get("PIA_BENCH_EMBED_STD", "5.5"))   # signal of the successor chain vs the layers' noise
 LM_SCALE = 0.25
 CPU_NEW_TOKENS = 16   # generated tokens per request of the bounded CPU samples (fixed, so the sample is reproducible)
 

@@ -229,6 +229,10 @@ int pia_gemm_plan_create_grouped(const void *d_w, int groups, int N, int K, cons
                                  pia_gemm_plan_t **out);
 int pia_gemm_plan_destroy(pia_gemm_plan_t *g);
 int pia_gemm_plan_splits(const pia_gemm_plan_t *g);
+/* on == 0: launch this plan without the programmatic-dependent-launch attribute, i.e. as a plain kernel boundary that
+ * neither starts before its predecessor has finished nor lets its successor start early (how a library GEMM behaves in
+ * the chain); default on. */
+int pia_gemm_plan_set_pdl(pia_gemm_plan_t *g, int on);
 /* fused SiLU(gate) * up epilogue (modeling_llama.py:185-186): the weight must be laid out so that every 128-row tile
  * holds 64 gate rows followed by the 64 up rows of the same columns; d_out of pia_gemm_run is then [rows, N/2]. */
 int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on);

@@ -84,6 +84,7 @@ SYMBOLS = {
     'pia_gemm_plan_create_grouped': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.POINTER(vp)]),
     'pia_gemm_plan_destroy': (C.c_int, [vp]),
     'pia_gemm_plan_splits': (C.c_int, [vp]),
+    'pia_gemm_plan_set_pdl': (C.c_int, [vp, C.c_int]),
     'pia_gemm_plan_set_silu': (C.c_int, [vp, C.c_int]),
     'pia_gemm_run': (C.c_int, [vp, C.c_int, vp, vp]),
     'pia_rope_kv_append': (C.c_int, [vp, vp, C.c_int, C.POINTER(Slots), C.c_int, C.c_int, C.c_int, vp, vp,

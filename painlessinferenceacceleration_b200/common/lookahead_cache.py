@@ -560,8 +560,8 @@ class Tree(object):
 
     @property
     def n_node(self):
-        return self._c.tree_counters(self.token_id)[0]
+        return max(self._c.tree_counters(self.token_id)[0], 0)   # an empty Tree counts 0 nodes (reference :29)
 
     @property
     def n_output_node(self):
-        return self._c.tree_counters(self.token_id)[1]
+        return max(self._c.tree_counters(self.token_id)[1], 0)

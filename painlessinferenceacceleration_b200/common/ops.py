@@ -88,6 +88,10 @@ class Gemm(object):
         self.out = torch.empty((G, 64, N), dtype=torch.bfloat16, device=weight.device)
         return self
 
+    def set_pdl(self, on=True):
+        L.check(self.lib.pia_gemm_plan_set_pdl(self.h, int(on)))
+        return self
+
     def set_silu(self, on=True):
         L.check(self.lib.pia_gemm_plan_set_silu(self.h, int(on)))
         return self

@@ -415,7 +415,13 @@ class LookaheadPreTrainedModel(nn.Module):
         if accept is None:  # referenced by captured graphs: lives as long as the runtime
             accept = ops.Accept(self.geometry()['vocab'], max_nodes, repetition_penalty, eos_token_id, max_length, dev)
             rt.accepts[akey] = accept
-        if logits_processor:   # the processors also see the prefill logits (:786)
+        host_path = bool(logits_processor or stopping_criteria)
+        if host_path:          # built-in penalty + the caller's processors, in generate()'s order (:349-355)
+            logits_processor = list(logits_processor or [])
+            if float(repetition_penalty) != 1.0:
+                from transformers import RepetitionPenaltyLogitsProcessor
+                logits_processor.insert(0, RepetitionPenaltyLogitsProcessor(penalty=float(repetition_penalty)))
+        if host_path:          # the processors also see the prefill logits (:786)
             self._prefill_logits(rt, prompt_len)
             first = self._host_pick(logits_processor, input_ids.to(dev), rt.logits[0:1], sample)
             rt.seq[0, prompt_len] = first
@@ -439,7 +445,7 @@ class LookaheadPreTrainedModel(nn.Module):
         min_out = max(dl // 2, 1)  # :710
         key = (use_trie, dl, bl, mql, tmode, fmt, akey, id(trie._t), sample)
         stream = torch.cuda.current_stream()
-        if (logits_processor or stopping_criteria) and not finished:
+        if host_path and not finished:
             finished = self._host_accept_loop(rt, trie, use_trie, dl, bl, mql, min_out, tmode,
                                               'hier' if fmt == 'hier' else 'one', logits_processor or [],
                                               stopping_criteria or [], sample, eos_token_id, max_length, new_tokens,

@@ -9,6 +9,7 @@ namespace pia {
 static thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 
+thread_local int g_pdl_off = 0;
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char *e = getenv("PIA_PDL"); v = (e && e[0] == '0') ? 0 : 1; }

@@ -121,6 +121,7 @@ struct Params {
   long long out_group_stride;                // elements between the groups' [rows_cap, N] outputs
   int cluster;              // > 1: the K splits of a tile are one thread-block cluster and reduce through DSMEM (bf16 out)
   int silu;                 // 1: tile rows are 64 gate rows + 64 up rows of the same columns -> out = silu(g) * u
+  int no_pdl;               // 1: plain kernel boundary - do not let the successor start early either
   __nv_bfloat16 *out_bf16;  // [rows_cap, N]  (or [rows_cap, N/2] with silu)   (n_split == 1)
   float *out_f32;           // [n_split, TOK, N] slices  (n_split > 1)
 };
@@ -158,7 +159,7 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  pdl_launch_dependents();
+  if (!p.no_pdl) pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -497,6 +498,7 @@ struct pia_gemm_plan {
   CUtensorMap map_w, map_x;
   Params p;
   int nstage;
+  int no_pdl;  // 1: launched without the programmatic-dependent-launch attribute (a plain kernel boundary, like cuBLAS)
   // stream-K mode
   int stream_k, sk_grid;
   SkParams sk;
@@ -593,7 +595,7 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_ws<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(8));
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
-  g->stream_k = 0;
+  g->stream_k = 0; g->no_pdl = 0;
   if (rc == PIA_OK && want_stream_k) {
     // stream-K over the HBM-tiled weight: grid = min(#SMs, units), fix-up workspace owned by the plan
     if (!w_tiled) { delete g; set_error("stream-K needs the tiled weight layout"); return PIA_ERR_INVALID; }
@@ -628,6 +630,11 @@ extern "C" int pia_gemm_plan_destroy(pia_gemm_plan_t *g) {
   }
   return PIA_OK;
 }
+extern "C" int pia_gemm_plan_set_pdl(pia_gemm_plan_t *g, int on) {
+  PIA_REQUIRE(g, "null plan");
+  g->no_pdl = on ? 0 : 1;
+  return PIA_OK;
+}
 extern "C" int pia_gemm_plan_splits(const pia_gemm_plan_t *g) { return g ? (g->p.cluster ? 1 : g->p.n_split) : 0; }
 extern "C" int pia_gemm_plan_set_silu(pia_gemm_plan_t *g, int on) {
   PIA_REQUIRE(g && g->p.n_split == 1 && !g->stream_k && g->p.N % BMW == 0, "the SiLU*up epilogue needs split_k == 1 and N %% 128 == 0");
@@ -650,7 +657,7 @@ extern "C" int pia_gemm_plan_create_grouped(const void *d_w, int groups, int N, 
   g->p.N = N; g->p.K = K; g->p.n_chunks = n_chunks; g->p.chunks_per_split = n_chunks; g->p.n_split = 1;
   g->p.rows = TOK; g->p.out_bf16 = nullptr; g->p.out_f32 = nullptr; g->p.silu = 0; g->p.tiled = 0; g->p.cluster = 0;
   g->p.groups = groups; g->p.w_group_rows = N; g->p.x_group_chunks = n_chunks; g->p.out_group_stride = (long long)TOK * N;
-  g->stream_k = 0;
+  g->stream_k = 0; g->no_pdl = 0;
   int rc = encode_2d(&g->map_w, d_w, (uint64_t)K, (uint64_t)groups * N, BK, BMW, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) rc = encode_2d(&g->map_x, d_x, (uint64_t)groups * K, (uint64_t)x_rows, BK, TOK, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc == PIA_OK) {
@@ -667,9 +674,12 @@ extern "C" int pia_gemm_plan_create_grouped(const void *d_w, int groups, int N, 
   return PIA_OK;
 }
 
+struct PdlScope { int on; explicit PdlScope(int off) : on(off) { if (on) ++pia::g_pdl_off; } ~PdlScope() { if (on) --pia::g_pdl_off; } };
+
 extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *stream) {
   PIA_REQUIRE(g && d_out, "null argument");
   PIA_REQUIRE(rows >= 1 && rows <= TOK, "rows %d outside [1,%d]", rows, TOK);
+  PdlScope pdl_scope(g->no_pdl);
   if (g->stream_k) {
     SkParams k = g->sk;
     k.rows = rows;
@@ -679,7 +689,7 @@ extern "C" int pia_gemm_run(pia_gemm_plan_t *g, int rows, void *d_out, void *str
     return PIA_OK;
   }
   Params p = g->p;
-  p.rows = rows;
+  p.rows = rows; p.no_pdl = g->no_pdl;
   if (p.n_split == 1 || p.cluster) p.out_bf16 = (__nv_bfloat16 *)d_out; else p.out_f32 = (float *)d_out;
   if (p.cluster) {
     dim3 cgrid(p.n_split, (p.N + BMW - 1) / BMW);

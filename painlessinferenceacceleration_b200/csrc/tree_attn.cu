@@ -205,7 +205,12 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 64);
 
   pdl_launch_dependents();
-  pdl_wait();  // the split decision below already reads device state written by the step's earlier kernels
+  // Programmatic dependent launch: this CTA may be running while its predecessor (RoPE + KV append of the same layer)
+  // still is.  What is read BEFORE griddepcontrol.wait is safe to read early: d_n / d_prefix_len / d_pad_len / the mask
+  // rows were written before the first kernel of the layer chain (trie get and the previous step's accept are launched
+  // without the PDL attribute, prefill meta is a stream-ordered copy), and cache rows below P were written by earlier
+  // steps.  Only Q, the rows [P, P + n) of this layer's K/V planes and the output buffer depend on the predecessor: the
+  // TMA producer waits before its first tile that reaches row P, the softmax warps wait before they read Q.
   const int split = blockIdx.x, group = blockIdx.y;
   const int slot = blockIdx.z;
   const int n = p.sl.d_n[slot], P = p.sl.d_prefix_len[slot];
@@ -272,11 +277,17 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     // ================================================================ TMA producer
     if (lane == 0 && ntile > 0) {
       const int plane = p.plane0 + slot * p.slot_planes + p.layer * p.n_kv_heads + hkv;
+      // rows the predecessor may still be appending start at P - or, when the slots share one cache (the chain chunks
+      // of a prefill pass: chunk c's prefix holds what the same RoPE launch appends for chunks < c), at the smallest P
+      int p_safe = P;
+      if (p.slot_planes == 0) for (int b2 = 0; b2 < p.sl.batch; ++b2) p_safe = min(p_safe, p.sl.d_prefix_len[b2]);
+      bool waited = false;
       for (int i = 0; i < ntile; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
+        const int key0 = (t0 + i) * BN;
+        if (!waited && key0 + BN > p_safe) { pdl_wait(); waited = true; }
         mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
-        const int key0 = (t0 + i) * BN;
         const uint32_t kd = base + SMEM_K + s * TILE_BYTES, vd = base + SMEM_V + s * TILE_BYTES;
         tma_load_3d(kd, &map_k, bar_kv_full + 8 * s, 0, key0, plane);
         tma_load_3d(kd + SUB, &map_k, bar_kv_full + 8 * s, 64, key0, plane);
@@ -331,6 +342,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   } else if (warp_active) {
     // ================================================================ softmax + accumulate
     // two threads per row: `half` selects 64 of the 128 S columns (keys) and 64 of the 128 O columns (head dim)
+    pdl_wait();  // Q below is the predecessor's output
     {
       uint4 qv[8];  // Q row -> shared memory (UMMA K-major SWIZZLE_128B); each half loads one 64-wide d sub-tile
       const bool have = hs < p.heads_per_cta && node < n;

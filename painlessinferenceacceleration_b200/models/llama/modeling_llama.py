@@ -234,6 +234,9 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             plans['o'] = self._mk_gemm(layer.self_attn.o_proj.weight.data, b.attn, split_k=sk)
         if 'down' in want and layer.mlp.down_proj.weight.shape[1] % 64 == 0 and layer.mlp.down_proj.weight.shape[1] >= 64 * abs(sk):
             plans['down'] = self._mk_gemm(layer.mlp.down_proj.weight.data, b.act, split_k=sk)
+        for name in os.environ.get('PIA_GEMM_NOPDL', '').split(','):   # experiment knob: plain kernel boundaries
+            if name in plans:
+                plans[name].set_pdl(False)
         return plans
 
     def _mk_gemm(self, w, x, split_k=1):

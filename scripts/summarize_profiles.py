@@ -31,7 +31,8 @@ def launch_list(path, name):
     rows = [(int(r['ID']), r['Kernel Name'], float(r['Metric Value'].replace(',', '')))
             for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
     gets = [i for i, r in enumerate(rows) if 'k_get' in r[1]]
-    cmd = 'bench.py --steps 2 --warmup 3 --no-cpu-baseline' if 'bench' in name else 'scripts/profile_step.py'
+    cmd = ('bench.py --steps 2 --warmup 3 --no-cpu-baseline' if 'bench' in name else
+           'scripts/profile_step.py --batch 8 (batched loop, 8 request slots)' if 'batch' in name else 'scripts/profile_step.py')
     out = [f'# ncu launch list ({name}): `ncu --metrics gpu__time_duration.sum --clock-control none` on '
            f'`{cmd}` (Llama-2-7B shape)', '',
            'Per-launch times are cold-cache and serialised: read the SHARES, not the absolutes.', '',
@@ -51,7 +52,7 @@ def launch_list(path, name):
         blas = sum(r[2] for r in seg if 'nvjet' in r[1] or 'cutlass' in r[1] or 'gemv' in r[1])
         out += ['', f'own kernels (libpia_b200, `pia::*`): {100 * own / tot:.1f}% of the step; cuBLAS GEMMs (`nvjet_*`): '
                     f'{100 * blas / tot:.1f}%; other (torch elementwise): {100 * (tot - own - blas) / tot:.1f}%']
-    open(os.path.join(OUT, f'{tag}_launches.md'), 'w').write('\n'.join(out) + '\n')
+    open(os.path.join(OUT, f'{tag}_{name}.md'), 'w').write('\n'.join(out) + '\n')
 
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',

@@ -297,7 +297,10 @@ def test_batched_slots_rope_and_attention(Hq, Hkv, rps, cases):
         ops.rope_kv_append(qkv[r0:], mask[r0:], one, Hq, Hkv, D, cos, sin, q1, kc[s_, layer], vc[s_, layer], max_seq)
         plan.forward(layer, q1, mask[r0:], one, o1)
         torch.cuda.synchronize()
-        assert torch.equal(qb[r0:r0 + rps], q1[:rps]) and torch.equal(ob[r0:r0 + rps], o1[:rps])
+        # RoPE / KV append: bit for bit.  Attention: a batch launch uses fewer KV splits per request (one wave of CTAs
+        # over all slots), i.e. another fp32 summation order - equal to the last bf16 bit or so
+        assert torch.equal(qb[r0:r0 + rps], q1[:rps])
+        assert torch.allclose(ob[r0:r0 + n].float(), o1[:n].float(), atol=4e-3, rtol=2e-2)
         assert torch.equal(kb[s_], kc[s_]) and torch.equal(vb[s_], vc[s_])
         assert float((qb[r0 + n:r0 + rps].float() - 7.0).abs().sum()) == 0   # rows beyond the draft: untouched
         assert float((ob[r0 + n:r0 + rps].float() - 9.0).abs().sum()) == 0
@@ -341,8 +344,9 @@ def test_prefill_chunks_share_one_cache():
                 plan.forward(0, q[R * c:], mask[R * c:], sl, o[R * c:])
         torch.cuda.synchronize()
         outs.append((q.clone(), o.clone(), kc.clone(), vc.clone()))
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    (q_a, o_a, k_a, v_a), (q_b, o_b, k_b, v_b) = outs
+    assert torch.equal(q_a, q_b) and torch.equal(k_a, k_b) and torch.equal(v_a, v_b)
+    assert torch.allclose(o_a.float(), o_b.float(), atol=4e-3, rtol=2e-2)   # KV split count differs (see above)
 
 
 def test_batched_accept_walk_and_compaction():
