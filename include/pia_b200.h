@@ -215,8 +215,8 @@ typedef struct pia_gemm_plan pia_gemm_plan_t;
 /* d_x : [x_rows >= 64, K] bf16 activation buffer the plan's TMA descriptor is bound to; K % 64 == 0.
  * split_k > 1 splits the K range over CTAs (for projections with few 128-row weight tiles) and yields fp32 partial
  * slices; split_k == -1 (tiled weights only) selects stream-K: the (tile, k-chunk) units are cut into one equal
- * contiguous range per SM and tiles spanning CTAs are fixed up in-kernel (bf16 output, deterministic); split_k == -2
- * or -4: the 2 / 4 K splits of a weight tile run as one thread-block cluster and reduce their fp32 partials through
+ * contiguous range per SM and tiles spanning CTAs are fixed up in-kernel (bf16 output, deterministic); split_k == -2,
+ * -4 or -8: the 2 / 4 / 8 K splits of a weight tile run as one thread-block cluster and reduce their fp32 partials through
  * distributed shared memory in split order (bf16 output, deterministic, no fp32 slices in HBM). Synchronous. */
 /* w_tiled != 0: d_w holds the same weight re-laid out as [N/128][K/64] contiguous blocks of 128 rows x 64 k
  * (W.view(N/128,128,K/64,64).permute(0,2,1,3)), so that every CTA streams one contiguous slab of HBM. */

@@ -565,8 +565,8 @@ extern "C" int pia_gemm_plan_create(const void *d_w, int N, int K, const void *d
   PIA_REQUIRE(g, "out of host memory");
   const int n_chunks = K / BK;
   const int want_stream_k = (split_k == -1);
-  const int want_cluster = (split_k == -2 || split_k == -4) ? -split_k : 0;
-  if (split_k < -1 && !want_cluster) { delete g; set_error("cluster split-K supports 2 or 4 CTAs"); return PIA_ERR_INVALID; }
+  const int want_cluster = (split_k == -2 || split_k == -4 || split_k == -8) ? -split_k : 0;
+  if (split_k < -1 && !want_cluster) { delete g; set_error("cluster split-K supports 2, 4 or 8 CTAs"); return PIA_ERR_INVALID; }
   if (want_cluster) split_k = want_cluster;
   if (split_k < 1) split_k = 1;
   if (split_k > n_chunks) split_k = n_chunks;

@@ -364,43 +364,6 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
             else:
                 torch.mm(b.y, self.lm_head.weight.t(), out=b.logits)
 
-    # ------------------------------------------------------------------ reference-shaped forward (API parity)
-    @torch.no_grad()
-    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, use_cache=True,
-                return_dict=True, **kwargs):
-        """The patched forward of the reference (:544-677, :710-790) for rank-4 lookahead masks
-        `[1, 1, n, P + n]` (visible prefix || tree).  `past_key_values` is the integer P returned by the previous
-        call (the KV cache itself is the model's preallocated device cache).  Returns (logits [1, n, V], P + n)."""
-        assert input_ids is not None and input_ids.shape[0] == 1
-        n = input_ids.shape[1]
-        P = int(past_key_values) if past_key_values is not None else 0
-        am = attention_mask
-        assert am is not None and am.dim() == 4 and am.shape[2] == n and am.shape[3] == P + n, \
-            'forward expects the lookahead mask [1,1,n,P+n] (modeling_llama.py:585-588)'
-        am = am[0, 0].to('cpu').long().numpy()
-        pad_len = 0
-        if P > 0:
-            nz = am[0, :P].nonzero()[0]
-            pad_len = int(nz[0]) if len(nz) else P
-        tree = am[:, P:]
-        need = P + n + 1
-        have = self._rt
-        rt = self._runtime(need if have is not None and have.max_seq >= need else max(need, 256),
-                           64 if n <= 64 else 128, keep_cache=P > 0)
-        assert n <= rt.max_nodes, 'at most 128 tree nodes per forward; prefill goes through generate()'
-        import numpy as np
-        packed = np.packbits(np.pad(tree.astype(np.uint8), ((0, rt.max_nodes - n), (0, rt.max_nodes - n))), axis=1,
-                             bitorder='little')
-        rows = torch.from_numpy(packed.view(np.int64).reshape(rt.max_nodes, rt.max_nodes // 64))
-        rt.mask.copy_(rows.to(rt.device))
-        rt.ids[:n] = input_ids[0].to(device=rt.device, dtype=torch.int32)
-        rt.n.fill_(n)
-        rt.prefix_len.fill_(P)
-        rt.set_request(0, pad_len, 1 << 30)
-        self._verify_layers(rt)
-        logits = rt.logits[:n].clone()[None]
-        return logits, P + n
-
 
 class LlamaPreTrainedModel(LookaheadPreTrainedModel):
     pass

@@ -375,3 +375,59 @@ def test_caller_supplied_logits_processor_and_stopping_criteria():
     assert got == full[:len(got)] and tok in got[40:] and len(got) < len(full)
     first = 40 + full[40:].index(tok)
     assert len(got) > first and sum(o.kwargs['edls']) == len(got) - 40
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPT-2 patch surface on the GPU (reference models/gpt2/modeling_gpt2.py:805-809, 183-221; BASELINE config 1's family)
+# ---------------------------------------------------------------------------------------------------------------
+def _gpt2_pair(seed):
+    from painlessinferenceacceleration_b200.models.gpt2.modeling_gpt2 import GPT2LMHeadModel
+    hf = tiny_hf_model('gpt2', seed=seed, dtype=torch.bfloat16, device=DEV, vocab=200)
+    ours = GPT2LMHeadModel(hf.config, device=torch.device(DEV))
+    missing = ours.load_state_dict(hf.state_dict(), strict=False)
+    assert not missing.missing_keys, missing
+    return hf, ours
+
+
+def test_gpt2_verify_logits_and_loop():
+    """GPT-2 (64-wide or narrower heads, learned positions, LayerNorm, gelu_new, Conv1D + bias, tied head) through the
+    shared kernels: heads zero-padded to the 128-wide tcgen05 attention tile.  (i) logits vs an fp32 evaluation of the
+    same weights within 2 x the eager bf16 model's own error + 0.02; (ii) the oracle loop (reference semantics, 16-token
+    / 4-branch drafts = BASELINE config 1) driving one copy == our fused device loop on the other copy: tokens, dls,
+    edls identical; (iii) lookahead == plain greedy on the same kernels."""
+    from oracle.loop import lookahead_generate
+    from oracle.trie import OracleLookaheadCache
+    from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
+    from painlessinferenceacceleration_b200.models.gpt2.modeling_gpt2 import GPT2LMHeadModel
+    hf, ours = _gpt2_pair(seed=16)
+    hf32 = tiny_hf_model('gpt2', seed=16, dtype=torch.float32, device=DEV, vocab=200)
+    hf32.load_state_dict({k: v.float() for k, v in hf.state_dict().items()})
+    p = prompts(78, 1, 100, 200)[0].to(DEV)
+    with torch.no_grad():
+        truth = hf32(input_ids=p).logits[0].float()
+        eager = hf(input_ids=p).logits[0].float()
+    m01 = torch.tril(torch.ones((1, 1, 100, 100), dtype=torch.long, device=DEV))
+    got = OursBackend(ours).forward(p, m01, None)[0].float()
+    e_ours, e_eager = (got - truth).abs().max().item(), (eager - truth).abs().max().item()
+    _diag('verify_logits', family='gpt2', e_ours=e_ours, e_eager=e_eager)
+    assert e_ours <= 2 * e_eager + 0.02, (e_ours, e_eager)
+    b = GPT2LMHeadModel(hf.config, device=torch.device(DEV))
+    b.load_state_dict(hf.state_dict(), strict=False)
+    ours.lookahead_cache = LookaheadCache(eos_ids=[2], device=DEV, vocab_capacity=1024, node_capacity=1 << 20)
+    otrie = OracleLookaheadCache(eos_ids=[2])
+    edl_all, same = [], 0
+    for rep in range(2):
+        for q in prompts(56, 3, 70, 200):
+            q = q.to(DEV)
+            dk = {'use_lookahead': True, 'decoding_length': 16, 'branch_length': 4}
+            out = ours.generate(input_ids=q, max_new_tokens=48, eos_token_id=2, decoding_kwargs=dk,
+                                return_dict_in_generate=True)
+            ref = lookahead_generate(None, otrie, q, max_new_tokens=48, eos_token_id=[2], decoding_length=16,
+                                     branch_length=4, backend=OursBackend(b, prefill_like_generate=True, max_seq=70 + 48 + 17))
+            assert out.sequences[0].tolist() == ref['sequences'][0].tolist()
+            assert out.kwargs['edls'] == ref['edls'] and out.kwargs['dls'] == ref['dls']
+            edl_all += ref['edls'][1:]
+            plain = ours.generate(input_ids=q, max_new_tokens=48, eos_token_id=2, decoding_kwargs={'use_lookahead': False})
+            same += int(plain[0].tolist() == out.sequences[0].tolist())
+    assert max(edl_all) > 2
+    assert same >= 4   # a draft of 1 vs 16 nodes changes the KV split count, i.e. the fp32 summation order (bf16 near-ties)

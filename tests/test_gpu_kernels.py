@@ -473,9 +473,9 @@ def test_gemm_weight_streaming(N, K, split):
         torch.cuda.synchronize()
         assert torch.equal(o1, o2)
         assert torch.allclose(o1.float(), ref, atol=2e-2, rtol=1.6e-2), (o1.float() - ref).abs().max().item()
-        # cluster split-K: 2 / 4 K splits of a tile reduce through DSMEM in split order; bf16 out, deterministic
-        for cs in (2, 4):
-            if K // 64 < cs:
+        # cluster split-K: 2 / 4 / 8 K splits of a tile reduce through DSMEM in split order; bf16 out, deterministic
+        for cs in (2, 4, 8):
+            if K // 64 < cs or -(-(K // 64) // (-(-(K // 64) // cs))) != cs:   # the K chunks must split into exactly cs parts
                 continue
             for tiled, wt in ((True, ops.tile_weight(w)), (False, w)):
                 gc = ops.Gemm(wt, x, split_k=-cs, tiled=tiled)
