@@ -272,6 +272,11 @@ int pia_embed_gather(const void *d_table, const int32_t *d_ids, const int32_t *d
  * selected by that token); d_out : [rows, hidden] bf16. */
 int pia_moe_combine(const void *d_expert_out, const void *d_weights, int n_experts, int rows, int rows_cap, int hidden,
                     void *d_out, void *stream);
+/* MoE router (mixtral/modeling_mixtral.py:721-727): gate Linear (bf16) -> fp32 softmax -> top-k -> renormalise -> bf16,
+ * written densely: d_dense_out [rows, n_experts] holds the routing weight of the selected experts and 0 elsewhere.
+ * d_y [rows, hidden] bf16, d_gate_weight [n_experts, hidden] bf16. */
+int pia_moe_router(const void *d_y, const void *d_gate_weight, int rows, int hidden, int n_experts, int top_k,
+                   void *d_dense_out, void *stream);
 /* L2 prefetch of immutable weights (no reference counterpart: the reference's eager loop leaves HBM idle while the
  * small kernels of a layer - RoPE, attention, norms - run; modeling_llama.py:272-292 sits between the qkv and the o
  * projection).  Issues cp.async.bulk.prefetch.L2 for n_ranges ranges of range_bytes (multiple of 16) that start

@@ -156,6 +156,15 @@ def moe_combine(expert_out, weights, out):
     L.check(L.load().pia_moe_combine(_p(expert_out), _p(weights), E, rows, rows_cap, hidden, _p(out), _s()))
 
 
+def moe_router(y, gate_weight, top_k, dense_out):
+    """dense routing weights [rows, E] (0 for unselected experts) of the rows of y (pia_moe_router)"""
+    rows, hidden = y.shape
+    E = gate_weight.shape[0]
+    assert gate_weight.shape[1] == hidden and dense_out.shape[0] >= rows and dense_out.shape[1] == E
+    assert y.is_contiguous() and gate_weight.is_contiguous() and dense_out.is_contiguous()
+    L.check(L.load().pia_moe_router(_p(y), _p(gate_weight), rows, hidden, E, int(top_k), _p(dense_out), _s()))
+
+
 def l2_prefetch(t, n_ranges=1, stride_bytes=0, range_bytes=None, gbytes_per_s=0.0, offset_bytes=0):
     """hint: pull (part of) an immutable weight tensor into L2 on the current stream (pia_l2_prefetch)"""
     if range_bytes is None:

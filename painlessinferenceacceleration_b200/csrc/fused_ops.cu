@@ -267,6 +267,62 @@ extern "C" int pia_moe_combine(const void *d_expert_out, const void *d_weights, 
   return PIA_OK;
 }
 
+// MoE router (mixtral/modeling_mixtral.py:721-727): router_logits = gate(hidden) (a bf16 Linear: fp32 accumulation,
+// one bf16 rounding), softmax in fp32, top-k, renormalise, cast to bf16; written DENSE: w[t][e] = routing weight or 0 for
+// the experts token t did not select (what k_moe_combine and the dense-over-experts verify path consume).
+// grid = rows; one warp per expert dot product (round robin), thread 0 does the 8-way softmax / top-k.
+__global__ void __launch_bounds__(256) k_moe_router(const __nv_bfloat16 *y, const __nv_bfloat16 *gate_w, int hidden,
+                                                    int n_exp, int top_k, __nv_bfloat16 *dense) {
+  __shared__ float s_logit[64];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16 *yr = y + (long long)t * hidden;
+  for (int e = warp; e < n_exp; e += 8) {
+    const __nv_bfloat16 *wr = gate_w + (long long)e * hidden;
+    float acc = 0.f;
+    for (int v = lane; v * 8 < hidden; v += 32) {
+      Pack8 a, w;
+      a.u = *reinterpret_cast<const uint4 *>(yr + v * 8);
+      w.u = *reinterpret_cast<const uint4 *>(wr + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += __bfloat162float(a.h[j]) * __bfloat162float(w.h[j]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (lane == 0) s_logit[e] = bf(acc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int e = 0; e < n_exp; ++e) mx = fmaxf(mx, s_logit[e]);
+    float den = 0.f, p[64];
+    for (int e = 0; e < n_exp; ++e) { p[e] = expf(s_logit[e] - mx); den += p[e]; }
+    for (int e = 0; e < n_exp; ++e) p[e] /= den;
+    unsigned long long chosen = 0ull;
+    float sum = 0.f;
+    for (int k = 0; k < top_k; ++k) {   // largest first, lowest index on ties
+      int best = -1;
+      for (int e = 0; e < n_exp; ++e)
+        if (!((chosen >> e) & 1ull) && (best < 0 || p[e] > p[best])) best = e;
+      chosen |= 1ull << best;
+      sum += p[best];
+    }
+    for (int e = 0; e < n_exp; ++e)
+      dense[(long long)t * n_exp + e] = __float2bfloat16_rn(((chosen >> e) & 1ull) ? p[e] / sum : 0.f);
+  }
+}
+
+extern "C" int pia_moe_router(const void *d_y, const void *d_gate_weight, int rows, int hidden, int n_experts, int top_k,
+                              void *d_dense_out, void *stream) {
+  PIA_REQUIRE(d_y && d_gate_weight && d_dense_out && rows > 0 && hidden % 8 == 0 && n_experts >= 1 && n_experts <= 64 &&
+                  top_k >= 1 && top_k <= n_experts, "bad router arguments");
+  PIA_CUDA_CHECK(launch_kernel(k_moe_router, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16 *)d_y,
+                              (const __nv_bfloat16 *)d_gate_weight, hidden, n_experts, top_k, (__nv_bfloat16 *)d_dense_out));
+  count_launch();
+  return PIA_OK;
+}
+
 // One warp per SM walks the ranges chunk by chunk (the bulk-prefetch issue rate of a single SM's TMA unit is only a
 // few hundred GB/s, so the chunks are dealt round-robin over the whole grid); bytes_per_ns paces the grid against
 // %globaltimer so that the demand loads of the kernels running beside it (attention's KV tiles) are not queued behind

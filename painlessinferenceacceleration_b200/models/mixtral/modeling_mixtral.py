@@ -108,21 +108,18 @@ class MixtralForCausalLM(LlamaForCausalLM):
 
     def _mlp(self, rt, layer, y, plans=None, pf=None):
         moe = layer.mlp
-        logits = torch.mm(y, moe.gate.weight.t())                                   # :721
-        probs = torch.softmax(logits.float(), dim=1)                                # :723
-        w, sel = torch.topk(probs, moe.top_k, dim=-1)                               # :724
-        w = (w / w.sum(dim=-1, keepdim=True)).to(y.dtype)                           # :725-727
         if plans:
             b = rt.decode_bufs
             E = moe.num_experts
             inter = moe.experts.down_proj.shape[2]
-            b.moe_dense.zero_().scatter_(1, sel, w)
+            ops.moe_router(y, moe.gate.weight, moe.top_k, b.moe_dense)              # :721-727 in one kernel
             plans['moe_gate_up'].run(64, out=b.moe_gu)
             ops.silu_mul(b.moe_gu.view(b.rows * E, 2 * inter), b.moe_act.view(b.rows * E, inter))
             ye = plans['moe_down'].run(64)                                          # [E, 64, H]
             ops.moe_combine(ye, b.moe_dense, b.moe_out)
             return b.moe_out, None
-        dense = torch.zeros((y.shape[0], moe.num_experts), dtype=y.dtype, device=y.device).scatter_(1, sel, w)
+        dense = torch.empty((y.shape[0], moe.num_experts), dtype=y.dtype, device=y.device)
+        ops.moe_router(y, moe.gate.weight, moe.top_k, dense)                        # :721-727
         out = torch.zeros_like(y)
         inter = moe.experts.down_proj.shape[2]
         act = torch.empty((y.shape[0], inter), dtype=y.dtype, device=y.device)

@@ -450,6 +450,31 @@ def test_multinomial_accept_draws_from_softmax():
         assert chi2 < 2.0 * int(keep.sum()) + 20, (penalty, chi2, int(keep.sum()))
 
 
+def test_moe_router():
+    """pia_moe_router vs the reference's router arithmetic (mixtral/modeling_mixtral.py:721-727): bf16 gate Linear,
+    fp32 softmax, top-2, renormalise, bf16; dense [rows, E] output"""
+    from painlessinferenceacceleration_b200.common import ops
+    torch.manual_seed(9)
+    rows, H, E = 64, 4096, 8
+    y = torch.randn((rows, H), device=DEV).to(torch.bfloat16)
+    g = (torch.randn((E, H), device=DEV) * 0.05).to(torch.bfloat16)
+    dense = torch.full((rows, E), 5.0, dtype=torch.bfloat16, device=DEV)
+    ops.moe_router(y, g, 2, dense)
+    logits = torch.mm(y, g.t())
+    probs = torch.softmax(logits.float(), dim=1)
+    w, sel = torch.topk(probs, 2, dim=-1)
+    w = (w / w.sum(dim=-1, keepdim=True)).to(torch.bfloat16)
+    ref = torch.zeros((rows, E), dtype=torch.bfloat16, device=DEV).scatter_(1, sel, w)
+    torch.cuda.synchronize()
+    assert ((dense != 0).sum(1) == 2).all()
+    assert torch.allclose(dense.float().sum(1), torch.ones(rows, device=DEV), atol=1e-2)
+    srt = probs.sort(dim=1, descending=True).values
+    clear = (srt[:, 1] - srt[:, 2]) > 5e-3              # rows whose 2nd / 3rd experts are not a bf16 near-tie
+    assert clear.float().mean() > 0.8
+    assert torch.equal((dense != 0)[clear], (ref != 0)[clear])
+    assert torch.allclose(dense[clear].float(), ref[clear].float(), atol=1.5e-2)
+
+
 @pytest.mark.parametrize('N,K,split', [(256, 128, 1), (12288, 4096, 1), (4096, 4096, 4), (22016, 4096, 1),
                                        (4096, 11008, 4), (32000, 4096, 1), (4096, 4096, 1), (1024, 14336, 7)])
 def test_gemm_weight_streaming(N, K, split):
