@@ -402,21 +402,23 @@ def gemm_roofline(model, dev):
     plans = getattr(rt, 'gemm_plans', None)
     if not plans:
         return None
-    lp = [p for p in plans['layers'] if 'gate_up' in p]
+    key = 'gate_up_silu' if any('gate_up_silu' in p for p in plans['layers']) else 'gate_up'
+    lp = [p for p in plans['layers'] if key in p]
     if not lp:
         return None
     b = rt.decode_bufs
+    out = b.act if key == 'gate_up_silu' else b.gu   # the fused epilogue writes SiLU(gate) * up [64, N/2] directly
 
     def sweep():
         for p in lp:
-            p['gate_up'].run(64, out=b.gu)
+            p[key].run(64, out=out)
 
     us = _graph_time(sweep) / len(lp)
-    N, Kd = lp[0]['gate_up'].N, b.y.shape[1]
-    by = N * Kd * 2 + 64 * Kd * 2 + 64 * N * 2
+    N, Kd = lp[0][key].N, b.y.shape[1]
+    by = N * Kd * 2 + 64 * Kd * 2 + 64 * out.shape[1] * 2
     hbm, _tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
-    return {'kernel': 'k_gemm_ws<4> (gate_up projection, one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
+    return {'kernel': 'k_gemm_ws<4> (gate_up projection' + (' + SiLU*up epilogue' if key == 'gate_up_silu' else '') + ', one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
             'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_gemm_ws', 'k_gemm_ws'),
             'bytes_per_launch': by, 'us_per_launch': us, 'shape': f'Y[64,{N}] = X[64,{Kd}] W[{N},{Kd}]^T',
             'peak_source': src}

@@ -266,26 +266,33 @@ k_gemm_ws(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUt
       }
     } else
     if (p.silu) {
-      // act(gate) * up (modeling_llama.py:185-186) in the epilogue: lanes 0-63 hold gate rows, lanes 64-127 the up
-      // rows of the same 64 output columns.  Rounding points as in eager bf16: GEMM out -> bf16, silu -> bf16, * -> bf16
-      __nv_bfloat16 *xb = reinterpret_cast<__nv_bfloat16 *>(sm + SMEM_BAR + 256);  // [64 tokens][64 rows]
+      // act(gate) * up (modeling_llama.py:185-186) in the epilogue: lanes 0-63 (warps q = 0, 1) hold gate rows, lanes
+      // 64-127 (q = 2, 3) the up rows of the same 64 output columns.  Each warp pair splits the 64 tokens: the gate warp
+      // finishes tokens 0-31 (it receives the up values through shared memory), the up warp tokens 32-63 (it receives the
+      // gate values), so all four warps share the exponentials.  Rounding points as in eager bf16 (and k_silu_mul):
+      // GEMM out -> bf16, silu -> bf16, product -> bf16.
+      __nv_bfloat16 *xu = reinterpret_cast<__nv_bfloat16 *>(sm + SMEM_BAR + 256);  // up   [32 tokens 0-31 ][64 rows]
+      __nv_bfloat16 *xg = xu + 32 * 64;                                             // gate [32 tokens 32-63][64 rows]
       const int rr = (q & 1) * 32 + lane;
       if (q >= 2) {
 #pragma unroll
-        for (int t = 0; t < TOK; ++t) xb[t * 64 + rr] = __float2bfloat16_rn(__uint_as_float(v[t]));
+        for (int t = 0; t < 32; ++t) xu[t * 64 + rr] = __float2bfloat16_rn(__uint_as_float(v[t]));
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) xg[t * 64 + rr] = __float2bfloat16_rn(__uint_as_float(v[32 + t]));
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (q < 2) {
-        const int col = tile * 64 + rr;
-        const int inter = p.N >> 1;
-        if (col < inter) {
+      const int col = tile * 64 + rr;
+      const int inter = p.N >> 1;
+      if (col < inter) {
+        const int tb = q < 2 ? 0 : 32;
 #pragma unroll
-          for (int t = 0; t < TOK; ++t) {
-            if (t < p.rows) {
-              const float g = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[t])));
-              const float sg = __bfloat162float(__float2bfloat16_rn(g / (1.f + expf(-g))));
-              p.out_bf16[(long long)t * inter + col] = __float2bfloat16_rn(sg * __bfloat162float(xb[t * 64 + rr]));
-            }
+        for (int t = 0; t < 32; ++t) {
+          if (tb + t < p.rows) {
+            const float g = q < 2 ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[t]))) : __bfloat162float(xg[t * 64 + rr]);
+            const float u = q < 2 ? __bfloat162float(xu[t * 64 + rr]) : __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[32 + t])));
+            const float sg = __bfloat162float(__float2bfloat16_rn(g / (1.f + expf(-g))));
+            p.out_bf16[(long long)(tb + t) * inter + col] = __float2bfloat16_rn(sg * u);
           }
         }
       }

@@ -223,7 +223,15 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         import os
         want = os.environ.get('PIA_GEMM_SET', 'gate_up,down').split(',')
         plans = {}
-        if 'gate_up' in want:
+        if 'gate_up_silu' in want and layer.mlp.gate_up_weight.shape[0] % 256 == 0:
+            # SiLU(gate) * up in the GEMM epilogue: every 128-row weight tile holds 64 gate rows + the 64 up rows of the same
+            # columns (ops.interleave_gate_up), the plan writes act [rows, inter] directly
+            cache = self.__dict__.setdefault('_tiled_weights', {})
+            key = ('gate_up_silu', layer.mlp.gate_up_weight.data_ptr())
+            if key not in cache:
+                cache[key] = ops.tile_weight(ops.interleave_gate_up(layer.mlp.gate_up_weight))
+            plans['gate_up_silu'] = ops.Gemm(cache[key], b.y, tiled=True).set_silu()
+        elif 'gate_up' in want or 'gate_up_silu' in want:
             plans['gate_up'] = self._mk_gemm(layer.mlp.gate_up_weight, b.y)
         if 'qkv' in want:
             plans['qkv'] = self._mk_gemm(layer.self_attn.qkv_weight, b.y)
@@ -293,13 +301,16 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         m = layer.mlp
         if plans:
             b = rt.decode_bufs
-            if 'gate_up' in plans:
-                plans['gate_up'].run(64, out=b.gu)
+            if 'gate_up_silu' in plans:
+                plans['gate_up_silu'].run(64, out=b.act)
             else:
-                torch.mm(y, m.gate_up_weight.t(), out=b.gu)
-            if pf:
-                self._prefetch(pf, [(m.down_proj.weight, pf['down'], 0)])
-            ops.silu_mul(b.gu, b.act)
+                if 'gate_up' in plans:
+                    plans['gate_up'].run(64, out=b.gu)
+                else:
+                    torch.mm(y, m.gate_up_weight.t(), out=b.gu)
+                if pf:
+                    self._prefetch(pf, [(m.down_proj.weight, pf['down'], 0)])
+                ops.silu_mul(b.gu, b.act)
             if 'down' in plans:
                 o = plans['down'].run(64)
                 return (o, None) if plans['down'].splits == 1 else (None, o)

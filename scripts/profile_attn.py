@@ -18,6 +18,8 @@ if which == 'short':
     r = bench.attention_roofline_long(dev, P=bench.PROMPT_LEN + bench.NEW_TOKENS // 2, layers=32)
 elif which == 'gqa':   # Mistral-7B / Mixtral attention geometry (GQA-4) at the benchmark's mid-generation step
     r = bench.attention_roofline_long(dev, P=bench.PROMPT_LEN + bench.NEW_TOKENS // 2, hq=32, hkv=8, layers=32)
+elif which == 'gqa_long':   # the same geometry at a 4 k context: where the tensor pipe has work to do (AI 256 FLOP/B)
+    r = bench.attention_roofline_long(dev, hq=32, hkv=8, layers=8)
 else:
     r = bench.attention_roofline_long(dev)
 print({k: r[k] for k in ('shape', 'us_per_launch', 'achieved', 'frac', 'bytes_per_launch')})

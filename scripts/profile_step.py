@@ -29,15 +29,23 @@ model = LlamaForCausalLM(cfg, device=dev)
 bench.synth_fill(model, cfg)
 model.lookahead_cache = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=cfg.vocab_size, n_input_slots=max(a.batch, 8))
 ps = bench.phrase_bank_prompts(max(4, a.batch), cfg.vocab_size, length=a.prompt)
+prof = torch.cuda.cudart()   # run under `ncu --profile-from-start off`: only the LAST request is captured (the weight
+                             # synthesis alone is thousands of elementwise launches)
 if a.batch:
     for r in range(a.requests):
+        if r == a.requests - 1:
+            prof.cudaProfilerStart()
         o = model.generate(input_ids=torch.tensor(ps[:a.batch], device=dev), max_new_tokens=a.new, eos_token_id=2,
                            decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8,
                                             'batch_share': a.share}, return_dict_in_generate=True)
         print('batch request', r, 'edls', o.kwargs['edls'][:24], 'dls', o.kwargs['dls'][:24])
+    prof.cudaProfilerStop()
     sys.exit(0)
 for r in range(a.requests):  # same prompt twice: the second request drafts from the first one's answer
+    if r == a.requests - 1:
+        prof.cudaProfilerStart()
     o = model.generate(input_ids=torch.tensor([ps[0]], device=dev), max_new_tokens=a.new, eos_token_id=2,
                        decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8},
                        return_dict_in_generate=True)
     print('request', r, 'edls', o.kwargs['edls'], 'dls', o.kwargs['dls'])
+prof.cudaProfilerStop()
