@@ -206,6 +206,17 @@ int pia_attn_plan_grid(const pia_attn_plan_t *p, int *n_split, int *n_groups);
 int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask, const pia_slots_t *slots,
                       float scale_mul, void *d_out, void *stream);
 
+/* The same attention with RoPE + KV append folded in (modeling_llama.py:261-268 + :272-292 in one launch): d_qkv is the
+ * fused projection output [batch * rows_per_slot, (Hq + 2*Hkv) * D] bf16; Q and the draft nodes' K are rotated at the
+ * nodes' positions (tables as pia_rope_kv_append), the n draft keys are one extra tile staged in shared memory, the
+ * TMA tiles only cover the cached prefix [0, P), and one CTA per KV head appends the rotated K / V rows to cache rows
+ * [P, P + n) for the steps to come.  Same arithmetic as pia_rope_kv_append + pia_tree_attn_fwd (the cache rows are bit
+ * identical, the output differs by the fp32 summation order of the tiles).  Needs one cache per slot
+ * (batch == 1 or kv_slot_stride != 0): prefill chunks that share a cache use the two-kernel path. */
+int pia_tree_attn_fused_fwd(pia_attn_plan_t *p, int layer, const void *d_qkv, const void *d_cos, const void *d_sin,
+                            int max_pos, const uint64_t *d_mask, const pia_slots_t *slots, float scale_mul, void *d_out,
+                            void *stream);
+
 /* ============================================================================================
  * Weight-streaming GEMM of the verify forward: Y[t, n] = sum_k X[t, k] W[n, k]  (X: <= 64 draft rows, W = an
  * nn.Linear weight [N, K] bf16), i.e. the projections of modeling_llama.py:254-256, :303, :185-186, :769.

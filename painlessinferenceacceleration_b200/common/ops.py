@@ -198,6 +198,13 @@ class AttnPlan(object):
         assert q.shape[0] >= slots.rows and mask.shape[0] >= slots.rows and out.shape[0] >= slots.rows
         L.check(self.lib.pia_tree_attn_fwd(self.h, layer, _p(q), _p(mask), slots.ref(), float(scale_mul), _p(out), _s()))
 
+    def forward_fused(self, layer, qkv, mask, slots, cos, sin, out, scale_mul=1.0):
+        """RoPE + KV append + tree attention in one launch (pia_tree_attn_fused_fwd): qkv is the fused projection
+        output; needs one cache per slot"""
+        assert qkv.shape[0] >= slots.rows and mask.shape[0] >= slots.rows and out.shape[0] >= slots.rows
+        L.check(self.lib.pia_tree_attn_fused_fwd(self.h, layer, _p(qkv), _p(cos), _p(sin), cos.shape[0], _p(mask),
+                                                 slots.ref(), float(scale_mul), _p(out), _s()))
+
     def close(self):
         if self.h:
             self.lib.pia_attn_plan_destroy(self.h)

@@ -172,6 +172,22 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int b_mn_major) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+union Pack8 { uint4 u; __nv_bfloat16 h[8]; };
+__device__ __forceinline__ float bfr(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// x * cos + rotate_half(x) * sin for 8 elements, every product / sum rounded to bf16 (k_rope_kv_append's arithmetic,
+// modeling_llama.py:167-168); `lower` = these elements lie in the first half of the head (partner enters negated)
+__device__ __forceinline__ uint4 rope8(uint4 xa, uint4 xb, uint4 cs, uint4 sn, bool lower) {
+  Pack8 a, b, c, s, o;
+  a.u = xa; b.u = xb; c.u = cs; s.u = sn;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float x = __bfloat162float(a.h[j]);
+    const float r = lower ? -__bfloat162float(b.h[j]) : __bfloat162float(b.h[j]);
+    o.h[j] = __float2bfloat16_rn(bfr(x * __bfloat162float(c.h[j])) + bfr(r * __bfloat162float(s.h[j])));
+  }
+  return o.u;
+}
+
 struct Params {
   const __nv_bfloat16 *q;  // [max_nodes, Hq, HD]
   const unsigned long long *mask;
@@ -180,6 +196,13 @@ struct Params {
   int plane0;              // first plane of the cache slot 0 addresses
   int layer, n_q_heads, n_kv_heads, np, mask_words, heads_per_cta, max_seq, n_split, tiles_per_cta;
   float scale_log2;
+  // fused mode (pia_tree_attn_fused_fwd): RoPE + KV append happen here.  Q and the draft nodes' K / V come straight from
+  // the fused projection output, the draft keys are one extra tile built in shared memory, the cache only holds [0, P)
+  int fused;
+  const __nv_bfloat16 *qkv;      // [rows, (Hq + 2 Hkv) * HD]
+  const __nv_bfloat16 *cos_t, *sin_t;  // [max_pos, HD / 2] bf16 (as k_rope_kv_append)
+  int max_pos;
+  __nv_bfloat16 *kc_layer, *vc_layer;  // this layer's [Hkv, max_seq, HD] planes of the cache slot 0 addresses
   __nv_bfloat16 *out;            // [max_nodes, Hq, HD]
   unsigned long long *dbg;       // optional per-CTA phase timestamps (pia_attn_plan_set_debug)
 };
@@ -201,7 +224,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const uint32_t bar0 = base + SMEM_BAR;
   const uint32_t bar_kv_full = bar0, bar_kv_empty = bar0 + 8 * NSTAGE, bar_s_full = bar0 + 16 * NSTAGE,
                  bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 16, bar_q_full = bar_o_full + 8,
-                 bar_o_free = bar_q_full + 8;
+                 bar_o_free = bar_q_full + 8, bar_draft = bar_o_free + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 64);
 
   pdl_launch_dependents();
@@ -220,7 +243,11 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const int L = P + n;
   const int hq0 = group * p.heads_per_cta;
   const int hkv = hq0 / (p.n_q_heads / p.n_kv_heads);
-  const int tiles_total = (L + BN - 1) / BN;
+  // tiles: plain mode = the keys [0, L) of the cache; fused mode = the prefix tiles [0, P) of the cache + ONE draft tile
+  // (the n draft keys, rotated and staged in shared memory by the softmax warps of the CTA that owns the last tile)
+  const bool fused = p.fused != 0;
+  const int Tp = (P + BN - 1) / BN;
+  const int tiles_total = fused ? Tp + 1 : (L + BN - 1) / BN;
   // Work split decided on the device from the live length: tiles_per_cta tiles per CTA (more only when the
   // plan's split limit is reached); a single split writes the final output directly (no partials, no merge).
   const int rows_used = p.heads_per_cta * p.np;          // 64 (MHA, 64 nodes) or 128
@@ -237,6 +264,10 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   int t1 = t0 + tps;
   if (t1 > tiles_total) t1 = tiles_total;
   const int ntile = t1 - t0;  // >= 1 for split < ns except possibly the last one
+  // the CTA that owns the last tile takes the draft tile FIRST (slot 0 of the ring is free at kernel start; the order of
+  // tiles does not matter to the online softmax) and its prefix tiles after it
+  const bool has_draft = fused && ntile > 0 && t1 == tiles_total;
+  auto tile_of = [&](int i) -> int { return has_draft ? (i == 0 ? Tp : t0 + i - 1) : t0 + i; };
   // cluster barrier A ("every CTA of the cluster is running and its merge buffers may be written"): with dedicated
   // merge buffers the arrive happens right here and the wait just before the push (it has long completed by then);
   // with aliased buffers (128-row tiles) A is a full barrier after the tile loop
@@ -260,6 +291,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     mbar_init(bar_o_free, 2 * rows_used);
     mbar_init(bar_o_full, 1);
     mbar_init(bar_q_full, 2 * rows_used);
+    mbar_init(bar_draft, NTHREADS - 64);  // all eight softmax warps stage the draft tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();  // warp 0 reconverges before the (warp-aligned) block barrier below (synccheck: divergent lane 0)
@@ -284,8 +316,14 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       bool waited = false;
       for (int i = 0; i < ntile; ++i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
-        const int key0 = (t0 + i) * BN;
-        if (!waited && key0 + BN > p_safe) { pdl_wait(); waited = true; }
+        if (has_draft && i == 0) {  // staged by the softmax warps (bar_draft); this arrive only keeps the phases aligned
+          mbar_arrive(bar_kv_full);
+          continue;
+        }
+        const int key0 = tile_of(i) * BN;
+        // fused mode: every TMA tile lies below P (a ragged last tile drags in rows >= P that are stale or being
+        // appended by this very launch - finite bf16 either way, and masked), nothing to wait for
+        if (!fused && !waited && key0 + BN > p_safe) { pdl_wait(); waited = true; }
         mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
         const uint32_t kd = base + SMEM_K + s * TILE_BYTES, vd = base + SMEM_V + s * TILE_BYTES;
@@ -306,6 +344,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       auto issue_qk = [&](int i) {
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         mbar_wait(bar_kv_full + 8 * s, ph);
+        if (has_draft && i == 0) mbar_wait(bar_draft, 0);
         tc_fence_after();
         const uint32_t qa = base + SMEM_Q, ka = base + SMEM_K + s * TILE_BYTES;
         const uint32_t d = tmem + ((i & 1) ? TM_S1 : TM_S0);
@@ -339,11 +378,30 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     }
     __syncwarp();
     if (ns > 1) { barrier_a(); cluster_sync_all(); }
+  } else if (fused && !warp_active) {
+    // ================================================================ idle softmax warps of a 64-row tile, fused mode:
+    // they zero the draft tile's key rows 64..127 (never live when the tile holds 64 nodes)
+    if (has_draft) {
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = half * SUB + row * 128 + ((ch ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4 *>(sm + SMEM_K + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(sm + SMEM_V + off) = make_uint4(0, 0, 0, 0);
+      }
+      fence_async_smem();
+      mbar_arrive(bar_draft);
+    }
+    if (ns > 1) { barrier_a(); cluster_sync_all(); }
   } else if (warp_active) {
     // ================================================================ softmax + accumulate
     // two threads per row: `half` selects 64 of the 128 S columns (keys) and 64 of the 128 O columns (head dim)
-    pdl_wait();  // Q below is the predecessor's output
-    {
+    pdl_wait();  // Q (or, fused, the projection output) below is the predecessor's output
+    unsigned long long mrow[2] = {0ull, 0ull};
+    if (row_live) {
+      mrow[0] = p.mask[(row0 + node) * p.mask_words];
+      if (p.mask_words > 1) mrow[1] = p.mask[(row0 + node) * p.mask_words + 1];
+    }
+    if (!fused) {
       uint4 qv[8];  // Q row -> shared memory (UMMA K-major SWIZZLE_128B); each half loads one 64-wide d sub-tile
       const bool have = hs < p.heads_per_cta && node < n;
       const uint4 *src = reinterpret_cast<const uint4 *>(p.q + ((row0 + node) * p.n_q_heads + hq0 + hs) * HD) + half * 8;
@@ -354,22 +412,89 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         *reinterpret_cast<uint4 *>(sm + SMEM_Q + half * SUB + row * 128 + ((ch ^ (row & 7)) << 4)) = qv[ch];
       fence_async_smem();
       mbar_arrive(bar_q_full);
+    } else {
+      // RoPE at the node's position = rowsum(mask) - 1 (modeling_llama.py:587): visible prefix + tree depth
+      int pos = (P > pad_len ? P - pad_len : 0) + __popcll(mrow[0]) + __popcll(mrow[1]) - 1;
+      pos = pos < 0 ? 0 : (pos >= p.max_pos ? p.max_pos - 1 : pos);
+      const uint4 *cs = reinterpret_cast<const uint4 *>(p.cos_t + (long long)pos * (HD / 2));
+      const uint4 *sn = reinterpret_cast<const uint4 *>(p.sin_t + (long long)pos * (HD / 2));
+      const long long row_elems = (long long)(p.n_q_heads + 2 * p.n_kv_heads) * HD;
+      const __nv_bfloat16 *xr = p.qkv + (row0 + node) * row_elems;
+      const bool have = hs < p.heads_per_cta && node < n;
+      // All global loads of a batch are issued (read-only path: the compiler may not move plain loads across the shared
+      // memory stores in between, and eight dependent load rounds of ~0.7 us each would serialise the prologue) before
+      // the first value is used; four 16-byte chunks per batch bound the registers.
+      {  // Q: rotate this thread's 64-wide half (the other half of the head is the rotation partner)
+        const uint4 *qa = reinterpret_cast<const uint4 *>(xr + (long long)(hq0 + hs) * HD) + half * 8;
+        const uint4 *qb = reinterpret_cast<const uint4 *>(xr + (long long)(hq0 + hs) * HD) + (half ^ 1) * 8;
+#pragma unroll
+        for (int b4 = 0; b4 < 2; ++b4) {
+          uint4 ra[4], rb[4], rc[4], rs[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = b4 * 4 + j;
+            if (have) { ra[j] = __ldg(qa + ch); rb[j] = __ldg(qb + ch); rc[j] = __ldg(cs + ch); rs[j] = __ldg(sn + ch); }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = b4 * 4 + j;
+            const uint4 o = have ? rope8(ra[j], rb[j], rc[j], rs[j], half == 0) : make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(sm + SMEM_Q + half * SUB + row * 128 + ((ch ^ (row & 7)) << 4)) = o;
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(bar_q_full);
+      }
+      if (has_draft) {
+        // the draft tile (ring slot 0): key row r = draft node r, K rotated at r's position, V as projected; rows that
+        // hold no node are zero.  The threads of the tile's first head (hs == 0: row == node) own the key rows; one CTA
+        // per KV head also appends the rows to the cache for the steps to come (pretrained_model.py: the reference's
+        // torch.cat of past and new K/V, modeling_llama.py:265-268)
+        const bool key_row = hs == 0 && node < n;
+        const bool writer = (hq0 % (p.n_q_heads / p.n_kv_heads)) == 0;
+        const uint4 *ka = reinterpret_cast<const uint4 *>(xr + (long long)(p.n_q_heads + hkv) * HD) + half * 8;
+        const uint4 *kb = reinterpret_cast<const uint4 *>(xr + (long long)(p.n_q_heads + hkv) * HD) + (half ^ 1) * 8;
+        const uint4 *va = reinterpret_cast<const uint4 *>(xr + (long long)(p.n_q_heads + p.n_kv_heads + hkv) * HD) + half * 8;
+        const long long crow = (long long)slot * p.sl.kv_slot_stride + ((long long)hkv * p.max_seq + P + node) * HD + half * 64;
+        uint4 *kdst = reinterpret_cast<uint4 *>(p.kc_layer + crow), *vdst = reinterpret_cast<uint4 *>(p.vc_layer + crow);
+#pragma unroll
+        for (int b4 = 0; b4 < 2; ++b4) {
+          uint4 ra[4], rb[4], rc[4], rs[4], rv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = b4 * 4 + j;
+            if (key_row) {
+              ra[j] = __ldg(ka + ch); rb[j] = __ldg(kb + ch); rc[j] = __ldg(cs + ch); rs[j] = __ldg(sn + ch);
+              rv[j] = __ldg(va + ch);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ch = b4 * 4 + j;
+            const uint32_t off = half * SUB + row * 128 + ((ch ^ (row & 7)) << 4);
+            uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
+            if (key_row) { ko = rope8(ra[j], rb[j], rc[j], rs[j], half == 0); vo = rv[j]; }
+            *reinterpret_cast<uint4 *>(sm + SMEM_K + off) = ko;
+            *reinterpret_cast<uint4 *>(sm + SMEM_V + off) = vo;
+            if (key_row && writer) { kdst[ch] = ko; vdst[ch] = vo; }
+          }
+        }
+        fence_async_smem();
+        mbar_arrive(bar_draft);
+      }
     }
     if (row == 0 && half == 0) DBG(5);
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const int pair_bar = 1 + (warp & 3);  // named barrier shared by the two warps of this lane quadrant
-    unsigned long long mrow[2] = {0ull, 0ull};
-    if (row_live) {
-      mrow[0] = p.mask[(row0 + node) * p.mask_words];
-      if (p.mask_words > 1) mrow[1] = p.mask[(row0 + node) * p.mask_words + 1];
-    }
     float acc[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) acc[j] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     uint32_t sv[64];
     for (int i = 0; i < ntile; ++i) {
-      const int key0 = (t0 + i) * BN + half * 64;
+      const int tl = tile_of(i);
+      const bool is_draft = fused && tl == Tp;
+      const int key0 = tl * BN + half * 64;
       const uint32_t s_addr = tmem + lane_addr + ((i & 1) ? TM_S1 : TM_S0) + half * 64;
       mbar_wait(bar_s_full + 8 * (i & 1), (i >> 1) & 1);
       tc_fence_after();
@@ -379,15 +504,24 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       tmem_ld_wait();
       // 32-bit visibility word of keys [kb, kb+32): prefix keys [pad_len, P) are visible to every row, the n draft
       // keys follow the row's ancestor bits (bits beyond the live nodes are never set in the trie's mask rows)
-      const bool all_visible = ((t0 + i) * BN >= pad_len) && ((t0 + i) * BN + BN <= P);
+      const bool all_visible = !is_draft && (tl * BN >= pad_len) && (tl * BN + BN <= P);
       auto vis32 = [&](int kb) -> uint32_t {
         if (all_visible) return 0xffffffffu;
+        if (is_draft) {  // key kb - Tp * BN is draft node j0: visible iff it is an ancestor (or the node itself)
+          const int j0 = kb - Tp * BN;
+          if (j0 < 64) {
+            unsigned long long x = mrow[0] >> j0;
+            if (j0 > 32) x |= mrow[1] << (64 - j0);
+            return (uint32_t)x;
+          }
+          return (uint32_t)(mrow[1] >> (j0 - 64));
+        }
         uint32_t m = 0;
         const int lo = kb < pad_len ? pad_len : kb;
         const int hi = kb + 32 < P ? kb + 32 : P;
         if (hi > lo) m = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u)) << (lo - kb);
         const int j0 = kb - P;
-        if (j0 + 32 > 0 && j0 < n) {
+        if (!fused && j0 + 32 > 0 && j0 < n) {
           uint32_t d;
           if (j0 < 0) d = (uint32_t)(mrow[0] << (-j0));
           else if (j0 < 64) {
@@ -565,6 +699,7 @@ struct pia_attn_plan {
   CUtensorMap map_k, map_v;
   int heads_per_cta, n_groups, n_split, mask_words, tiles_per_cta;
   unsigned long long *dbg;
+  __nv_bfloat16 *k_base, *v_base;  // the caches the TMA maps describe (fused mode appends the draft rows itself)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -626,6 +761,7 @@ extern "C" int pia_attn_plan_create(const pia_attn_config_t *cfg, void *d_k_cach
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); rc = PIA_ERR_CUDA; }
   }
   p->dbg = nullptr;
+  p->k_base = (__nv_bfloat16 *)d_k_cache; p->v_base = (__nv_bfloat16 *)d_v_cache;
   if (rc != PIA_OK) { delete p; return rc; }
   *out = p;
   return PIA_OK;
@@ -647,9 +783,11 @@ extern "C" int pia_attn_plan_destroy(pia_attn_plan_t *p) {
   return PIA_OK;
 }
 
-extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask,
-                                 const pia_slots_t *slots, float scale_mul, void *d_out, void *stream) {
-  PIA_REQUIRE(p && d_q && d_mask && slots && slots->d_n && slots->d_prefix_len && d_out, "null argument");
+static int attn_launch(pia_attn_plan_t *p, int layer, const void *d_q, const void *d_qkv, const void *d_cos,
+                       const void *d_sin, int max_pos, const uint64_t *d_mask, const pia_slots_t *slots, float scale_mul,
+                       void *d_out, void *stream) {
+  const bool fused = d_qkv != nullptr;
+  PIA_REQUIRE(p && (d_q || d_qkv) && d_mask && slots && slots->d_n && slots->d_prefix_len && d_out, "null argument");
   PIA_REQUIRE(layer >= 0 && layer < p->cfg.n_layers, "layer %d outside [0,%d)", layer, p->cfg.n_layers);
   PIA_REQUIRE(slots->batch >= 1 && slots->batch <= 65535 && slots->rows_per_slot >= 1 &&
                   slots->rows_per_slot <= p->cfg.max_nodes, "bad slot table");
@@ -659,6 +797,11 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   PIA_REQUIRE(slots->kv_slot_stride == 0 || (slots->kv_slot_stride == cache_elems &&
                                               slots->kv_first_slot + slots->batch <= plan_slots),
               "kv_slot_stride must be 0 or one whole cache, and the plan must span `batch` caches");
+  // fused mode appends the draft rows of every slot from inside the launch: slots that share one cache (the chain
+  // chunks of a prefill pass) would read rows their neighbours are still writing - they take the two-kernel path
+  PIA_REQUIRE(!fused || slots->batch == 1 || slots->kv_slot_stride != 0,
+              "the fused RoPE / KV-append attention needs one cache per slot");
+  PIA_REQUIRE(!fused || (d_cos && d_sin && max_pos > 0), "fused mode needs the RoPE tables");
   Params a;
   a.q = (const __nv_bfloat16 *)d_q;
   a.mask = (const unsigned long long *)d_mask;
@@ -673,10 +816,29 @@ extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q,
   if (ns < 1) ns = 1;
   a.n_split = ns; a.tiles_per_cta = p->tiles_per_cta;
   a.out = (__nv_bfloat16 *)d_out; a.dbg = p->dbg;
+  a.fused = fused ? 1 : 0;
+  a.qkv = (const __nv_bfloat16 *)d_qkv; a.cos_t = (const __nv_bfloat16 *)d_cos; a.sin_t = (const __nv_bfloat16 *)d_sin;
+  a.max_pos = max_pos;
+  const long long layer_off = ((long long)slots->kv_first_slot * p->cfg.n_layers + layer) * p->cfg.n_kv_heads *
+                              (long long)p->cfg.max_seq * p->cfg.head_dim;
+  a.kc_layer = p->k_base + layer_off; a.vc_layer = p->v_base + layer_off;
   a.scale_log2 = scale_mul * 1.4426950408889634f / sqrtf((float)HD);
   cudaStream_t s = (cudaStream_t)stream;
   PIA_CUDA_CHECK(launch_kernel_cluster(k_tree_attn, dim3(ns, p->n_groups, slots->batch), dim3(NTHREADS), SMEM_TOTAL, s,
                                        (unsigned)ns, p->map_k, p->map_v, a));
   count_launch();
   return PIA_OK;
+}
+
+extern "C" int pia_tree_attn_fwd(pia_attn_plan_t *p, int layer, const void *d_q, const uint64_t *d_mask,
+                                 const pia_slots_t *slots, float scale_mul, void *d_out, void *stream) {
+  PIA_REQUIRE(d_q, "null q");
+  return attn_launch(p, layer, d_q, nullptr, nullptr, nullptr, 0, d_mask, slots, scale_mul, d_out, stream);
+}
+
+extern "C" int pia_tree_attn_fused_fwd(pia_attn_plan_t *p, int layer, const void *d_qkv, const void *d_cos,
+                                       const void *d_sin, int max_pos, const uint64_t *d_mask, const pia_slots_t *slots,
+                                       float scale_mul, void *d_out, void *stream) {
+  PIA_REQUIRE(d_qkv, "null qkv");
+  return attn_launch(p, layer, nullptr, d_qkv, d_cos, d_sin, max_pos, d_mask, slots, scale_mul, d_out, stream);
 }

@@ -333,6 +333,8 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
         ops.embed_gather(self.model.embed_tokens.weight, b.ids, b.n_total, b.h)
         plans = self._gemm_plans(rt) if b is rt.decode_bufs else False
         pf = self._prefetch_cfg(rt) if plans else False
+        fused_attn = b is rt.decode_bufs and os.environ.get('PIA_ATTN_FUSED', '0') != '0' and \
+            (b.slots.batch == 1 or b.slots.kv_slot_stride != 0)
         x, parts, resid_in = b.h, None, None  # norm(x | parts, resid_in) -> (resid = x + resid_in, y = norm(resid))
 
         def norm(w):
@@ -354,9 +356,12 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
                 self._prefetch(pf, [(a.o_proj.weight, pf['o'], 0),
                                     (gw, pf['gate_up'], gw.shape[1] * gw.shape[2] * gw.shape[3] * 2 if gw.dim() == 4 else 0)])
             # every request slot / prefill chunk of the table in one launch each (pia_slots_t)
-            ops.rope_kv_append(b.qkv, b.mask, b.slots, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], rt.rope_cos,
-                               rt.rope_sin, b.q, rt.k_layer(li, b.kv_slot), rt.v_layer(li, b.kv_slot), rt.max_seq)
-            rt.plan.forward(li, b.q, b.mask, b.slots, b.attn)
+            if fused_attn:   # decode steps: RoPE + KV append happen inside the attention kernel
+                rt.plan.forward_fused(li, b.qkv, b.mask, b.slots, rt.rope_cos, rt.rope_sin, b.attn)
+            else:            # prefill chunks share one cache: append first, then attend
+                ops.rope_kv_append(b.qkv, b.mask, b.slots, g['n_q_heads'], g['n_kv_heads'], g['head_dim'], rt.rope_cos,
+                                   rt.rope_sin, b.q, rt.k_layer(li, b.kv_slot), rt.v_layer(li, b.kv_slot), rt.max_seq)
+                rt.plan.forward(li, b.q, b.mask, b.slots, b.attn)
             if lp and 'o' in lp:
                 o = lp['o'].run(64)
                 x, parts, resid_in = (o, None, b.resid) if lp['o'].splits == 1 else (None, o, b.resid)

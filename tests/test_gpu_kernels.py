@@ -309,6 +309,56 @@ def test_batched_slots_rope_and_attention(Hq, Hkv, rps, cases):
             assert torch.allclose(ob[r0:r0 + n].float(), ref, atol=1.5e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize('Hq,Hkv,rps,cases', [
+    (32, 32, 64, [(64, 384, 0)]),                                  # the benchmark's mid-generation step, MHA
+    (32, 8, 64, [(47, 1000, 5)]),                                  # GQA-4, ragged draft, left padding
+    (8, 8, 64, [(1, 130, 0)]),                                     # a root-only draft right after a tile boundary
+    (4, 2, 64, [(33, 0, 0)]),                                      # empty cache: the draft tile is the only tile
+    (32, 8, 8, [(8, 300, 0), (3, 290, 0), (8, 310, 2), (1, 5, 0), (7, 128, 0), (8, 64, 0), (2, 500, 0), (6, 301, 0)]),
+    (32, 32, 64, [(64, 2500, 0)])])                                # several prefix tiles per CTA behind the draft tile
+def test_fused_rope_kv_append_attention(Hq, Hkv, rps, cases):
+    """pia_tree_attn_fused_fwd (RoPE + KV append + tree attention in one launch; draft keys staged in shared memory,
+    TMA only over the cached prefix) against the two-kernel path pia_rope_kv_append + pia_tree_attn_fwd on the same
+    inputs: the cache rows it appends are bit identical (and nothing else in the cache moves), the attention output
+    agrees to the fp32 summation order of the tiles, and with the fp32 reference"""
+    from painlessinferenceacceleration_b200.common import ops
+    rng = np.random.default_rng(Hq + rps)
+    torch.manual_seed(Hq * 3 + rps)
+    D, R, n_layers, B = 128, 64, 2, len(cases)
+    max_seq = max(P + n for n, P, _ in cases) + 70
+    kc = (torch.randn((B, n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    vc = (torch.randn((B, n_layers, Hkv, max_seq, D), device=DEV) * 0.7).to(torch.bfloat16)
+    qkv = torch.randn((R, (Hq + 2 * Hkv) * D), device=DEV).to(torch.bfloat16)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=DEV).float() / D))
+    ang = torch.arange(max_seq + 8, device=DEV).float()[:, None] * inv[None]
+    cos, sin = ang.cos().to(torch.bfloat16).contiguous(), ang.sin().to(torch.bfloat16).contiguous()
+    mask = torch.zeros((R, 1), dtype=torch.int64, device=DEV)
+    trees = []
+    for s_, (n, P, pad) in enumerate(cases):
+        rows = _random_tree(rng, n)[2]
+        trees.append(rows)
+        mask[s_ * rps:s_ * rps + n, 0] = torch.from_numpy(rows.view(np.int64)).to(DEV)
+    ns, Ps, pads = [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases]
+    layer = 1
+    k2, v2 = kc.clone(), vc.clone()
+    plan, plan2 = ops.AttnPlan(kc, vc, Hq, Hkv, D, R), ops.AttnPlan(k2, v2, Hq, Hkv, D, R)
+    sl = _slots(ns, Ps, pads, rps, stride=plan.slot_stride if B > 1 else 0)
+    q = torch.zeros((R, Hq, D), dtype=torch.bfloat16, device=DEV)
+    o1 = torch.full((R, Hq, D), 9.0, dtype=torch.bfloat16, device=DEV)
+    o2 = torch.full((R, Hq, D), 9.0, dtype=torch.bfloat16, device=DEV)
+    ops.rope_kv_append(qkv, mask, sl, Hq, Hkv, D, cos, sin, q, kc[0, layer], vc[0, layer], max_seq)
+    plan.forward(layer, q, mask, sl, o1)
+    plan2.forward_fused(layer, qkv, mask, sl, cos, sin, o2)
+    torch.cuda.synchronize()
+    assert torch.equal(k2, kc) and torch.equal(v2, vc)
+    for s_, (n, P, pad) in enumerate(cases):
+        r0 = s_ * rps
+        assert torch.allclose(o2[r0:r0 + n].float(), o1[r0:r0 + n].float(), atol=4e-3, rtol=2e-2), s_
+        assert float((o2[r0 + n:r0 + rps].float() - 9.0).abs().sum()) == 0      # rows beyond the draft: untouched
+        ref = _ref_attention(q[r0:], kc[s_, layer], vc[s_, layer], trees[s_], n, P, pad, Hq // Hkv)
+        assert torch.allclose(o2[r0:r0 + n].float(), ref, atol=1.5e-2, rtol=2e-2), s_
+
+
 def test_prefill_chunks_share_one_cache():
     """a prefill pass = one table slot per 64-row chain chunk over the SAME cache (kv_slot_stride 0): chunk c must see
     the rows chunk c-1 appended in the same launch sequence; equals feeding the chunks one after the other"""
