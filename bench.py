@@ -485,9 +485,22 @@ def attention_roofline_long(dev, P=3968, n=DL, hq=32, hkv=32, layers=4):
             'shape': f'n={n} P={P} Hq={hq} Hkv={hkv} D={D}', 'peak_source': src}
 
 
-def _forest(dev, n_docs):
+def _forest(dev, n_docs, full_walk=False):
+    """full_walk: a handle whose queries visit the whole matched subtree like the reference (PIA_TRIE_PRUNE=0 is read
+    when the handle is created) - used once to count the algorithmic bytes of the scan"""
     from painlessinferenceacceleration_b200.common.lookahead_cache import LookaheadCache
-    c = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=32000, node_capacity=1 << 23, max_resident_queries=592)
+    old = os.environ.get('PIA_TRIE_PRUNE')
+    if full_walk:
+        os.environ['PIA_TRIE_PRUNE'] = '0'
+    try:
+        c = LookaheadCache(eos_ids=[2], device=dev, vocab_capacity=32000, node_capacity=1 << 23,
+                           max_resident_queries=592)
+    finally:
+        if full_walk:
+            if old is None:
+                del os.environ['PIA_TRIE_PRUNE']
+            else:
+                os.environ['PIA_TRIE_PRUNE'] = old
     docs = phrase_bank_prompts(n_docs, 32000, length=256, seed=7)
     for d in docs:
         c.put(d, branch_length=9, mode='output', idx=-1)
@@ -496,7 +509,9 @@ def _forest(dev, n_docs):
 
 def trie_roofline(dev, n_docs=1500, n_queries=4096):
     """batched synthetic scan of SURVEY.md 8d: forest grown from phrase-bank documents, 4096 concurrent hier_get
-    queries; bytes = node records (32 B) + child entries (8 B) actually visited, counted by the kernel."""
+    queries.  ALGORITHMIC bytes (matched subtree x node record) = node records (32 B) + child entries
+    (8 B) the reference's full walk of every matched subtree visits, counted by the kernel on a handle with the pruned
+    walk switched off; `bytes_visited_per_launch` is what the timed (pruned) kernel really read."""
     import torch
     from painlessinferenceacceleration_b200 import _lib as L
     c, docs = _forest(dev, n_docs)
@@ -511,7 +526,7 @@ def trie_roofline(dev, n_docs=1500, n_queries=4096):
     dl = torch.full((n_queries,), 2, dtype=torch.int32, device=dev)
     o = t.out_buffers(n_queries, 64)
 
-    def launch():
+    def launch(t=t):
         L.check(t.lib.pia_trie_get(t.h, dq.data_ptr(), dl.data_ptr(), n_queries, 2, 2, None, 0, 64, 8, 0, 32,
                                    L.MODE['mix'], L.GET_HIER, 0, 0, None, o['ids'].data_ptr(), o['mask'].data_ptr(),
                                    o['n'].data_ptr(), o['sizes'].data_ptr(), o['nsizes'].data_ptr(),
@@ -531,13 +546,27 @@ def trie_roofline(dev, n_docs=1500, n_queries=4096):
         times.append(e0.elapsed_time(e1))
     s1 = c.stats()
     ms = float(np.median(times))
-    by = ((s1['nodes_visited'] - s0['nodes_visited']) * 32 + (s1['edges_visited'] - s0['edges_visited']) * 8) / 5.0
-    by += n_queries * (64 * 4 + 64 * 8)
+    out_bytes = n_queries * (64 * 4 + 64 * 8)
+    visited = ((s1['nodes_visited'] - s0['nodes_visited']) * 32 + (s1['edges_visited'] - s0['edges_visited']) * 8) / 5.0
+    visited += out_bytes
+    mean_draft = float(o['n'].float().mean())
+    ids_pruned = o['ids'].clone()
+    n_pruned = o['n'].clone()
+    del c
+    cf, _ = _forest(dev, n_docs, full_walk=True)   # same forest, full walks: the algorithmic byte count (untimed)
+    f0 = cf.stats()
+    launch(cf._t)
+    torch.cuda.synchronize()
+    f1 = cf.stats()
+    by = (f1['nodes_visited'] - f0['nodes_visited']) * 32 + (f1['edges_visited'] - f0['edges_visited']) * 8 + out_bytes
+    same = bool(torch.equal(n_pruned, o['n']) and torch.equal(ids_pruned, o['ids']))
     hbm, _tf, src = peaks()
     ach = by / (ms * 1e-3) / 1e9
     return {'kernel': 'k_get<64,16> (4096 hier_get rows)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm, 'unit': 'GB/s',
-            'frac': ach / hbm, 'traffic': ncu_traffic('prof_trie_batch', 'k_get'), 'bytes_per_launch': by, 'ms_per_launch': ms,
-            'forest_nodes': s1['nodes_used'], 'mean_draft': float(o['n'].float().mean()), 'peak_source': src}
+            'frac': ach / hbm, 'traffic': ncu_traffic('prof_trie_batch', 'k_get'), 'bytes_per_launch': by,
+            'bytes_visited_per_launch': visited, 'achieved_on_visited_bytes': visited / (ms * 1e-3) / 1e9,
+            'pruned_walk_equals_full_walk': same, 'ms_per_launch': ms, 'us_per_get': ms * 1e3 / n_queries,
+            'forest_nodes': s1['nodes_used'], 'mean_draft': mean_draft, 'peak_source': src}
 
 
 def trie_counters(dev, n_docs=200, n_ops=200):

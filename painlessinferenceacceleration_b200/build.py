@@ -7,10 +7,10 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, 'csrc')
-SO = os.path.join(PKG, 'libpia_b200.so')
+SO = os.environ.get('PIA_B200_LIB') or os.path.join(PKG, 'libpia_b200.so')   # override: diagnostic builds
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr'] + os.environ.get('PIA_NVCC_EXTRA', '').split()
 
 
 def sources():

@@ -18,6 +18,7 @@
 //          k_get (hier_get / one_get -> Tree.get :65-144, 224-293, 171-222),
 //          k_reset_input (:320-333, 566-570), k_squeeze (:295-318, 572-576), k_fresh (:563-564).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -51,6 +52,7 @@ struct Hdr {
   int get_ticket, get_done;  // dynamic row scheduling of batched k_get (self-resetting)
 };
 
+
 struct Dev {
   Node *nodes;
   int2 *edges;
@@ -70,6 +72,15 @@ struct Dev {
 constexpr int ERR_NODE_POOL = 1, ERR_EDGE_POOL = 2, ERR_FRONTIER = 4, ERR_OUTBUF = 8, ERR_HIST = 16, ERR_TOKEN = 32;
 constexpr int FLAG_UPD = 1, FLAG_UPDIN = 2;
 constexpr int NT = 256;  // threads per CTA of every trie kernel
+
+// -DPIA_TRIE_PHASES: the leader's thread 0 prints the nanoseconds between the phases of one tree_get (diagnostic builds
+// only: scripts/time_trie_get.py)
+#ifdef PIA_TRIE_PHASES
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PHASE(i) do { if (threadIdx.x == 0 && rank == 0) ph[i] = gtime(); } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ float load_fi(const Dev &D, const Node &nd, int id, int idx) {
   return idx == 0 ? nd.fi : D.fi_extra[(long long)(idx - 1) * D.node_cap + id];
@@ -332,100 +343,185 @@ __global__ void k_put_finish(Dev D, int B, int final, int slot, const int *d_slo
 }
 
 // ---------------------------------------------------------------------------------------------------
-// CTA-wide breadth-first walk below `start`; visit(id, node) -> descend?
+// Breadth-first walk below `start`; visit(id, node) -> descend?   One CTA, or the CL CTAs of a thread-block cluster
+// working on the same frontier (a hot subtree is a latency problem: ~3 dependent memory round trips per node, so the
+// cure is more loads in flight than one SM's 256 threads can hold).
+//   * the level counters live in the LEADER CTA's shared memory (`sh`, a generic pointer that is a distributed-
+//     shared-memory address for the other ranks); every warp reserves its slice of the next level with one atomic;
+//   * CL == 1: the first SFR entries of every level stay in shared memory (`sfr`), only larger levels touch the
+//     per-CTA region in HBM - cold queries (a few hundred nodes) never write global memory;
+//   * CL > 1: the frontier is the leader's region in global memory, written/read through L2 (st.cg / ld.cg), one
+//     cluster barrier (release/acquire) per level.
 // ---------------------------------------------------------------------------------------------------
 struct BfsShared { int next_cnt[3]; int err; };  // three rotating level counters: one barrier per BFS level
+constexpr int BFS_U = 4;                         // frontier entries per thread and round
+static_assert(NT * BFS_U == 1024, "bfs_below searches its expansion table in 10 steps");
+struct ExpandTab { int start[NT * BFS_U + 1]; int src[NT * BFS_U]; int wsum[NT / 32]; int rbase; };  // see bfs_below
+constexpr int SFR = 1024;                        // shared-memory frontier entries per buffer (CL == 1)
 
-template <class Visit>
-__device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, BfsShared *sh, Visit &&visit,
-                          unsigned long long &nv, unsigned long long &ne) {
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// generic address of `p` (a generic pointer into this CTA's shared memory) in CTA `rank` of the cluster
+template <class T>
+__device__ __forceinline__ T *map_to_rank(T *p, unsigned rank) {
+  unsigned long long r;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"((unsigned long long)p), "r"(rank));
+  return reinterpret_cast<T *>(r);
+}
+
+// node records and child entries are read-only while a query kernel runs: the non-coherent path lets the compiler keep
+// several of them in flight across the frontier stores in between
+template <bool RO>
+__device__ __forceinline__ Node load_node(const Node *p) {
+  if (!RO) return *p;  // walks that modify the records they visit (reset_input_freqs) use coherent loads
+  union { Node n; uint4 v[2]; } u;
+  u.v[0] = __ldg(reinterpret_cast<const uint4 *>(p));
+  u.v[1] = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+  return u.n;
+}
+
+struct Frontier {
+  int *g;  // global region (fr_cap entries)
+  int *s;  // shared-memory head (SFR entries) or nullptr
+  __device__ __forceinline__ int get(int e) const { return (s != nullptr && e < SFR) ? s[e] : __ldcg(g + e); }
+  __device__ __forceinline__ void put(int e, int v) const { if (s != nullptr && e < SFR) s[e] = v; else __stcg(g + e, v); }
+};
+
+// level_end() runs in every thread (uniform) between two levels, after the level barrier: the query walk uses it to
+// tighten its pruning thresholds (CL == 1 only).
+template <bool RO, class Visit, class LevelEnd>
+__device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int *fr1, int *sfr, ExpandTab *xt,
+                                          BfsShared *sh, int CL, int rank, Visit &&visit, LevelEnd &&level_end,
+                                          unsigned long long &nv,
+                                          unsigned long long &ne) {
   const int tid = threadIdx.x, lane = lane_id();
-  const Node s = D.nodes[start];
-  if (tid == 0) { sh->next_cnt[0] = 0; sh->next_cnt[1] = 0; sh->next_cnt[2] = 0; }
+  auto sync_all = [&]() { if (CL > 1) cluster_sync_all(); else __syncthreads(); };
+  const Node s = load_node<RO>(D.nodes + start);
+  if (rank == 0 && tid == 0) { sh->next_cnt[0] = 0; sh->next_cnt[1] = 0; sh->next_cnt[2] = 0; }
+  Frontier cur = {fr0, sfr}, nxt = {fr1, sfr ? sfr + SFR : nullptr};
   int cnt = s.n_child;
   if (s.cap == 0) {
-    if (tid == 0 && cnt == 1) fr0[0] = s.child;
+    if (rank == 0 && tid == 0 && cnt == 1) cur.put(0, s.child);
   } else {
-    if (cnt > D.fr_cap) { if (tid == 0) atomicOr(&sh->err, ERR_FRONTIER); cnt = 0; }
-    for (int i = tid; i < cnt; i += NT) fr0[i] = D.edges[s.child + i].y;
-    if (tid == 0) ne += cnt;
+    if (cnt > D.fr_cap) { if (rank == 0 && tid == 0) atomicOr(&sh->err, ERR_FRONTIER); cnt = 0; }
+    for (int i0 = rank * NT + tid; i0 < cnt; i0 += 4 * CL * NT) {  // four child entries in flight per thread
+      int c[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int i = i0 + j * CL * NT; c[j] = i < cnt ? __ldg(&D.edges[s.child + i].y) : 0; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int i = i0 + j * CL * NT; if (i < cnt) cur.put(i, c[j]); }
+    }
+    if (rank == 0 && tid == 0) ne += cnt;
   }
-  __syncthreads();
-  int *cur = fr0, *nxt = fr1;
+  sync_all();
+#ifdef PIA_TRIE_PHASES
+  __shared__ unsigned long long lv_t[16], lv_e[16];
+  __shared__ int lv_c[16], lv_n;
+  if (tid == 0) { lv_e[0] = gtime(); lv_n = 1; }
+#endif
   for (int level = 0; cnt > 0; ++level) {
     int *push_cnt = &sh->next_cnt[(level + 1) % 3];
-    if (tid == 0) sh->next_cnt[(level + 2) % 3] = 0;  // the counter of the level after next: idle during this level
+    if (rank == 0 && tid == 0) sh->next_cnt[(level + 2) % 3] = 0;  // the counter of the level after next: idle during this level
     // U frontier entries per thread and iteration: the U node records (dependent on the U frontier loads) are all in
     // flight before the first is inspected - one record per thread at a time left a hot subtree latency-bound
-    constexpr int U = 2;
-    for (int base = 0; base < cnt; base += NT * U) {
+    constexpr int U = BFS_U;
+    for (int base = rank * NT * U; base < cnt; base += CL * NT * U) {
       int id[U], push[U];
       Node nd[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int e = base + u * NT + tid;
-        id[u] = e < cnt ? cur[e] : -1;
+        id[u] = e < cnt ? cur.get(e) : -1;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (id[u] >= 0) nd[u] = D.nodes[id[u]];
+        if (id[u] >= 0) nd[u] = load_node<RO>(D.nodes + id[u]);
         else { nd[u].child = -1; nd[u].cap = 0; nd[u].n_child = 0; }
       }
-      int many = 0, ones = 0;  // entries this thread appends: single-child (inline) nodes / expanded child blocks
+      // visit() is called by every lane (valid or not): it may use warp collectives
+      int mine = 0;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        push[u] = 0;
-        if (id[u] >= 0) {
-          ++nv;
-          if (visit(id[u], nd[u]) && nd[u].n_child > 0) push[u] = nd[u].n_child;
-        }
-        if (push[u] == 1 && nd[u].cap == 0) ++ones; else many += push[u];
+        const bool valid = id[u] >= 0;
+        if (valid) ++nv;
+        const bool descend = visit(id[u], nd[u], valid);
+        push[u] = (valid && descend && nd[u].n_child > 0) ? nd[u].n_child : 0;
+        mine += push[u];
       }
-      // frontier reservation: one warp scan + one atomic per iteration for all U entries of every lane
-      const int mine = ones + many;
-      const unsigned any = __ballot_sync(FULL, mine > 0);
-      if (any == 0) continue;  // warp-uniform
+      // Load-balanced expansion.  The CTA reserves one slice [rbase, rbase + total) of the next level per round (block
+      // scan + one atomic) and fills it with all threads, flat index by flat index: each (thread, u) entry publishes
+      // where its children start in the slice and where they come from (the inline child, or its block of child
+      // entries), a flat index finds its entry by binary search.  A hot node with hundreds of children no longer
+      // serialises the level behind one lane or one warp, four child entries are in flight per thread, stores are
+      // contiguous.
       int incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      const int total = __shfl_sync(FULL, incl, 31);
-      int wbase = 0;
-      if (lane == 0) wbase = atomicAdd(push_cnt, total);
-      wbase = __shfl_sync(FULL, wbase, 0);
-      if (wbase + total > D.fr_cap) {
-        if (lane == 0) atomicOr(&sh->err, ERR_FRONTIER);
-      } else {
-        int pos = wbase + incl - mine;
+      if (lane == 31) xt->wsum[warp_id()] = incl;
+      __syncthreads();
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < NT / 32; ++w2) { const int v = xt->wsum[w2]; if (w2 < warp_id()) woff += v; total += v; }
+      if (tid == 0) xt->rbase = total > 0 ? atomicAdd(push_cnt, total) : 0;
+      {
+        int off = woff + incl - mine;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool one = push[u] == 1 && nd[u].cap == 0;
-          // child blocks of >= 32 entries (the hot nodes of a Zipf vocabulary hold thousands) are copied by the whole
-          // warp, lane-strided; left to the owning lane they serialise the level behind one thread
-          const bool big = !one && push[u] >= 32;
-          if (one) nxt[pos] = nd[u].child;
-          else if (push[u] > 0 && !big) {
-            for (int k = 0; k < push[u]; ++k) nxt[pos + k] = D.edges[nd[u].child + k].y;
-          }
-          unsigned mb = __ballot_sync(FULL, big);
-          while (mb) {
-            const int src = __ffs(mb) - 1;
-            mb &= mb - 1;
-            const int c0 = __shfl_sync(FULL, nd[u].child, src);
-            const int cn = __shfl_sync(FULL, push[u], src);
-            const int p0 = __shfl_sync(FULL, pos, src);
-            for (int k = lane; k < cn; k += 32) nxt[p0 + k] = D.edges[c0 + k].y;
-          }
+          xt->start[tid * U + u] = off;
+          xt->src[tid * U + u] = one ? -(nd[u].child + 1) : nd[u].child;
           if (!one) ne += push[u];
-          pos += push[u];
+          off += push[u];
+        }
+        if (tid == NT - 1) xt->start[NT * U] = total;
+      }
+      __syncthreads();
+      const int rbase = xt->rbase;
+      if (total > 0 && rbase + total > D.fr_cap) {
+        if (tid == 0) atomicOr(&sh->err, ERR_FRONTIER);
+      } else {
+        for (int f0 = 0; f0 < total; f0 += NT * 4) {
+          int val[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int f = f0 + j * NT + tid;
+            val[j] = 0;
+            if (f < total) {
+              int lo = 0, hi = NT * U;  // the entry e with start[e] <= f < start[e + 1] (empty entries never qualify)
+#pragma unroll
+              for (int step = 0; step < 10; ++step) { const int mid = (lo + hi) >> 1; if (xt->start[mid] <= f) lo = mid; else hi = mid; }
+              const int src = xt->src[lo];
+              const int k = f - xt->start[lo];
+              val[j] = src < 0 ? -(src + 1) : (RO ? __ldg(&D.edges[src + k].y) : D.edges[src + k].y);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int f = f0 + j * NT + tid; if (f < total) nxt.put(rbase + f, val[j]); }
         }
       }
+      __syncthreads();  // the table is rewritten by the next round
     }
-    __syncthreads();
+    sync_all();
     cnt = *push_cnt;
     if (cnt > D.fr_cap) cnt = 0;  // overflowed level: err already set
-    int *t = cur; cur = nxt; nxt = t;
+    const Frontier t = cur; cur = nxt; nxt = t;
+#ifdef PIA_TRIE_PHASES
+    if (tid == 0 && rank == 0 && level < 15) { lv_t[level + 1] = gtime(); lv_c[level + 1] = cnt; lv_n = level + 2; }
+#endif
+    if (cnt > 0) level_end(cnt);
+#ifdef PIA_TRIE_PHASES
+    if (tid == 0 && rank == 0 && level < 15) lv_e[level + 1] = gtime();
+#endif
   }
-  __syncthreads();
+  sync_all();
+#ifdef PIA_TRIE_PHASES
+  if (tid == 0 && rank == 0)
+    for (int i = 1; i < lv_n; ++i)
+      printf("  bfs level %d: walk %llu ns, level_end %llu ns, next cnt %d\n", i - 1, lv_t[i] - lv_e[i - 1], lv_e[i] - lv_t[i], lv_c[i]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -433,6 +529,7 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
 // ---------------------------------------------------------------------------------------------------
 constexpr int HCAP = 512;                        // distinct frequency values per histogram
 constexpr unsigned long long HEMPTY = ~0ull;
+static_assert(HCAP % NT == 0, "kth_value compacts with whole warps");
 
 struct Hist { unsigned long long key[HCAP]; unsigned cnt[HCAP]; };
 
@@ -445,36 +542,17 @@ __device__ __forceinline__ void hist_add(Hist *h, unsigned long long bits, unsig
   }
   *ovf = 1;
 }
-// per-thread run-length front end: n-gram counts are overwhelmingly 1.0, so consecutive equal values are
-// accumulated in registers and reach the shared histogram (one contended address otherwise) only on a change
-struct HistRun {
-  unsigned long long key; unsigned cnt;
-  __device__ __forceinline__ void add(Hist *h, unsigned long long bits, int *ovf) {
-    if (cnt && bits == key) { ++cnt; return; }
-    if (cnt) hist_add(h, key, cnt, ovf);
-    key = bits; cnt = 1;
-  }
-  __device__ __forceinline__ void flush(Hist *h, int *ovf) { if (cnt) hist_add(h, key, cnt, ovf); cnt = 0; }
-};
-
-// sorted(values, reverse=True)[rank-1] from the histogram; `found` stays 0 if rank is out of range
-__device__ void hist_kth(const Hist *h, long long rank, unsigned long long *result, int *found) {
-  for (int s = threadIdx.x; s < HCAP; s += NT) {
-    const unsigned long long k = h->key[s];
-    if (k == HEMPTY) continue;
-    long long greater = 0;
-    for (int j = 0; j < HCAP; ++j) {
-      const unsigned long long kj = h->key[j];
-      if (kj != HEMPTY && kj > k) greater += h->cnt[j];
-    }
-    if (greater < rank && rank <= greater + (long long)h->cnt[s]) { *result = k; *found = 1; }
-  }
+// one update per distinct value of a warp (all lanes call; `active` lanes contribute)
+__device__ __forceinline__ void warp_hist_add(Hist *h, unsigned long long bits, bool active, int *ovf) {
+  const unsigned m = __match_any_sync(FULL, active ? bits : HEMPTY);
+  if (active && lane_id() == __ffs(m) - 1) hist_add(h, bits, __popc(m), ovf);
 }
 
 struct GetParams {
   const int *queries, *qlen, *d_idx, *d_max_seq;
   int batch, q_stride, max_query, idx, dl, bl, min_in, min_out, mode, kind, flags, max_seq;
   int *out_ids; unsigned long long *out_mask; int *out_n, *out_sizes, *out_nsizes, *status;
+  int prune;  // 1: the frequency walk may skip subtrees that cannot reach the thresholds (see tree_get)
 };
 
 template <int MAXS, int MAXD>
@@ -493,15 +571,51 @@ struct GetSmem {
   unsigned long long mask[MAXS][(MAXS + 63) / 64];
   int ids[MAXS];
   int q[16];
+  int sfr[2 * SFR];  // shared-memory head of the two BFS frontiers
+  ExpandTab xt;
   BfsShared bfs;
   int hist_ovf;
   long long n_live, n_in, n_out;
   unsigned long long thr_bits; int thr_found;
-  int pool_n, match_node, n, sizes0, sizes1, depth, state, ticket;
+  unsigned long long hk[HCAP]; unsigned hc[HCAP]; int hn;  // the occupied histogram slots, compacted (kth_value)
+  unsigned long long t_in, t_out;                          // running pruning thresholds (bits of non-negative doubles)
+  int pool_n, pool_ovf, match_node, n, sizes0, sizes1, depth, state, ticket;
+  int pub_rc, pub_n;  // leader -> followers of a cluster: result of the last tree_get
   int best_node, best_tok; unsigned long long best_key; int best_ord;
 };
 
 constexpr int CF_FI = 1, CF_FO = 2, CF_KIDS = 4;
+
+// sorted(values, reverse=True)[rank-1] from a histogram -> S->thr_bits; false if rank is out of range.  CTA-uniform,
+// synchronises.  The occupied slots (a few dozen distinct n-gram counts) are compacted first, then ranked pairwise.
+// `lo`: a known lower bound of the answer (0 = none) - slots below it are left out of the pairwise ranking.
+template <class SM>
+__device__ bool kth_value(SM *S, const Hist *h, long long rank, unsigned long long lo) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) { S->hn = 0; S->thr_found = 0; }
+  __syncthreads();
+  for (int s = tid; s < HCAP; s += NT) {  // HCAP is a multiple of NT: whole warps
+    const unsigned long long k = h->key[s];
+    const bool keep = k != HEMPTY && k >= lo;
+    const unsigned m = __ballot_sync(FULL, keep);
+    int base = 0;
+    if (lane_id() == 0 && m) base = atomicAdd(&S->hn, __popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (keep) { const int j = base + __popc(m & ((1u << lane_id()) - 1)); S->hk[j] = k; S->hc[j] = h->cnt[s]; }
+  }
+  __syncthreads();
+  const int n = S->hn;
+  for (int e = tid; e < n; e += NT) {
+    const unsigned long long k = S->hk[e];
+    long long greater = 0;
+    for (int j = 0; j < n; ++j) if (S->hk[j] > k) greater += S->hc[j];
+    if (greater < rank && rank <= greater + (long long)S->hc[e]) { S->thr_bits = k; S->thr_found = 1; }
+  }
+  __syncthreads();
+  return S->thr_found != 0;
+}
+
 
 // Builds the sorted candidate list of `parent`'s children for one DFS frame: children that pass the
 // threshold filter (lookahead_cache.py:264-272), ordered by fm descending, ties by insertion order (:254-258),
@@ -513,32 +627,44 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
   const int tid = threadIdx.x;
   const Node p = D.nodes[parent];
   const int C = p.n_child;
+#ifdef PIA_TRIE_PHASES
+  const unsigned long long tf0 = gtime();
+#endif
   int m = 0;  // current size of the running top list (uniform)
-  bool pool_stale = true;  // S->pool_n != m (uniform)
-  constexpr int U = 2;  // child chunks whose records are fetched together (memory-level parallelism on wide nodes)
+  // child chunks whose records are fetched together: a frame below a hot node ranks thousands of children, and every
+  // chunk costs two dependent memory round trips (child entry -> record); only the fields the ranking needs are kept
+  constexpr int U = 8;
+  struct Slim { int token, n_child; double fo; float fi; };
   for (int base = 0; base < C; base += NT * U) {
     int cid[U];
-    Node cn[U];
+    Slim cn[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = base + u * NT + tid;
       cid[u] = -1;
-      if (i < C) { if (p.cap == 0) cid[u] = p.child; else { cid[u] = D.edges[p.child + i].y; ++ne; } }
+      if (i < C) { if (p.cap == 0) cid[u] = p.child; else { cid[u] = __ldg(&D.edges[p.child + i].y); ++ne; } }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      if (cid[u] >= 0) { cn[u] = D.nodes[cid[u]]; ++nv; }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (base + u * NT >= C) break;  // uniform
-      // pool_n is only rewritten when it differs from m: after a chunk that added nothing it still equals m, and the
-      // other threads may not have read it yet (no barrier on that path)
-      if (pool_stale && tid == 0) S->pool_n = m;
-      __syncthreads();
-      const int i = base + u * NT + tid;
       if (cid[u] >= 0) {
-        const Node &c = cn[u];
-        const double fi = (double)load_fi(D, c, cid[u], idx), fo = c.fo;
+        const Node full = load_node<true>(D.nodes + cid[u]);
+        cn[u].token = full.token; cn[u].n_child = full.n_child; cn[u].fo = full.fo;
+        cn[u].fi = idx == 0 ? full.fi : __ldg(&D.fi_extra[(long long)(idx - 1) * D.node_cap + cid[u]]);
+        ++nv;
+      }
+    // One pool round over the chunks [u_lo, u_hi): survivors of the threshold filter join the running top list, the
+    // first K in (key desc, insertion index asc) order stay.  All U chunks go through one round (a hot node's frame
+    // is mostly children below the thresholds); if their survivors do not fit the pool the chunks are redone one by
+    // one (a chunk cannot overflow).  Selecting the top K of a union in pieces gives the same list.
+    auto round = [&](int u_lo, int u_hi) -> bool {
+      if (tid == 0) { S->pool_n = m; S->pool_ovf = 0; }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u < u_lo || u >= u_hi || cid[u] < 0) continue;
+        const int i = base + u * NT + tid;
+        const Slim &c = cn[u];
+        const double fi = (double)c.fi, fo = c.fo;
         const double fm = mix_freq(omw, w, fi, fo);
         bool skip;
         if (mode == PIA_MODE_MIX) skip = (fi < min_in && fo < min_out && fm < min_mix);
@@ -550,17 +676,21 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
         if (!skip && K <= 0) skip = true;
         if (!skip) {
           const int slot = atomicAdd(&S->pool_n, 1);
-          S->pkey[slot] = dbits(fm);
-          S->pord[slot] = i;
-          S->pnode[slot] = cid[u];
-          S->ptok[slot] = c.token;
-          S->pflag[slot] = (fi > 0.0 ? CF_FI : 0) | (fo > 0.0 ? CF_FO : 0) | (c.n_child > 0 ? CF_KIDS : 0);
+          if (slot < MAXS + NT) {
+            S->pkey[slot] = dbits(fm);
+            S->pord[slot] = i;
+            S->pnode[slot] = cid[u];
+            S->ptok[slot] = c.token;
+            S->pflag[slot] = (fi > 0.0 ? CF_FI : 0) | (fo > 0.0 ? CF_FO : 0) | (c.n_child > 0 ? CF_KIDS : 0);
+          } else {
+            S->pool_ovf = 1;
+          }
         }
       }
       __syncthreads();
+      if (S->pool_ovf) { __syncthreads(); return false; }  // uniform; the held list [0, m) is untouched
       const int total = S->pool_n;
-      if (total == m) { pool_stale = false; continue; }  // nothing new (uniform): the running list stands
-      pool_stale = true;
+      if (total == m) return true;  // nothing new (uniform): the running list stands
       // rank every pool element; the first K in (key desc, ord asc) order survive
       for (int e = tid; e < total; e += NT) {
         const unsigned long long k = S->pkey[e];
@@ -582,10 +712,19 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
         S->pflag[e] = S->qflag[e];
       }
       __syncthreads();
+      return true;
+    };
+    if (!round(0, U)) {
+      for (int u = 0; u < U && base + u * NT < C; ++u) round(u, u + 1);
     }
   }
   for (int e = tid; e < m; e += NT) { onode[e] = S->pnode[e]; otok[e] = S->ptok[e]; oflag[e] = (unsigned char)S->pflag[e]; }
   __syncthreads();
+#ifdef PIA_TRIE_PHASES
+#ifdef PIA_TRIE_PHASES_FRAMES
+  if (tid == 0) printf("  frame: C %d K %d kept %d  %llu ns\n", C, K, m, gtime() - tf0);
+#endif
+#endif
   return m;
 }
 
@@ -594,9 +733,16 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
 template <int MAXS, int MAXD>
 __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int tree_token, const int *q, int nq,
                         int max_size, int max_length, int min_in_sz, int min_out_sz, int mode, int idx, int *fr0,
-                        int *fr1, unsigned long long &nv, unsigned long long &ne) {
+                        int *fr1, int CL, int rank, int prune, unsigned long long &nv, unsigned long long &ne) {
   const int tid = threadIdx.x;
   constexpr int W = (MAXS + 63) / 64;
+  // CL > 1: the CTAs of a cluster share the frequency walk below the match (everything up to the merge is executed by
+  // every rank with identical control flow); thresholds and _ravel are the leader's
+  GetSmem<MAXS, MAXD> *L = CL > 1 ? map_to_rank(S, 0) : S;
+#ifdef PIA_TRIE_PHASES
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  PHASE(0);
   // ---- _match (:224-246), one warp
   if (tid < 32) {
     int cur = root;
@@ -616,11 +762,12 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
     if (tid == 0) {
       S->match_node = cur;
       S->sizes0 = 0; S->sizes1 = 0;
-      S->hist_ovf = 0; S->n_live = 0; S->n_in = 0; S->n_out = 0; S->thr_found = 0;
+      S->hist_ovf = 0; S->n_live = 0; S->n_in = 0; S->n_out = 0; S->thr_found = 0; S->t_in = 0; S->t_out = 0;
     }
   }
   for (int s = tid; s < HCAP; s += NT) { S->hin.key[s] = HEMPTY; S->hin.cnt[s] = 0; S->hout.key[s] = HEMPTY; S->hout.cnt[s] = 0; }
   __syncthreads();
+  PHASE(1);
   const int start = S->match_node;
   if (start < 0) {  // miss: ([last query token or tree token], ones(1,1), [0,0])  (:70-72)
     if (tid == 0) {
@@ -635,27 +782,81 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
   // ---- _dfs_get_freqs (:146-154): every live node below the match, any order
   const bool need_in = (mode == PIA_MODE_INPUT) || (mode == PIA_MODE_MIX && min_in_sz > 0);
   const bool need_out = (mode == PIA_MODE_OUTPUT) || (mode == PIA_MODE_MIX && min_out_sz > 0);
+  // Pruned walk.  The reference lists the frequencies of EVERY live node below the match and takes the k-th largest
+  // fi / fo as thresholds when there are more than max_size of them (:74-125).  Counts only ever grow along root
+  // paths (_put :40-56 adds `freq` to every node of the path, _squeeze :302-310 halves top-down and drops whole
+  // subtrees, _reset_input_freq :326-333 zeroes top-down), so a node's fi and fo bound those of its descendants.  Once
+  // more than max_size live nodes have been seen (the `size > max_size` decision is then made) a subtree below a
+  // node with fo <= the running k-th largest fo (and fi likewise) cannot change the k-th largest value: it is not
+  // entered.  The running thresholds are recomputed after every level from the nodes seen so far (a subset, hence a
+  // lower bound of the final value).  A hot match (137 k nodes below a frequent bigram) visits the first level and a
+  // few hundred nodes instead of all of them; the thresholds, hence the draft, are bit-identical.  Not applicable
+  // (full walk) when an index is python-negative (k == 0 -> rank N) or beyond max_size, when the forest was imported
+  // with a violated bound (pia_trie_import checks), or in cluster mode.
+  const bool may_prune = prune && CL == 1 && (!need_in || (min_in_sz >= 1 && min_in_sz <= max_size)) &&
+                         (!need_out || (min_out_sz >= 1 && min_out_sz <= max_size));
+  unsigned long long t_in = 0, t_out = 0;  // running thresholds of the pruned walk: lower bounds of the final ones
   {
     long long my_live = 0, my_in = 0, my_out = 0;
-    HistRun run_in, run_out;
-    run_in.cnt = 0; run_in.key = 0; run_out.cnt = 0; run_out.key = 0;
-    auto visit = [&](int id, const Node &nd) -> bool {
-      const float fi = load_fi(D, nd, id, idx);
-      const double fo = nd.fo;
-      if (!(fo > 0.0 || fi > 0.f)) return false;
-      ++my_live; my_in += fi > 0.f; my_out += fo > 0.0;
-      if (need_in) run_in.add(&S->hin, dbits((double)fi), &S->hist_ovf);
-      if (need_out) run_out.add(&S->hout, dbits(fo), &S->hist_ovf);
+    bool pruning = false;
+    // called convergently by all lanes of a warp; equal values of a warp reach the shared histogram as one update
+    // (n-gram counts are overwhelmingly 1.0: one contended address otherwise).  While pruning, values at or below the
+    // running threshold are not recorded at all: they cannot change the k-th largest value.
+    auto visit = [&](int id, const Node &nd, bool valid) -> bool {
+      float fi = 0.f;
+      double fo = 0.0;
+      if (valid) { fi = load_fi(D, nd, id, idx); fo = nd.fo; }
+      const bool live = valid && (fo > 0.0 || fi > 0.f);
+      const unsigned long long bi = dbits((double)fi), bo = dbits(fo);
+      if (!pruning) { my_live += live; my_in += live && fi > 0.f; my_out += live && fo > 0.0; }
+      if (need_in) warp_hist_add(&S->hin, bi, live && (!pruning || bi > t_in), &S->hist_ovf);
+      if (need_out) warp_hist_add(&S->hout, bo, live && (!pruning || bo > t_out), &S->hist_ovf);
+      if (!live) return false;
+      if (pruning) return (need_in && bi > t_in) || (need_out && bo > t_out);
       return true;
     };
-    bfs_below(D, start, fr0, fr1, &S->bfs, visit, nv, ne);
-    run_in.flush(&S->hin, &S->hist_ovf);
-    run_out.flush(&S->hout, &S->hist_ovf);
-    if (my_live) { atomicAdd((unsigned long long *)&S->n_live, (unsigned long long)my_live);
-                   atomicAdd((unsigned long long *)&S->n_in, (unsigned long long)my_in);
-                   atomicAdd((unsigned long long *)&S->n_out, (unsigned long long)my_out); }
+    long long pushed = 0;  // nodes handed to the walk so far (uniform): an upper bound of the live nodes seen
+    auto level_end = [&](int next_cnt) {
+      pushed += next_cnt;
+      // nothing to decide while fewer than max_size nodes were reached at all; once pruning is on, the thresholds are
+      // only tightened ahead of a large level (a stale threshold is a valid, lower, bound)
+      if (!may_prune || pushed <= max_size || (pruning && next_cnt < 2 * NT)) return;
+      for (int o = 16; o > 0; o >>= 1) {
+        my_live += __shfl_down_sync(FULL, my_live, o); my_in += __shfl_down_sync(FULL, my_in, o);
+        my_out += __shfl_down_sync(FULL, my_out, o);
+      }
+      if (lane_id() == 0 && my_live) { atomicAdd((unsigned long long *)&S->n_live, (unsigned long long)my_live);
+                                       atomicAdd((unsigned long long *)&S->n_in, (unsigned long long)my_in);
+                                       atomicAdd((unsigned long long *)&S->n_out, (unsigned long long)my_out); }
+      my_live = 0; my_in = 0; my_out = 0;
+      __syncthreads();
+      const long long seen = mode == PIA_MODE_INPUT ? S->n_in : (mode == PIA_MODE_OUTPUT ? S->n_out : S->n_live);
+      if (seen <= max_size || S->hist_ovf) return;  // uniform
+      if (need_in && kth_value(S, &S->hin, min_in_sz, t_in)) t_in = S->thr_bits;
+      if (need_out && kth_value(S, &S->hout, min_out_sz, t_out)) t_out = S->thr_bits;
+      pruning = true;
+    };
+    if (CL > 1) cluster_sync_all();  // the leader's counters / histograms are initialised before any remote access
+    PHASE(2);
+    bfs_below<true>(D, start, fr0, fr1, CL > 1 ? nullptr : S->sfr, &S->xt, &L->bfs, CL, rank, visit, level_end, nv, ne);
+    PHASE(3);
+    if (my_live) { atomicAdd((unsigned long long *)&L->n_live, (unsigned long long)my_live);
+                   atomicAdd((unsigned long long *)&L->n_in, (unsigned long long)my_in);
+                   atomicAdd((unsigned long long *)&L->n_out, (unsigned long long)my_out); }
     __syncthreads();
+    if (CL > 1) {  // followers fold their histograms into the leader's (distributed-shared-memory atomics)
+      if (rank != 0) {
+        for (int e = tid; e < HCAP; e += NT) {
+          if (need_in && S->hin.key[e] != HEMPTY) hist_add(&L->hin, S->hin.key[e], S->hin.cnt[e], &L->hist_ovf);
+          if (need_out && S->hout.key[e] != HEMPTY) hist_add(&L->hout, S->hout.key[e], S->hout.cnt[e], &L->hist_ovf);
+        }
+        if (tid == 0 && S->hist_ovf) L->hist_ovf = 1;
+      }
+      cluster_sync_all();
+      if (rank != 0) return PIA_OK;
+    }
   }
+  PHASE(4);
   if (S->bfs.err) return PIA_ERR_CAPACITY;
   // ---- thresholds (:78-125)
   double min_in = 1e9, min_out = 1e9, min_mix = 1e9, w = 1e-4;
@@ -668,22 +869,12 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
     if (S->hist_ovf) return PIA_ERR_CAPACITY;
     // python index k-1 with negative wrap: k == 0 -> the smallest value (rank N)
     if (need_in) {
-      long long rank = min_in_sz >= 1 ? min_in_sz : N;
-      hist_kth(&S->hin, rank, &S->thr_bits, &S->thr_found);
-      __syncthreads();
-      if (!S->thr_found) return PIA_ERR_INDEX;
+      if (!kth_value(S, &S->hin, min_in_sz >= 1 ? min_in_sz : N, t_in)) return PIA_ERR_INDEX;
       min_in = __longlong_as_double((long long)S->thr_bits);
-      __syncthreads();
-      if (tid == 0) S->thr_found = 0;
-      __syncthreads();
     }
     if (need_out) {
-      long long rank = min_out_sz >= 1 ? min_out_sz : N;
-      hist_kth(&S->hout, rank, &S->thr_bits, &S->thr_found);
-      __syncthreads();
-      if (!S->thr_found) return PIA_ERR_INDEX;
+      if (!kth_value(S, &S->hout, min_out_sz >= 1 ? min_out_sz : N, t_out)) return PIA_ERR_INDEX;
       min_out = __longlong_as_double((long long)S->thr_bits);
-      __syncthreads();
     }
     // mix mode: the reference's refinement loop never lowers min_mix_freq (every record carries None in
     // slot 0, :100-123), so it stays 1e9
@@ -692,6 +883,7 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
     else if (mode == PIA_MODE_OUTPUT) min_out = 0.0;
     else min_mix = 0.0;
   }
+  PHASE(5);
   const double omw = __dsub_rn(1.0, w);
   // ---- _ravel (:248-293): DFS pre-order, iterative with one sorted frame per depth
   if (tid == 0) {
@@ -707,6 +899,7 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
     int cnt0 = build_frame(D, S, start, max_size - 1, idx, mode, omw, w, min_in, min_out, min_mix, S->fnode[0],
                            S->ftok[0], S->fflag[0], nv, ne);
     if (tid == 0) { S->fcnt[0] = cnt0; S->fcur[0] = 0; S->fpid[0] = -1; S->depth = 0; }
+    PHASE(6);
     __syncthreads();
     while (true) {
       // thread 0 advances the DFS until a sorted frame must be built (state 1) or the walk ends (state 0).
@@ -729,9 +922,10 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
           S->n = rid + 1;
           // recurse (:283-293): children exist, depth budget max_length-1-d > 0, room left
           int cur_node = S->fnode[d][e], cur_d = d;
+          Node x;
+          bool have_x = false;  // the record of cur_node is already in registers (it was the child of the last step)
           while ((fl & CF_KIDS) && (max_length - 1 - cur_d) > 0 && S->n < max_size && cur_d + 1 < MAXD) {
-            const Node x = D.nodes[cur_node];
-            ++nv;
+            if (!have_x) { x = load_node<true>(D.nodes + cur_node); ++nv; }
             if (x.n_child != 1) {  // several children: they must be ranked by fm -> build a frame
               S->best_node = cur_node;
               S->fpid[cur_d + 1] = rid;
@@ -740,8 +934,8 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
               break;
             }
             int cid;
-            if (x.cap == 0) cid = x.child; else { cid = D.edges[x.child].y; ++ne; }
-            const Node c = D.nodes[cid];
+            if (x.cap == 0) cid = x.child; else { cid = __ldg(&D.edges[x.child].y); ++ne; }
+            const Node c = load_node<true>(D.nodes + cid);
             ++nv;
             const double fi = (double)load_fi(D, c, cid, idx), fo = c.fo;
             const double fm = mix_freq(omw, w, fi, fo);
@@ -763,6 +957,7 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
             fl = c.n_child > 0 ? CF_KIDS : 0;
             cur_node = cid;
             cur_d = cur_d + 1;
+            x = c; have_x = true;
           }
         }
         S->state = st;
@@ -777,6 +972,13 @@ __device__ __forceinline__ int tree_get(const Dev &D, GetSmem<MAXS, MAXD> *S, in
     }
   }
   __syncthreads();
+#ifdef PIA_TRIE_PHASES
+  PHASE(7);
+  if (tid == 0 && rank == 0)
+    printf("tree_get phases ns: match %llu sync %llu bfs %llu merge %llu thr %llu frame0 %llu ravel %llu | n_live %lld n %d\n",
+           ph[1] - ph[0], ph[2] - ph[1], ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4], ph[6] - ph[5], ph[7] - ph[6],
+           S->n_live, S->n);
+#endif
   return PIA_OK;
 }
 
@@ -870,20 +1072,26 @@ __device__ int tree_get_one(const Dev &D, GetSmem<MAXS, MAXD> *S, int root, int 
 }
 
 // LookaheadCache.hier_get / one_get (lookahead_cache.py:408-439, 490-517): one CTA per query row
+#ifndef PIA_GET_MINB
+#define PIA_GET_MINB 2  // resident CTAs per SM the register budget is sized for (128 registers: no spills in the walk)
+#endif
 template <int MAXS, int MAXD>
-__global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
+__global__ void __launch_bounds__(NT, PIA_GET_MINB) k_get(Dev D, GetParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GetSmem<MAXS, MAXD> *S = reinterpret_cast<GetSmem<MAXS, MAXD> *>(smem_raw);
   constexpr int W = (MAXS + 63) / 64;
   const int tid = threadIdx.x;
-  int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
+  // a hier_get of few rows is launched as one thread-block cluster per row (the frequency walk below a hot match is
+  // shared by its CTAs); rank 0 leads and owns the row's outputs
+  const int CL = (int)cluster_size(), rank = (int)cluster_rank();
+  int *fr0 = D.frontier + (long long)(blockIdx.x / CL) * 2 * D.fr_cap;
   int *fr1 = fr0 + D.fr_cap;
   unsigned long long nv = 0, ne = 0;
   const int Wout = (P.dl + 63) / 64;
   // rows are handed out by a ticket counter when there are more rows than CTAs (a batched scan: query cost varies by
   // three orders of magnitude with the matched subtree, a static stride leaves SMs idle behind the hot rows)
-  const bool dynamic = P.batch > (int)gridDim.x;
-  for (int b = blockIdx.x;; ) {
+  const bool dynamic = CL == 1 && P.batch > (int)gridDim.x;
+  for (int b = blockIdx.x / CL;; ) {
     if (dynamic) {
       __syncthreads();
       if (tid == 0) S->ticket = atomicAdd(&D.hdr->get_ticket, 1);
@@ -925,10 +1133,18 @@ __global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
         if (rest == 0 && is_stop(D, t)) continue;  // (:422-423)
         int rc, miss = 0;
         if (P.kind == PIA_GET_ONE) rc = tree_get_one<MAXS, MAXD>(D, S, root, t, S->q + i + 1, rest, bl, P.mode, idx, &miss, nv, ne);
-        else rc = tree_get<MAXS, MAXD>(D, S, root, t, S->q + i + 1, rest, P.dl, bl, P.min_in, P.min_out, P.mode, idx, fr0, fr1, nv, ne);
+        else rc = tree_get<MAXS, MAXD>(D, S, root, t, S->q + i + 1, rest, P.dl, bl, P.min_in, P.min_out, P.mode, idx, fr0, fr1, CL, rank, P.prune, nv, ne);
+        int n_res = S->n;
+        if (CL > 1) {  // the loop below must take the same turns in every CTA of the cluster: the leader's result decides
+          if (rank == 0 && tid == 0) { S->pub_rc = rc; S->pub_n = S->n; }
+          cluster_sync_all();
+          const GetSmem<MAXS, MAXD> *L = map_to_rank(S, 0);
+          rc = L->pub_rc; n_res = L->pub_n;
+          cluster_sync_all();
+        }
         if (rc != PIA_OK) { status = rc; break; }
         have = true;
-        n_out = S->n;
+        n_out = n_res;
         if (P.kind == PIA_GET_ONE) { if (miss) { nsizes = 2; sz0 = sz1 = 0; } else { nsizes = 1; sz0 = n_out - 1; sz1 = 0; } }
         else { nsizes = 2; sz0 = S->sizes0; sz1 = S->sizes1; }
         if (P.kind == PIA_GET_ONE ? (n_out >= bl / 2) : (n_out >= bl)) break;  // (:433-434, :512)
@@ -938,6 +1154,7 @@ __global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
     __syncthreads();
     int *oid = P.out_ids + (long long)b * P.dl;
     unsigned long long *om = P.out_mask + (long long)b * P.dl * Wout;
+    if (rank != 0) break;  // followers of a cluster: one row, no outputs
     if (status == PIA_OK && have) {
       for (int i = tid; i < n_out; i += NT) {
         oid[i] = S->ids[i];
@@ -981,6 +1198,7 @@ __global__ void __launch_bounds__(NT, 4) k_get(Dev D, GetParams P) {
 // single_key >= 0: Tree.reset_input_freq(idx) of that one tree (:320-333), the touched-tree list is left alone
 __global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx, int single_key) {
   __shared__ BfsShared sh;
+  __shared__ ExpandTab xt;
   int *fr0 = D.frontier + (long long)blockIdx.x * 2 * D.fr_cap;
   int *fr1 = fr0 + D.fr_cap;
   unsigned long long nv = 0, ne = 0;
@@ -991,13 +1209,14 @@ __global__ void __launch_bounds__(NT) k_reset_input(Dev D, int idx, int single_k
     if (threadIdx.x == 0) { sh.err = 0; if (single_key < 0) D.tree_flags[key] &= ~FLAG_UPDIN; }
     __syncthreads();
     if (root < 0) continue;
-    auto visit = [&](int id, const Node &nd) -> bool {
+    auto visit = [&](int id, const Node &nd, bool valid) -> bool {
+      if (!valid) return false;
       const float f = load_fi(D, nd, id, idx);
       if (f == 0.f) return false;
       if (idx == 0) D.nodes[id].fi = 0.f; else D.fi_extra[(long long)(idx - 1) * D.node_cap + id] = 0.f;
       return true;
     };
-    bfs_below(D, root, fr0, fr1, &sh, visit, nv, ne);
+    bfs_below<false>(D, root, fr0, fr1, nullptr, &xt, &sh, 1, 0, visit, [](int) {}, nv, ne);
     if (threadIdx.x == 0 && sh.err) atomicOr(&D.hdr->err, ERR_FRONTIER);
     __syncthreads();
   }
@@ -1115,6 +1334,9 @@ struct pia_trie {
   pia_trie_config_t cfg;
   std::vector<void *> allocs;
   int n_sm;
+  int get_cluster;  // CTAs per row of a small hier_get that cannot prune (PIA_TRIE_GET_CLUSTER, default 8; 1 = off)
+  int prune;        // PIA_TRIE_PRUNE (default 1): pruned frequency walk (tree_get)
+  int monotone;     // every node's fi / fo bound its children's: true for forests built by put, checked on import
 };
 
 template <class T>
@@ -1174,6 +1396,14 @@ extern "C" int pia_trie_create(const pia_trie_config_t *c, pia_trie_t **out) {
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->n_sm, cudaDevAttrMultiProcessorCount, dev_id);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GetSmem<64, 16>));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_get<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GetSmem<128, 32>));
+  {
+    const char *ev = getenv("PIA_TRIE_GET_CLUSTER");
+    int c = ev ? atoi(ev) : 8;
+    t->get_cluster = (c == 2 || c == 4 || c == 8) ? c : 1;
+    ev = getenv("PIA_TRIE_PRUNE");
+    t->prune = ev ? atoi(ev) != 0 : 1;
+    t->monotone = 1;
+  }
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     set_error("pia_trie_create: %s", cudaGetErrorString(e));
@@ -1313,10 +1543,30 @@ extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32
   P.flags = flags; P.max_seq = max_seq_length; P.d_max_seq = d_max_seq_length;
   P.out_ids = d_out_ids; P.out_mask = (unsigned long long *)d_out_mask; P.out_n = d_out_n; P.out_sizes = d_out_sizes;
   P.out_nsizes = d_out_nsizes; P.status = d_status;
-  const int grid = batch < t->dev.max_resident ? batch : t->dev.max_resident;
+  int grid = batch < t->dev.max_resident ? batch : t->dev.max_resident;
   cudaStream_t s = (cudaStream_t)stream;
-  if (decoding_length <= 64 && branch_length <= 16) k_get<64, 16><<<grid, NT, sizeof(GetSmem<64, 16>), s>>>(t->dev, P);
-  else k_get<128, 32><<<grid, NT, sizeof(GetSmem<128, 32>), s>>>(t->dev, P);
+  // The walk below the match is pruned (tree_get) whenever the forest's counts are known to be monotone along root
+  // paths.  Otherwise, for few rows (the decode step: 1 row, the batched loop: <= 16), a cluster of GET_CLUSTER CTAs
+  // per row shares the full walk; a batched scan keeps one CTA per row (rows are the parallelism there).
+  P.prune = t->prune && t->monotone;
+  int cl = 1;
+  if (kind == PIA_GET_HIER && !P.prune && t->get_cluster > 1 && batch * t->get_cluster <= 128 &&
+      batch * t->get_cluster <= t->dev.max_resident)
+    cl = t->get_cluster;
+  grid *= cl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NT); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;  // no programmatic-serialization attribute: the kernel has no griddepcontrol.wait
+  if (decoding_length <= 64 && branch_length <= 16) {
+    cfg.dynamicSmemBytes = sizeof(GetSmem<64, 16>);
+    PIA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_get<64, 16>, t->dev, P));
+  } else {
+    cfg.dynamicSmemBytes = sizeof(GetSmem<128, 32>);
+    PIA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_get<128, 32>, t->dev, P));
+  }
   PIA_LAUNCH_CHECK();
   return PIA_OK;
 }
@@ -1430,6 +1680,21 @@ extern "C" int pia_trie_import(pia_trie_t *t, const void *h_nodes, int64_t n_nod
   PIA_CUDA_CHECK(cudaMemsetAsync(t->dev.tree_flags, 0, v, s));
   if (t->dev.fi_extra) PIA_CUDA_CHECK(cudaMemsetAsync(t->dev.fi_extra, 0, (size_t)(t->cfg.n_input_slots - 1) * t->cfg.node_capacity * sizeof(float), s));
   PIA_CUDA_CHECK(cudaStreamSynchronize(s));
+  {  // the pruned query walk relies on parent counts bounding child counts; a forest written by put/squeeze/reset has
+     // that property, an arbitrary file may not: check it once here (host, one pass) and fall back to full walks if not
+    const Node *hn = static_cast<const Node *>(h_nodes);
+    const int2 *he = static_cast<const int2 *>(h_edges);
+    int mono = 1;
+    for (int64_t i = 0; i < n_nodes && mono; ++i) {
+      const Node &p = hn[i];
+      for (int k = 0; k < p.n_child; ++k) {
+        const int64_t c = p.cap == 0 ? p.child : (p.child + k < n_edges ? he[p.child + k].y : -1);
+        if (c < 0 || c >= n_nodes) continue;
+        if (hn[c].fo > p.fo || hn[c].fi > p.fi) { mono = 0; break; }
+      }
+    }
+    t->monotone = mono;
+  }
   Hdr h;
   PIA_CUDA_CHECK(cudaMemcpy(&h, t->dev.hdr, sizeof(h), cudaMemcpyDeviceToHost));
   h.node_top = (unsigned long long)n_nodes; h.edge_top = (unsigned long long)n_edges;

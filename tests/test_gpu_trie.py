@@ -161,3 +161,51 @@ def test_tree_methods_against_the_reference_tree():
     from painlessinferenceacceleration_b200.common.lookahead_cache import Tree
     from tests.replay import replay_tree_methods
     assert replay_tree_methods(lambda tok, mn, mo: Tree(tok, max_node=mn, max_output_node=mo)) > 40
+
+
+def test_pruned_walk_and_cluster_walk_match_the_full_walk(monkeypatch):
+    """The three frequency walks of hier_get (pruned by the parent >= child count bound, full in one CTA, full in a
+    thread-block cluster) give identical drafts on a forest with hot subtrees (tens of thousands of nodes below a
+    frequent bigram), input-mode counts, squeezed trees and every mode / min-size combination incl. the python
+    negative-index case (min size 0 -> the pruned walk must fall back)."""
+    import bench
+    LookaheadCache = _gpu_cache_cls()
+    rng = np.random.default_rng(77)
+    docs = bench.phrase_bank_prompts(300, 32000, seed=3)
+
+    def build(prune, cluster):
+        monkeypatch.setenv('PIA_TRIE_PRUNE', str(prune))
+        monkeypatch.setenv('PIA_TRIE_GET_CLUSTER', str(cluster))
+        c = LookaheadCache(eos_ids=[2], max_output_node=4096)
+        for i, d in enumerate(docs):
+            c.put(d, branch_length=9, mode='output', idx=-1)
+            if i % 3 == 0:
+                c.put(d[:64], branch_length=9, mode='input', idx=0)
+        return c
+
+    caches = [build(1, 1), build(0, 1), build(0, 8)]
+    queries = [[3, 3], [3], [4, 3], [3, 4]]
+    for _ in range(60):
+        d = docs[int(rng.integers(0, len(docs)))]
+        j = int(rng.integers(0, len(d) - 2))
+        queries.append(d[j:j + 2])
+    variants = [('mix', 0, 32), ('mix', 8, 16), ('mix', 0, 0), ('output', 0, 32), ('output', 0, 0), ('input', 16, 0),
+                ('input', 0, 0), ('mix', 0, 64)]
+    n_hot = 0
+    for q in queries:
+        for mode, mi, mo in variants:
+            outs = []
+            for c in caches:
+                try:
+                    ids, m, sizes = c.hier_get(list(q), decoding_length=64, branch_length=8, min_input_size=mi,
+                                               min_output_size=mo, mode=mode, idx=0)
+                    outs.append(([int(x) for x in ids], R.mask_rows(m), [int(x) for x in sizes]))
+                except IndexError:
+                    outs.append('IndexError')
+            assert outs[0] == outs[1] == outs[2], f'{q} {mode} {mi} {mo}\n{outs[0]}\n{outs[1]}\n{outs[2]}'
+            n_hot += outs[0] != 'IndexError' and len(outs[0][0]) >= 32
+    assert n_hot > 50
+    visited = [c.stats()['nodes_visited'] for c in caches]
+    assert visited[0] * 2 < visited[1], visited      # the pruned walk really skips most of the hot subtrees
+    for c in caches:
+        assert c.stats()['error_flags'] == 0
