@@ -541,9 +541,14 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
           if (!((vm1 >> j) & 1u)) sv[32 + j] = 0xff800000u;
         }
       }
-      float m_half = -INFINITY;
+      // four independent chains (a single 64-long fmaxf / FADD chain is ~250 cycles of pure latency per tile)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) m_half = fmaxf(m_half, __uint_as_float(sv[j]));
+      for (int j = 0; j < 64; j += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[j])); mx1 = fmaxf(mx1, __uint_as_float(sv[j + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[j + 2])); mx3 = fmaxf(mx3, __uint_as_float(sv[j + 3]));
+      }
+      const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // row max across the two halves (double-buffered exchange slot, one named barrier per quadrant pair)
       float *xm = reinterpret_cast<float *>(sm + SMEM_XCH) + (i & 1) * 256;
       xm[half * 128 + row] = m_half;
@@ -554,7 +559,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_use);
       // p = exp2(s*scale - m) -> bf16 pairs -> TMEM (A operand of the PV MMA: lane = row, one 32-bit column per key
       // pair; this half owns columns [32*half, 32*half+32)), row sum
-      float l_tile = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[32];
 #pragma unroll
       for (int e = 0; e < 32; ++e) {  // ex2(-inf) = 0 for the hidden keys (m_use is finite)
@@ -562,9 +567,10 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         const float p1 = ex2(__uint_as_float(sv[2 * e + 1]) * p.scale_log2 - m_use);
         const __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
         // the row sum uses the bf16-rounded probabilities, i.e. exactly what the PV MMA consumes
-        l_tile += __bfloat162float(b.x) + __bfloat162float(b.y);
+        ls[e & 3] += __bfloat162float(b.x) + __bfloat162float(b.y);
         pk[e] = *reinterpret_cast<const uint32_t *>(&b);
       }
+      const float l_tile = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       // P buffer (i & 1) is free: PV(i-2) completed before o_full(i-2), which this thread observed in iteration i-1
       tmem_st32(tmem + lane_addr + ((i & 1) ? TM_P1 : TM_P0) + half * 32, pk);
       tmem_st_wait();
@@ -629,6 +635,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
       // row's (m, l) - straight into the shared memory of the CTA that owns that row's slice (DSMEM), barrier B,
       // and every CTA combines its slice locally: no workspace round trip through L2, no serial last-arriver merge.
       barrier_a();
+      if (row == 0 && half == 0) DBG(14);
       const int RS = (rows_used + ns - 1) / ns;       // rows per owner CTA
       const int owner = row / RS, rl = row % RS;
       if (row_live) {
@@ -641,6 +648,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         if (half == 0) st_cluster_f2(map_to_cta(base + mrg_ml + (uint32_t)(split * RS + rl) * 8, owner), m_run, l_run);
       }
       __syncwarp();  // the live-row branch above diverges; the cluster barrier is warp-aligned
+      if (row == 0 && half == 0) DBG(15);
       cluster_sync_all();
     }
     if (row == 0 && half == 0) DBG(10);
@@ -653,23 +661,34 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
     const float4 *macc = reinterpret_cast<const float4 *>(sm + mrg_acc);
     const float2 *mml = reinterpret_cast<const float2 *>(sm + mrg_ml);
     const int items = RS * (HD / 4);
+    // RS and np are powers of two in every configuration but ragged ones: shifts instead of four integer divisions per
+    // item, and all ns partials of an item are loaded before the first is used (the loop over a runtime ns was a chain
+    // of dependent shared-memory round trips: 1.7 us for 512 items on 320 threads)
+    const bool pow2 = (RS & (RS - 1)) == 0 && (p.np & (p.np - 1)) == 0;
+    const int rs_sh = 31 - __clz(RS), np_sh = 31 - __clz(p.np);
     for (int it = tid; it < items; it += NTHREADS) {
-      const int rl = it % RS, c4 = it / RS;
+      const int rl = pow2 ? (it & (RS - 1)) : it % RS, c4 = pow2 ? (it >> rs_sh) : it / RS;
       const int r = split * RS + rl;
       if (r >= rows_used) continue;
-      const int rh = r / p.np, rn = r % p.np;
+      const int rh = pow2 ? (r >> np_sh) : r / p.np, rn = pow2 ? (r & (p.np - 1)) : r % p.np;
       if (rn >= n) continue;
+      float2 ml[MAX_SPLIT];
+      float4 a4[MAX_SPLIT];
+#pragma unroll
+      for (int i = 0; i < MAX_SPLIT; ++i) {
+        if (i < ns) { ml[i] = mml[i * RS + rl]; a4[i] = macc[c4 * mrg_stride + i * RS + rl]; }
+        else { ml[i] = make_float2(-INFINITY, 0.f); a4[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      }
       float M = -INFINITY;
-      for (int i = 0; i < ns; ++i) M = fmaxf(M, mml[i * RS + rl].x);
+#pragma unroll
+      for (int i = 0; i < MAX_SPLIT; ++i) M = fmaxf(M, ml[i].x);
       float den = 0.f;
       float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = 0; i < ns; ++i) {
-        const float2 ml = mml[i * RS + rl];
-        if (ml.x == -INFINITY) continue;
-        const float w = ex2(ml.x - M);
-        den += ml.y * w;
-        const float4 a4 = macc[c4 * mrg_stride + i * RS + rl];
-        o4.x += a4.x * w; o4.y += a4.y * w; o4.z += a4.z * w; o4.w += a4.w * w;
+#pragma unroll
+      for (int i = 0; i < MAX_SPLIT; ++i) {
+        const float w = ml[i].x == -INFINITY ? 0.f : ex2(ml[i].x - M);
+        den += ml[i].y * w;
+        o4.x += a4[i].x * w; o4.y += a4[i].y * w; o4.z += a4[i].z * w; o4.w += a4[i].w * w;
       }
       const float inv = den > 0.f ? 1.f / den : 0.f;
       __nv_bfloat162 b0 = __floats2bfloat162_rn(o4.x * inv, o4.y * inv), b1 = __floats2bfloat162_rn(o4.z * inv, o4.w * inv);
@@ -677,9 +696,11 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
           make_uint2(*reinterpret_cast<uint32_t *>(&b0), *reinterpret_cast<uint32_t *>(&b1));
     }
   }
+  if (tid == 0) DBG(12);
   // every tcgen05 access of this CTA is complete (the softmax warps observed the last o_full): release TMEM
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) DBG(13);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));

@@ -356,7 +356,7 @@ __global__ void k_put_finish(Dev D, int B, int final, int slot, const int *d_slo
 struct BfsShared { int next_cnt[3]; int err; };  // three rotating level counters: one barrier per BFS level
 constexpr int BFS_U = 4;                         // frontier entries per thread and round
 static_assert(NT * BFS_U == 1024, "bfs_below searches its expansion table in 10 steps");
-struct ExpandTab { int start[NT * BFS_U + 1]; int src[NT * BFS_U]; int wsum[NT / 32]; int rbase; };  // see bfs_below
+struct ExpandTab { int start[NT * BFS_U + 1]; int src[NT * BFS_U]; int wsum[2][NT / 32]; int rbase; };  // see bfs_below
 constexpr int SFR = 1024;                        // shared-memory frontier entries per buffer (CL == 1)
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -402,6 +402,7 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
   const Node s = load_node<RO>(D.nodes + start);
   if (rank == 0 && tid == 0) { sh->next_cnt[0] = 0; sh->next_cnt[1] = 0; sh->next_cnt[2] = 0; }
   Frontier cur = {fr0, sfr}, nxt = {fr1, sfr ? sfr + SFR : nullptr};
+  int round = 0;
   int cnt = s.n_child;
   if (s.cap == 0) {
     if (rank == 0 && tid == 0 && cnt == 1) cur.put(0, s.child);
@@ -428,6 +429,7 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
     // U frontier entries per thread and iteration: the U node records (dependent on the U frontier loads) are all in
     // flight before the first is inspected - one record per thread at a time left a hot subtree latency-bound
     constexpr int U = BFS_U;
+    int level_base = 0;
     for (int base = rank * NT * U; base < cnt; base += CL * NT * U) {
       int id[U], push[U];
       Node nd[U];
@@ -460,28 +462,57 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
       int incl = mine;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) xt->wsum[warp_id()] = incl;
+      int *wsum = xt->wsum[round & 1];  // double buffered: the sparse path below has no second barrier
+      ++round;
+      if (lane == 31) wsum[warp_id()] = incl;
       __syncthreads();
       int woff = 0, total = 0;
 #pragma unroll
-      for (int w2 = 0; w2 < NT / 32; ++w2) { const int v = xt->wsum[w2]; if (w2 < warp_id()) woff += v; total += v; }
-      if (tid == 0) xt->rbase = total > 0 ? atomicAdd(push_cnt, total) : 0;
-      {
+      for (int w2 = 0; w2 < NT / 32; ++w2) { const int v = wsum[w2]; if (w2 < warp_id()) woff += v; total += v; }
+      if (total == 0) continue;  // uniform
+      const bool dense = total > 64;
+      int rbase;
+      if (CL == 1) {  // a lone CTA keeps the level's running count in a register: no atomic, no broadcast
+        rbase = level_base;
+        level_base += total;
+      } else {
+        if (tid == 0) xt->rbase = atomicAdd(push_cnt, total);
+      }
+      if (dense) {
         int off = woff + incl - mine;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool one = push[u] == 1 && nd[u].cap == 0;
           xt->start[tid * U + u] = off;
           xt->src[tid * U + u] = one ? -(nd[u].child + 1) : nd[u].child;
-          if (!one) ne += push[u];
           off += push[u];
         }
         if (tid == NT - 1) xt->start[NT * U] = total;
       }
-      __syncthreads();
-      const int rbase = xt->rbase;
-      if (total > 0 && rbase + total > D.fr_cap) {
+      if (dense || CL > 1) __syncthreads();
+      if (CL > 1) rbase = xt->rbase;
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (!(push[u] == 1 && nd[u].cap == 0)) ne += push[u];
+      if (rbase + total > D.fr_cap) {
         if (tid == 0) atomicOr(&sh->err, ERR_FRONTIER);
+      } else if (!dense) {
+        // a handful of children in the whole round (chains, cold subtrees): every thread appends its own
+        int pos = rbase + woff + incl - mine;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (push[u] == 1 && nd[u].cap == 0) nxt.put(pos, nd[u].child);
+          else {
+            for (int k0 = 0; k0 < push[u]; k0 += 4) {
+              int c[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                c[j] = k0 + j < push[u] ? (RO ? __ldg(&D.edges[nd[u].child + k0 + j].y) : D.edges[nd[u].child + k0 + j].y) : 0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) if (k0 + j < push[u]) nxt.put(pos + k0 + j, c[j]);
+            }
+          }
+          pos += push[u];
+        }
       } else {
         for (int f0 = 0; f0 < total; f0 += NT * 4) {
           int val[4];
@@ -502,10 +533,10 @@ __device__ __forceinline__ void bfs_below(const Dev &D, int start, int *fr0, int
           for (int j = 0; j < 4; ++j) { const int f = f0 + j * NT + tid; if (f < total) nxt.put(rbase + f, val[j]); }
         }
       }
-      __syncthreads();  // the table is rewritten by the next round
+      if ((dense || CL > 1) && base + CL * NT * U < cnt) __syncthreads();  // table / rbase are rewritten by the next round
     }
     sync_all();
-    cnt = *push_cnt;
+    cnt = CL == 1 ? level_base : *push_cnt;
     if (cnt > D.fr_cap) cnt = 0;  // overflowed level: err already set
     const Frontier t = cur; cur = nxt; nxt = t;
 #ifdef PIA_TRIE_PHASES
@@ -620,20 +651,18 @@ __device__ bool kth_value(SM *S, const Hist *h, long long rank, unsigned long lo
 // Builds the sorted candidate list of `parent`'s children for one DFS frame: children that pass the
 // threshold filter (lookahead_cache.py:264-272), ordered by fm descending, ties by insertion order (:254-258),
 // truncated to K (no more than K can still be emitted).
-template <int MAXS, int MAXD>
-__device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int K, int idx, int mode, double omw,
+template <int MAXS, int MAXD, int U>
+__device__ __noinline__ int build_frame_u(const Dev &D, GetSmem<MAXS, MAXD> *S, const Node p, int K, int idx, int mode, double omw,
                            double w, double min_in, double min_out, double min_mix, int *onode, int *otok,
                            unsigned char *oflag, unsigned long long &nv, unsigned long long &ne) {
   const int tid = threadIdx.x;
-  const Node p = D.nodes[parent];
   const int C = p.n_child;
 #ifdef PIA_TRIE_PHASES
   const unsigned long long tf0 = gtime();
 #endif
   int m = 0;  // current size of the running top list (uniform)
-  // child chunks whose records are fetched together: a frame below a hot node ranks thousands of children, and every
-  // chunk costs two dependent memory round trips (child entry -> record); only the fields the ranking needs are kept
-  constexpr int U = 8;
+  // U child chunks are fetched together: a frame below a hot node ranks thousands of children, and every chunk costs
+  // two dependent memory round trips (child entry -> record); only the fields the ranking needs are kept
   struct Slim { int token, n_child; double fo; float fi; };
   for (int base = 0; base < C; base += NT * U) {
     int cid[U];
@@ -726,6 +755,17 @@ __device__ __noinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, in
 #endif
 #endif
   return m;
+}
+
+// narrow nodes (the common case) take the 2-chunk instance: its registers stay registers; wide nodes the 8-chunk one
+template <int MAXS, int MAXD>
+__device__ __forceinline__ int build_frame(const Dev &D, GetSmem<MAXS, MAXD> *S, int parent, int K, int idx, int mode, double omw,
+                           double w, double min_in, double min_out, double min_mix, int *onode, int *otok,
+                           unsigned char *oflag, unsigned long long &nv, unsigned long long &ne) {
+  const Node p = load_node<true>(D.nodes + parent);
+  if (p.n_child <= 2 * NT)
+    return build_frame_u<MAXS, MAXD, 2>(D, S, p, K, idx, mode, omw, w, min_in, min_out, min_mix, onode, otok, oflag, nv, ne);
+  return build_frame_u<MAXS, MAXD, 8>(D, S, p, K, idx, mode, omw, w, min_in, min_out, min_mix, onode, otok, oflag, nv, ne);
 }
 
 // Tree.get (lookahead_cache.py:65-144) for the tree rooted at `root`, query suffix q[0..nq).
@@ -1559,7 +1599,9 @@ extern "C" int pia_trie_get(pia_trie_t *t, const int32_t *d_queries, const int32
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;  // no programmatic-serialization attribute: the kernel has no griddepcontrol.wait
+  // no programmatic-serialization attribute: the kernel has no griddepcontrol.wait; no cluster attribute either for the
+  // ordinary one-CTA-per-row launch
+  cfg.attrs = attr; cfg.numAttrs = cl > 1 ? 1 : 0;
   if (decoding_length <= 64 && branch_length <= 16) {
     cfg.dynamicSmemBytes = sizeof(GetSmem<64, 16>);
     PIA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_get<64, 16>, t->dev, P));

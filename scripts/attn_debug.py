@@ -42,7 +42,7 @@ torch.cuda.synchronize()
 dbg = torch.zeros((ns.value * ng.value, 16), dtype=torch.int64, device=dev)
 L.check(plan.lib.pia_attn_plan_set_debug(plan.h, dbg.data_ptr()))
 names = ['start', 'setup done', 'tma0 issued', 'qk0 issued', 'mma done', 'q loaded', 's0 ready', 'p0 written',
-         'o0 ready', 'tiles done', 'row written', 'cta end']
+         'o0 ready', 'tiles done', 'row written', 'cta end', 'combined(t0)', 'synced(t0)', 'barrier A', 'pushed']
 for trial in range(3):
     dbg.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -47,6 +47,25 @@ seq2 = torch.zeros((1, 64), dtype=torch.int32, device=dev)
 seq2[0, :2] = torch.tensor(doc[40:42], dtype=torch.int32, device=dev)
 us, nv, o = timed(seq2, n)
 print('cold query: %.1f us, %d nodes visited, draft n %d' % (us, nv, int(o['n'][0])))
+# a sample of ordinary queries (adjacent pairs of the documents), each timed alone
+import numpy as np  # noqa: E402
+rng = np.random.default_rng(5)
+res = []
+for _ in range(int(os.environ.get('SAMPLE', 150))):
+    d = docs[int(rng.integers(0, len(docs)))]
+    j = int(rng.integers(0, len(d) - 2))
+    sq = torch.zeros((1, 64), dtype=torch.int32, device=dev)
+    sq[0, :2] = torch.tensor(d[j:j + 2], dtype=torch.int32, device=dev)
+    us, nv, o = timed(sq, n, reps=5)
+    res.append((us, nv, int(o['n'][0])))
+a = np.array(res)
+order = np.argsort(a[:, 1])
+print('sample of %d pair queries: mean %.1f us, p50 %.1f, p90 %.1f, max %.1f; nodes visited p50 %d p90 %d max %d'
+      % (len(a), a[:, 0].mean(), np.percentile(a[:, 0], 50), np.percentile(a[:, 0], 90), a[:, 0].max(),
+         np.percentile(a[:, 1], 50), np.percentile(a[:, 1], 90), a[:, 1].max()))
+for lo in range(0, len(a), len(a) // 5):
+    sl = a[order[lo:lo + len(a) // 5]]
+    print('   visited %6d..%6d: mean %.1f us (draft n %.0f)' % (sl[:, 1].min(), sl[:, 1].max(), sl[:, 0].mean(), sl[:, 2].mean()))
 if os.environ.get('SKIP_SCAN'):
     sys.exit(0)
 r = bench.trie_roofline(dev, n_docs=1500, n_queries=4096)
