@@ -18,6 +18,7 @@ left padding, max_length - lives in device scalars, so one captured graph serves
 The runtime is organised in request SLOTS (include/pia_b200.h pia_slots_t): this per-request loop runs one slot,
 the batched loop (pretrained_model_batch.py) one slot per request, a prefill pass one slot per 64-row prompt chunk.
 There is no CPU fallback."""
+import os
 import time
 from collections import OrderedDict
 from threading import Thread
@@ -129,6 +130,8 @@ class _Runtime(object):
         self.graphs = OrderedDict()
         self.replays = 0
         self.kernels_per_graph = 0
+        self.prefill_graphs, self.prefill_kernels, self.prefill_warm = {}, {}, set()
+        self.graph_launches = 0  # kernels of replayed prefill graphs
         self.accepts = {}
         self.pad_host = 0
 
@@ -457,15 +460,22 @@ class LookaheadPreTrainedModel(nn.Module):
             # step k+1 is enqueued before the host reads record k: the ~0.25 ms of host work per step (record read,
             # python bookkeeping, streamer) overlaps the next verify forward; a step that runs after `finished` was
             # raised changes nothing on the device (pia_accept no-op, zero-length stream_put)
+            # A step launched ahead of the one that ends the request is a whole wasted forward (3.5 ms at 7B): near the end
+            # of the length budget - when the step in flight could already exhaust it (a step accepts at most
+            # branch_length + 1 tokens) - the next step is only launched once the record has been read.  An EOS / stop
+            # still costs the one step that was in flight.
             events = [torch.cuda.Event(), torch.cuda.Event()]
             k = 0
+            launched = 1
             graphs[0].replay()
             events[0].record(stream)
             rt.replays += 1
             while True:
-                graphs[(k + 1) & 1].replay()
-                events[(k + 1) & 1].record(stream)
-                rt.replays += 1
+                if launched == k + 1 and max_length - (prompt_len + len(new_tokens)) > bl + 1:
+                    graphs[launched & 1].replay()
+                    events[launched & 1].record(stream)
+                    rt.replays += 1
+                    launched += 1
                 events[k & 1].synchronize()
                 rec = rt.record_host[k & 1][0]
                 count, fin, n, status = int(rec[0]), int(rec[1]), int(rec[2]), int(rec[3])
@@ -492,7 +502,13 @@ class LookaheadPreTrainedModel(nn.Module):
                 k += 1
                 if fin:
                     break
-            events[k & 1].synchronize()  # the step launched ahead (a no-op on the device) has drained
+                if launched == k:  # near the end of the budget: launch only now that the request is known to go on
+                    graphs[launched & 1].replay()
+                    events[launched & 1].record(stream)
+                    rt.replays += 1
+                    launched += 1
+            if launched > k:
+                events[k & 1].synchronize()  # a step launched ahead (a no-op on the device) has drained
         if use_trie:  # :1237-1238
             trie.stream_put([], branch_length=bl + 1, final=True, mode='output', idx=0)
         if streamer is not None:
@@ -608,11 +624,33 @@ class LookaheadPreTrainedModel(nn.Module):
                 pb.mask.copy_(rt.chain.repeat(C, 1))
                 rt.pf_mask_dirty = False
             last = pos + m >= prompt_len
-            self._verify_layers(rt, bufs=pb, last_only=not last)
+            self._prefill_pass(rt, pb, slot, last)
             torch.cuda.current_stream().synchronize()  # pf_meta_host is rewritten by the next pass
             pos += m
         last_row = (prompt_len - 1) % (R * C)
         return pb.y[last_row:last_row + 1]
+
+    def _prefill_pass(self, rt, pb, slot, last):
+        """one pass of the prompt through the layers.  Everything a pass depends on (ids, chunk table, masks, cursors)
+        lives in device buffers, so the ~350 launches are captured once per (slot, last) - the first pass of a runtime
+        runs eagerly (library handles / workspaces come into being outside a capture), the second is captured, later
+        ones replay: an eager pass is bound by the host's launch rate, not by the GPU."""
+        key = (slot, last)
+        g = rt.prefill_graphs.get(key)
+        if g is None:
+            if key not in rt.prefill_warm or os.environ.get('PIA_PREFILL_GRAPH', '1') == '0':
+                rt.prefill_warm.add(key)
+                self._verify_layers(rt, bufs=pb, last_only=not last)
+                return
+            torch.cuda.current_stream().synchronize()
+            l0 = ops.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._verify_layers(rt, bufs=pb, last_only=not last)
+            rt.prefill_graphs[key] = g
+            rt.prefill_kernels[key] = ops.launch_count() - l0
+        g.replay()
+        rt.graph_launches += rt.prefill_kernels[key]   # libpia_b200 kernels replayed (bench.py gpu_launches)
 
     def _prefill_logits(self, rt, prompt_len, slot=0, row=0):
         """prefill of slot `slot` + the last prompt row's logits into rt.logits[row]"""
