@@ -102,5 +102,8 @@ for f in sorted(os.listdir(GO)):
     elif f.endswith('.ncu-rep'):
         full(p, f[:-8])
 if TRAFFIC:
-    json.dump({k: float(sum(v) / len(v)) for k, v in TRAFFIC.items()}, open(os.path.join(OUT, f'{tag}_traffic.json'), 'w'), indent=1)
+    tp = os.path.join(OUT, f'{tag}_traffic.json')
+    merged = json.load(open(tp)) if os.path.exists(tp) else {}   # captures summarised earlier stay
+    merged.update({k: float(sum(v) / len(v)) for k, v in TRAFFIC.items()})
+    json.dump(merged, open(tp, 'w'), indent=1, sort_keys=True)
 print(sorted(os.listdir(OUT)))
