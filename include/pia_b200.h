@@ -134,6 +134,12 @@ int pia_trie_copy_error_flags(pia_trie_t *t, int32_t *d_out, void *stream);
 /* per-tree counters Tree.n_node / n_output_node (lookahead_cache.py:29-30); -1 when the tree is absent. Synchronous. */
 int pia_trie_tree_counters(pia_trie_t *t, int token, int64_t *h_n_node, int64_t *h_n_output_node, void *stream);
 
+/* Storage reclamation (the reference relies on Python's garbage collection after Tree._squeeze pops nodes,
+ * lookahead_cache.py:302-310, and on dict growth): copies the reachable forest to the front of the pools (host round
+ * trip), child order, counts, per-tree counters and touched-tree lists unchanged; clears the pool-exhausted error bits.
+ * h_nodes_before / h_nodes_after (optional) receive the node-pool fill before and after.  Synchronous, between requests. */
+int pia_trie_compact(pia_trie_t *t, int64_t *h_nodes_before, int64_t *h_nodes_after, void *stream);
+
 /* Persistence (LookaheadCache.save_mem / load_mem, lookahead_cache.py:578-587): the forest as raw pools in HOST
  * memory.  Node record (32 bytes): {int32 token, int32 n_child, int32 child, int32 cap, double fo, float fi, int32 aux};
  * cap == 0: `child` is the node id of the only child, else the offset of a block of (int32 token, int32 node) entries,

@@ -70,6 +70,7 @@ SYMBOLS = {
     'pia_trie_stats': (C.c_int, [vp, C.POINTER(TrieStats), vp]),
     'pia_trie_copy_error_flags': (C.c_int, [vp, vp, vp]),
     'pia_trie_tree_counters': (C.c_int, [vp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
+    'pia_trie_compact': (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     'pia_trie_export_sizes': (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]),
     'pia_trie_export': (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),
     'pia_trie_import': (C.c_int, [vp, vp, C.c_int64, vp, C.c_int64, vp, vp, vp, vp]),

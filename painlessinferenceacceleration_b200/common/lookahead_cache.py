@@ -76,6 +76,8 @@ class LookaheadCache(object):
                  vocab_capacity=262144, node_capacity=1 << 24, edge_capacity=None, n_input_slots=8,
                  max_put_tokens=16384, frontier_capacity=1 << 18, max_resident_queries=296):
         self.debug = debug
+        self._node_capacity = node_capacity
+        self._edge_capacity = edge_capacity if edge_capacity is not None else node_capacity
         self._t = _DeviceTrie(device, eos_ids, stop_words, max_node, max_output_node, vocab_capacity, node_capacity,
                               edge_capacity if edge_capacity is not None else node_capacity, n_input_slots,
                               max_put_tokens, frontier_capacity, max_resident_queries)
@@ -329,6 +331,23 @@ class LookaheadCache(object):
         with torch.cuda.device(self._t.device):
             L.check(self._t.lib.pia_trie_stats(self._t.h, C.byref(s), self._t.stream()))
         return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def compact(self):
+        """reclaims the storage of squeezed / abandoned nodes and child blocks (pia_trie_compact): the reachable forest
+        is copied to the front of the pools; nothing a get / put can observe changes.  Returns (nodes before, after).
+        The reference gets this from Python's garbage collector (Tree._squeeze pops nodes, lookahead_cache.py:302-310)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        with torch.cuda.device(self._t.device):
+            L.check(self._t.lib.pia_trie_compact(self._t.h, C.byref(a), C.byref(b), self._t.stream()))
+        return a.value, b.value
+
+    def maybe_compact(self, threshold=0.75):
+        """compact() once a pool is more than `threshold` full; the generation loops call this between requests.  If
+        the forest itself (not garbage) fills the pools the warning of warn_trie_errors() still applies."""
+        s = self.stats()
+        if s['nodes_used'] > threshold * self._node_capacity or s['edges_used'] > threshold * self._edge_capacity:
+            return self.compact()
+        return None
 
     def tree_counters(self, token_id):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -132,6 +132,7 @@ class _Runtime(object):
         self.kernels_per_graph = 0
         self.prefill_graphs, self.prefill_kernels, self.prefill_warm = {}, {}, set()
         self.graph_launches = 0  # kernels of replayed prefill graphs
+        self.last_compact_check = 0
         self.accepts = {}
         self.pad_host = 0
 
@@ -511,6 +512,9 @@ class LookaheadPreTrainedModel(nn.Module):
                 events[k & 1].synchronize()  # a step launched ahead (a no-op on the device) has drained
         if use_trie:  # :1237-1238
             trie.stream_put([], branch_length=bl + 1, final=True, mode='output', idx=0)
+            if rt.replays - rt.last_compact_check >= 2048:   # every few thousand steps: reclaim squeezed storage if a pool fills up
+                rt.last_compact_check = rt.replays
+                trie.maybe_compact()
         if streamer is not None:
             streamer.end()
         out_ids = torch.cat([input_ids.to(dev), torch.tensor([new_tokens], dtype=input_ids.dtype, device=dev)], dim=1)

@@ -233,6 +233,9 @@ class LookaheadPreTrainedModel(_Base):
             ts = te
         for i in range(bs):                              # :1287-1289
             trie.stream_put([], branch_length=bl + 1, final=True, mode='output', idx=i)
+        if rt.replays - rt.last_compact_check >= 2048:   # reclaim squeezed trie storage if a pool fills up
+            rt.last_compact_check = rt.replays
+            trie.maybe_compact()
         if streamer is not None:
             streamer.end()
         width = prompt_len + max(len(x) for x in seqs)

@@ -1707,6 +1707,95 @@ extern "C" int pia_trie_export(pia_trie_t *t, void *h_nodes, int64_t n_nodes, vo
   return PIA_OK;
 }
 
+// Storage reclamation.  The pools are bump allocators: squeeze unlinks subtrees (the reference pops them, :302-310, and
+// Python frees them), grown child blocks are abandoned, and every request's input-mode prompt adds up to
+// prompt_len * (branch_length + 1) nodes, so a long-running process would sooner or later exhaust a pool and stop
+// learning.  pia_trie_compact copies the REACHABLE forest (host round trip: D2H, depth-first renumbering so that chains
+// stay contiguous, child order kept, blocks trimmed to the next power of two >= 4, H2D) and resets the allocator tops.
+// Nothing a query or an update can observe changes: same trees, children, order, counts, per-tree counters, touched-tree
+// lists.  Synchronous; call it between requests (LookaheadCache.maybe_compact does, past a fill threshold).
+extern "C" int pia_trie_compact(pia_trie_t *t, int64_t *h_nodes_before, int64_t *h_nodes_after, void *stream) {
+  PIA_REQUIRE(t, "null trie");
+  cudaStream_t s = (cudaStream_t)stream;
+  PIA_CUDA_CHECK(cudaStreamSynchronize(s));
+  Hdr h;
+  PIA_CUDA_CHECK(cudaMemcpy(&h, t->dev.hdr, sizeof(h), cudaMemcpyDeviceToHost));
+  const int64_t nn = (int64_t)(h.node_top < (unsigned long long)t->cfg.node_capacity ? h.node_top : t->cfg.node_capacity);
+  const int64_t ne = (int64_t)(h.edge_top < (unsigned long long)t->cfg.edge_capacity ? h.edge_top : t->cfg.edge_capacity);
+  const int V = t->cfg.vocab_capacity, extra = t->cfg.n_input_slots - 1;
+  std::vector<Node> on((size_t)nn), nw;
+  std::vector<int2> oe((size_t)ne), we;
+  std::vector<int> root((size_t)V), newid((size_t)nn, -1), order;
+  std::vector<float> ofx((size_t)extra * nn), nfx;
+  if (nn) PIA_CUDA_CHECK(cudaMemcpy(on.data(), t->dev.nodes, (size_t)nn * sizeof(Node), cudaMemcpyDeviceToHost));
+  if (ne) PIA_CUDA_CHECK(cudaMemcpy(oe.data(), t->dev.edges, (size_t)ne * sizeof(int2), cudaMemcpyDeviceToHost));
+  PIA_CUDA_CHECK(cudaMemcpy(root.data(), t->dev.root_of, (size_t)V * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int e = 0; e < extra; ++e)
+    if (nn) PIA_CUDA_CHECK(cudaMemcpy(ofx.data() + (size_t)e * nn, t->dev.fi_extra + (size_t)e * t->cfg.node_capacity,
+                                      (size_t)nn * sizeof(float), cudaMemcpyDeviceToHost));
+  auto child_of = [&](const Node &p, int k) -> int {
+    if (p.cap == 0) return p.child;
+    const long long o = (long long)p.child + k;
+    return (o >= 0 && o < ne) ? oe[(size_t)o].y : -1;
+  };
+  // pass 1: depth-first pre-order numbering of everything reachable from a root
+  order.reserve((size_t)nn);
+  std::vector<int> stack;
+  for (int tok = 0; tok < V; ++tok) {
+    const int r = root[tok];
+    if (r < 0 || r >= nn || newid[r] >= 0) continue;
+    stack.push_back(r);
+    while (!stack.empty()) {
+      const int i = stack.back();
+      stack.pop_back();
+      if (i < 0 || i >= nn || newid[i] >= 0) continue;
+      newid[i] = (int)order.size();
+      order.push_back(i);
+      const Node &p = on[i];
+      for (int k = p.n_child - 1; k >= 0; --k) stack.push_back(child_of(p, k));  // first child numbered next
+    }
+  }
+  // pass 2: records and trimmed child blocks
+  const size_t live = order.size();
+  nw.resize(live);
+  nfx.resize((size_t)extra * live);
+  for (size_t j = 0; j < live; ++j) {
+    const int i = order[j];
+    Node p = on[i];
+    if (p.n_child <= 0) { p.n_child = 0; p.child = -1; p.cap = 0; }
+    else if (p.cap == 0) { const int c = child_of(on[i], 0); p.child = (c >= 0 && c < nn) ? newid[c] : -1; if (p.child < 0) p.n_child = 0; }
+    else {
+      int cap = 4;
+      while (cap < p.n_child) cap *= 2;
+      const size_t off = we.size();
+      we.resize(off + (size_t)cap, make_int2(-1, -1));
+      for (int k = 0; k < p.n_child; ++k) {
+        const long long o = (long long)on[i].child + k;
+        int2 e = (o >= 0 && o < ne) ? oe[(size_t)o] : make_int2(-1, -1);
+        e.y = (e.y >= 0 && e.y < nn) ? newid[e.y] : -1;
+        we[off + k] = e;
+      }
+      p.child = (int)off; p.cap = cap;
+    }
+    nw[j] = p;
+    for (int e = 0; e < extra; ++e) nfx[(size_t)e * live + j] = ofx[(size_t)e * nn + i];
+  }
+  PIA_REQUIRE((int64_t)we.size() <= t->cfg.edge_capacity, "compacted child blocks do not fit the edge pool");
+  for (int tok = 0; tok < V; ++tok) if (root[tok] >= 0) root[tok] = root[tok] < nn ? newid[root[tok]] : -1;
+  if (live) PIA_CUDA_CHECK(cudaMemcpy(t->dev.nodes, nw.data(), live * sizeof(Node), cudaMemcpyHostToDevice));
+  if (!we.empty()) PIA_CUDA_CHECK(cudaMemcpy(t->dev.edges, we.data(), we.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  PIA_CUDA_CHECK(cudaMemcpy(t->dev.root_of, root.data(), (size_t)V * sizeof(int), cudaMemcpyHostToDevice));
+  for (int e = 0; e < extra; ++e)
+    if (live) PIA_CUDA_CHECK(cudaMemcpy(t->dev.fi_extra + (size_t)e * t->cfg.node_capacity, nfx.data() + (size_t)e * live,
+                                        live * sizeof(float), cudaMemcpyHostToDevice));
+  h.node_top = (unsigned long long)live; h.edge_top = (unsigned long long)we.size();
+  h.err &= ~(ERR_NODE_POOL | ERR_EDGE_POOL);  // room again: inserts resume (what was dropped while full stays dropped)
+  PIA_CUDA_CHECK(cudaMemcpy(t->dev.hdr, &h, sizeof(h), cudaMemcpyHostToDevice));
+  if (h_nodes_before) *h_nodes_before = nn;
+  if (h_nodes_after) *h_nodes_after = (int64_t)live;
+  return PIA_OK;
+}
+
 // replaces the whole forest (like `self.mem = pickle.loads(...)`, :587); pending update sets are dropped
 extern "C" int pia_trie_import(pia_trie_t *t, const void *h_nodes, int64_t n_nodes, const void *h_edges, int64_t n_edges,
                                const int32_t *h_root_of, const int32_t *h_n_node, const int32_t *h_n_out, void *stream) {

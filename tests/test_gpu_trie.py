@@ -209,3 +209,58 @@ def test_pruned_walk_and_cluster_walk_match_the_full_walk(monkeypatch):
     assert visited[0] * 2 < visited[1], visited      # the pruned walk really skips most of the hot subtrees
     for c in caches:
         assert c.stats()['error_flags'] == 0
+
+
+def test_compact_reclaims_storage_and_changes_nothing_observable():
+    """pia_trie_compact after squeezes and request resets: every query answers as before, the per-tree counters, the
+    update lists' effects (a later squeeze) and further puts behave identically to an uncompacted twin, and the pools
+    shrink."""
+    LookaheadCache = _gpu_cache_cls()
+    rng = np.random.default_rng(21)
+
+    def stream(c, seed, n_req):
+        r = np.random.default_rng(seed)
+        for req in range(n_req):
+            prompt = np.clip(r.zipf(1.3, size=int(r.integers(20, 120))), 3, 4999).tolist()
+            c.put(prompt[1:], branch_length=9, final=False, mode='input', idx=req % 2)
+            for _ in range(int(r.integers(2, 12))):
+                c.stream_put(np.clip(r.zipf(1.3, size=int(r.integers(1, 9))), 3, 4999).tolist(), branch_length=9,
+                             final=False, mode='output', idx=req % 2)
+            c.stream_put([], branch_length=9, final=True, mode='output', idx=req % 2)
+
+    # pools large enough for the UNcompacted twin to survive the whole test (it leaks ~0.8 M nodes per 1200 requests)
+    twins = [LookaheadCache(eos_ids=[2], max_node=64, max_output_node=24, n_input_slots=2, node_capacity=1 << 22)
+             for _ in range(2)]
+    for c in twins:
+        stream(c, 1, 1200)          # > 1024 touched trees: squeezes happen (tiny per-tree limits)
+    before = twins[0].stats()
+    nb, na = twins[0].compact()
+    after = twins[0].stats()
+    assert nb == before['nodes_used'] and na == after['nodes_used'] and na < 0.8 * nb, (nb, na)
+    assert after['edges_used'] <= before['edges_used'] and after['n_trees'] == before['n_trees']
+    assert after['error_flags'] == 0
+    qs = [rng.integers(3, 40, size=2).tolist() for _ in range(300)] + [[3, 3], [4, 3], [3]]
+
+    def answers():
+        out = []
+        for q in qs:
+            rows = []
+            for c in twins:
+                ids, m, sizes = c.hier_get(list(q), decoding_length=64, branch_length=8, min_output_size=32)
+                rows.append(([int(x) for x in ids], R.mask_rows(m), [int(x) for x in sizes]))
+            assert rows[0] == rows[1], (q, rows)
+            out.append(rows[0])
+        return out
+
+    a1 = answers()
+    assert sum(len(r[0]) > 1 for r in a1) > 50
+    for t in (3, 4, 5, 17):
+        assert twins[0].tree_counters(t) == twins[1].tree_counters(t)
+    for c in twins:                 # life goes on identically: more requests (and squeezes) on both
+        stream(c, 2, 1100)
+    answers()
+    s0, s1 = twins[0].stats(), twins[1].stats()
+    assert s0['error_flags'] == 0 and s1['error_flags'] == 0
+    assert s0['n_trees'] == s1['n_trees'] and s0['nodes_used'] < s1['nodes_used']
+    assert twins[0].maybe_compact(threshold=2.0) is None and twins[1].maybe_compact(threshold=0.0) is not None
+    answers()
