@@ -289,6 +289,13 @@ def run_ours(args):
     second = timed_pass(host_io=False)  # second pass: the trie has seen every answer once (the round-1 headline regime)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    my_clk = sampler.summary()          # every rank samples its own GPU; rank 0 prints them all
+    per_rank_clocks = [dict(my_clk, n_throttle_reasons=len(my_clk['reasons']))]
+    if world > 1:
+        t = torch.tensor([my_clk['sm_mhz'] or 0, my_clk['sm_max_mhz'] or 0, len(my_clk['reasons'])], device=dev)
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        per_rank_clocks = [{'sm_mhz': int(c[0]), 'sm_max_mhz': int(c[1]), 'n_throttle_reasons': int(c[2])} for c in allc]
     same_tokens = all(torch.equal(a.cpu(), b.cpu()) for a, b in zip(res['outs'], e2e['outs']))
     extra = {}
     if rank == 0:
@@ -319,6 +326,7 @@ def run_ours(args):
             'config': workload_config(args, world, src),
             'clocks': sampler.summary(),
             'per_rank_ms': res['per_rank_ms'],
+            'per_rank_clocks': per_rank_clocks,
             'e2e': {'value': e2e['tokens'] / (e2e['ms'] / 1e3), 'unit': 'tokens/s',
                     'h2d_bytes_per_step': PROMPT_LEN * 8,
                     'd2h_bytes_per_step': int((PROMPT_LEN + NEW_TOKENS) * 8 + (e2e['steps'] / max(K * world, 1)) * 4 * (5 + DL)),

@@ -180,13 +180,6 @@ class LlamaForCausalLM(LookaheadPreTrainedModel):
                 inv_freq = 1.0 / (base ** (torch.arange(0, hd, 2, dtype=torch.int64).float().to(dev) / hd))
         else:                        # the reference raises on unknown types as well (:241 `Unknown RoPE scaling type`)
             raise ValueError(f'Unknown RoPE scaling type {rtype}')
-        window = getattr(c, 'sliding_window', None)
-        if window is not None and max_pos > int(window) + 8:
-            # the reference ignores the window on the lookahead branch (mistral/modeling_mistral.py:979-982);
-            # so does this kernel - say so instead of silently diverging from sliding-window checkpoints
-            import warnings
-            warnings.warn(f'sliding_window={window} is ignored on the lookahead path (as in the reference); contexts '
-                          f'beyond it attend to the full prefix')
         freqs = pos[:, None] * inv_freq[None, :]
         return freqs.cos().to(torch.bfloat16).contiguous(), freqs.sin().to(torch.bfloat16).contiguous()
 

@@ -14,6 +14,7 @@ from torch import nn
 
 from ...common import ops
 from ..llama.modeling_llama import LlamaDecoderLayer, LlamaForCausalLM, LlamaModel
+from ..mistral.modeling_mistral import warn_sliding_window
 
 
 class MixtralRouter(nn.Module):
@@ -53,6 +54,10 @@ class MixtralForCausalLM(LlamaForCausalLM):
 
     def _fuse_mlp(self, layer):
         pass  # experts are stored fused ([E, 2I, H]) already
+
+    def rope_tables(self, max_pos):
+        warn_sliding_window(self.config, max_pos)  # mixtral/modeling_mixtral.py:1032-1036: no window on the lookahead branch
+        return super().rope_tables(max_pos)
 
     def _convert_checkpoint_keys(self, sd):
         """published Mixtral checkpoints (and the reference, mixtral/modeling_mixtral.py:692-759) name the MoE block

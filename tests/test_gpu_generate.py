@@ -9,7 +9,7 @@ whose oracle margin is below MARGIN, and requires that the great majority of seq
 import pytest
 import torch
 
-from tests.tiny_models import prompts, tiny_hf_model
+from tests.tiny_models import prompts, tiny_config, tiny_hf_model
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -431,3 +431,27 @@ def test_gpt2_verify_logits_and_loop():
             same += int(plain[0].tolist() == out.sequences[0].tolist())
     assert max(edl_all) > 2
     assert same >= 4   # a draft of 1 vs 16 nodes changes the KV split count, i.e. the fp32 summation order (bf16 near-ties)
+
+
+@pytest.mark.parametrize('family', ['mistral', 'mixtral'])
+def test_sliding_window_checkpoints_warn_instead_of_diverging_silently(family):
+    """the reference's lookahead branch ignores the window (mistral/modeling_mistral.py:979-982), so does the kernel:
+    a config that sets one gets a warning as soon as a context can outgrow it, and the same tokens as without it"""
+    from painlessinferenceacceleration_b200.models.mistral.modeling_mistral import MistralForCausalLM
+    from painlessinferenceacceleration_b200.models.mixtral.modeling_mixtral import MixtralForCausalLM
+    hf = tiny_hf_model(family, seed=3, dtype=torch.bfloat16, device=DEV, vocab=200)
+    cls = MixtralForCausalLM if family == 'mixtral' else MistralForCausalLM
+    outs = []
+    for window in (None, 16):
+        cfg = tiny_config(family, vocab=200, sliding_window=window)
+        ours = cls(cfg, device=torch.device(DEV))
+        assert not ours.load_state_dict(hf.state_dict(), strict=False).missing_keys
+        ids = prompts(5, 1, 24, 200)[0].to(DEV)
+        kw = dict(input_ids=ids, max_new_tokens=12, eos_token_id=2,
+                  decoding_kwargs={'use_lookahead': True, 'decoding_length': 64, 'branch_length': 8})
+        if window is None:
+            outs.append(ours.generate(**kw))
+        else:
+            with pytest.warns(UserWarning, match='sliding_window=16 is ignored'):
+                outs.append(ours.generate(**kw))
+    assert torch.equal(outs[0], outs[1])
