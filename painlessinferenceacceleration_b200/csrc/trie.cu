@@ -356,7 +356,9 @@ __global__ void k_put_finish(Dev D, int B, int final, int slot, const int *d_slo
 struct BfsShared { int next_cnt[3]; int err; };  // three rotating level counters: one barrier per BFS level
 constexpr int BFS_U = 4;                         // frontier entries per thread and round
 static_assert(NT * BFS_U == 1024, "bfs_below searches its expansion table in 10 steps");
-struct ExpandTab { int start[NT * BFS_U + 1]; int src[NT * BFS_U]; int wsum[2][NT / 32]; int rbase; };  // see bfs_below
+// wsum is 16-byte aligned: the compiler reads it with 128-bit loads, and unaligned those reach back into src[]
+// (harmless, but compute-sanitizer racecheck reports the overlap with the thread that writes src's last entry)
+struct ExpandTab { int start[NT * BFS_U + 1]; int src[NT * BFS_U]; alignas(16) int wsum[2][NT / 32]; int rbase; };  // see bfs_below
 constexpr int SFR = 1024;                        // shared-memory frontier entries per buffer (CL == 1)
 
 __device__ __forceinline__ void cluster_sync_all() {
