@@ -457,7 +457,7 @@ def attention_roofline(model, dev):
     hbm, tf, src = peaks()
     ach = by / (us * 1e-6) / 1e9
     return {'kernel': 'k_tree_attn (one layer)', 'bound': 'hbm', 'achieved': ach, 'peak': hbm,
-            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_attn_short', 'k_tree_attn'),
+            'unit': 'GB/s', 'frac': ach / hbm, 'traffic': ncu_traffic('prof_attn_gqa_r' if g['n_kv_heads'] != g['n_q_heads'] else 'prof_attn_short', 'k_tree_attn'),
             'bytes_per_launch': by, 'us_per_launch': us, 'tensor_tflops': fl / (us * 1e-6) / 1e12,
             'tensor_frac': fl / (us * 1e-6) / 1e12 / tf,
             'shape': f'n={n} P={P} Hq={g["n_q_heads"]} Hkv={g["n_kv_heads"]} D={g["head_dim"]}', 'peak_source': src}
