@@ -224,10 +224,15 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
   const uint32_t bar0 = base + SMEM_BAR;
   const uint32_t bar_kv_full = bar0, bar_kv_empty = bar0 + 8 * NSTAGE, bar_s_full = bar0 + 16 * NSTAGE,
                  bar_p_full = bar_s_full + 16, bar_o_full = bar_p_full + 16, bar_q_full = bar_o_full + 8,
-                 bar_o_free = bar_q_full + 8, bar_draft = bar_o_free + 8;
+                 bar_o_free = bar_q_full + 8, bar_draft = bar_o_free + 8,
+                 bar_v_full = bar0 + 128;  // V tiles complete on their own barriers: QK^T starts as soon as K has landed
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + SMEM_BAR + 16 * NSTAGE + 64);
 
   pdl_launch_dependents();
+  if (tid == 0) {  // the two TMA descriptors are fetched while the barriers / TMEM are set up
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(&map_v)) : "memory");
+  }
   // Programmatic dependent launch: this CTA may be running while its predecessor (RoPE + KV append of the same layer)
   // still is.  What is read BEFORE griddepcontrol.wait is safe to read early: d_n / d_prefix_len / d_pad_len / the mask
   // rows were written before the first kernel of the layer chain (trie get and the previous step's accept are launched
@@ -285,7 +290,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
 
   // ---- setup
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_kv_full + 8 * s, 1); mbar_init(bar_kv_empty + 8 * s, 1); mbar_init(bar_v_full + 8 * s, 1); }
     mbar_init(bar_s_full, 1); mbar_init(bar_s_full + 8, 1);
     mbar_init(bar_p_full, 2 * rows_used); mbar_init(bar_p_full + 8, 2 * rows_used);
     mbar_init(bar_o_free, 2 * rows_used);
@@ -318,6 +323,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         const int s = i % NSTAGE, ph = (i / NSTAGE) & 1;
         if (has_draft && i == 0) {  // staged by the softmax warps (bar_draft); this arrive only keeps the phases aligned
           mbar_arrive(bar_kv_full);
+          mbar_arrive(bar_v_full);
           continue;
         }
         const int key0 = tile_of(i) * BN;
@@ -325,12 +331,13 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         // appended by this very launch - finite bf16 either way, and masked), nothing to wait for
         if (!fused && !waited && key0 + BN > p_safe) { pdl_wait(); waited = true; }
         mbar_wait(bar_kv_empty + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_kv_full + 8 * s, 2 * TILE_BYTES);
         const uint32_t kd = base + SMEM_K + s * TILE_BYTES, vd = base + SMEM_V + s * TILE_BYTES;
+        mbar_expect_tx(bar_kv_full + 8 * s, TILE_BYTES);
         tma_load_3d(kd, &map_k, bar_kv_full + 8 * s, 0, key0, plane);
         tma_load_3d(kd + SUB, &map_k, bar_kv_full + 8 * s, 64, key0, plane);
-        tma_load_3d(vd, &map_v, bar_kv_full + 8 * s, 0, key0, plane);
-        tma_load_3d(vd + SUB, &map_v, bar_kv_full + 8 * s, 64, key0, plane);
+        mbar_expect_tx(bar_v_full + 8 * s, TILE_BYTES);
+        tma_load_3d(vd, &map_v, bar_v_full + 8 * s, 0, key0, plane);
+        tma_load_3d(vd + SUB, &map_v, bar_v_full + 8 * s, 64, key0, plane);
         if (i == 0) DBG(2);
       }
     }
@@ -362,6 +369,7 @@ k_tree_attn(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ C
         const int s = i % NSTAGE;
         mbar_wait(bar_p_full + 8 * (i & 1), (i >> 1) & 1);
         if (i > 0) mbar_wait(bar_o_free, (i - 1) & 1);  // the softmax warps have folded O(i-1) into their registers
+        mbar_wait(bar_v_full + 8 * s, (i / NSTAGE) & 1);
         tc_fence_after();
         const uint32_t va = base + SMEM_V + s * TILE_BYTES;
         const uint32_t pa = tmem + ((i & 1) ? TM_P1 : TM_P0);
