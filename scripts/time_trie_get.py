@@ -40,7 +40,7 @@ seq = torch.zeros((1, 64), dtype=torch.int32, device=dev)
 seq[0, :2] = torch.tensor([3, 3], dtype=torch.int32, device=dev)
 n = torch.tensor([2], dtype=torch.int32, device=dev)
 us, nv, o = timed(seq, n)
-print('cluster', os.environ.get('PIA_TRIE_GET_CLUSTER', '8'), 'hot query: %.1f us, %d nodes visited, draft n %d, ids %s'
+print('prune', os.environ.get('PIA_TRIE_PRUNE', '1'), 'cluster', os.environ.get('PIA_TRIE_GET_CLUSTER', '8'), 'hot query: %.1f us, %d nodes visited, draft n %d, ids %s'
       % (us, nv, int(o['n'][0]), o['ids'][0, :8].tolist()))
 doc = docs[17]
 seq2 = torch.zeros((1, 64), dtype=torch.int32, device=dev)
