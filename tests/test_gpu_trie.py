@@ -53,6 +53,28 @@ def test_recorded_streams(name):
     assert cache.stats()['error_flags'] == 0
 
 
+def _assert_counts_bound_children(cache):
+    """the invariant the pruned query walk relies on (csrc/trie.cu tree_get; lookahead_cache.py:40-56, :302-310,
+    :326-333): after any sequence of put / stream_put / squeeze / reset, every node's fo and fi are >= those of each of
+    its children (a tree's root record carries no counts of its own and is exempt)"""
+    nodes, edges, root_of, _n, _o = cache.snapshot()
+    nch, child, cap, fo, fi = nodes['n_child'], nodes['child'], nodes['cap'], nodes['fo'], nodes['fi']
+    roots = set(int(r) for r in root_of[root_of >= 0])
+    stack = list(roots)
+    checked = 0
+    while stack:
+        i = stack.pop()
+        if nch[i] == 0:
+            continue
+        kids = [int(child[i])] if cap[i] == 0 else edges[child[i]:child[i] + nch[i], 1].tolist()
+        for c in kids:
+            if i not in roots:
+                assert fo[c] <= fo[i] and fi[c] <= fi[i], (i, c, fo[i], fo[c], fi[i], fi[c])
+                checked += 1
+            stack.append(c)
+    assert checked > 0
+
+
 def _random_stream(seed, V, n_req, stop=(), dl=64, bl=8, zipf=False):
     """yields op tuples; the same generator drives oracle and GPU"""
     rng = np.random.default_rng(seed)
@@ -107,6 +129,7 @@ def test_differential_vs_oracle(seed, V, n_req, zipf):
     assert checked > 50
     s = gpu.stats()
     assert s['error_flags'] == 0 and s['n_trees'] == cpu.n_trees()
+    _assert_counts_bound_children(gpu)
 
 
 def test_batched_get_matches_single():
