@@ -15,8 +15,11 @@
 // as (1-w)*fi + w*fo with two rounded multiplies and one rounded add (__dmul_rn/__dadd_rn, no FMA).
 //
 // Kernels: k_put_prepare / k_put_insert / k_put_finish (put, stream_put :349-406),
-//          k_get (hier_get / one_get -> Tree.get :65-144, 224-293, 171-222),
+//          k_get (hier_get / one_get -> Tree.get :65-144, 224-293, 171-222): warp match, level-synchronous frequency
+//                walk (pruned by the parent >= child count bound; full, as an 8-CTA cluster per row, when that bound is
+//                not known to hold), k-th largest from exact shared-memory histograms, DFS emit with ranked frames,
 //          k_reset_input (:320-333, 566-570), k_squeeze (:295-318, 572-576), k_fresh (:563-564).
+// Host:    pia_trie_compact (storage reclamation between requests), export / import (save_mem / load_mem).
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
